@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py — LZ4 unpack + XXH3-64 verify throughput (BASELINE.json metric) on N B200s.
+
+A "step" is one pass of the hot path (zpb_unpack_device: descriptor upload, one kernel, status /
+digest download) over one synthetic archive.  See DESIGN.md §Measurement for the definitions of
+value / e2e / roofline / cpu_baseline.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "lz4_unpack_xxh3_verify_uncompressed_GBps"
+ENTRY_SIZE = 131072
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------ archive preparation (untimed)
+def _pack_shard(args):
+    """Worker: generate entries [lo,hi) and pack them with the CPU checker's LZ4 frame writer.
+    (Archive preparation only — the reference-format writer, never part of a timed region.)"""
+    lo, hi, size, independent = args
+    from zpack_b200 import corpus
+    from oracle import oracle as O
+    frames, hashes = [], np.empty(hi - lo, np.uint64)
+    for k, i in enumerate(range(lo, hi)):
+        b = corpus.entry_bytes(i, size)
+        frames.append(O.lz4f_encode_port(b, 0, independent))
+        hashes[k] = O.xxh3_port(b)
+    return lo, frames, hashes
+
+
+def build_archive(n_entries, size, first=0, independent=False, workers=None):
+    """zpk-synth-v1 corpus -> ZPack archive with reference-format LZ4 frames (linked 64 KB blocks =
+    what zpack_write_files emits; byte-identical to the reference's frames, tests/test_oracle.py)."""
+    import multiprocessing as mp
+    from zpack_b200 import container, corpus
+    workers = workers or min(os.cpu_count() or 1, 64)
+    step = max(1, min(256, n_entries // (workers * 4) or 1))
+    jobs = [(first + a, first + min(a + step, n_entries), size, independent) for a in range(0, n_entries, step)]
+    frames, hashes = [None] * len(jobs), [None] * len(jobs)
+    if workers > 1 and len(jobs) > 1:
+        with mp.get_context("fork").Pool(workers) as pool:
+            for j, (lo, fr, hs) in enumerate(pool.imap(_pack_shard, jobs, chunksize=1)):
+                frames[j], hashes[j] = fr, hs
+    else:
+        for j, job in enumerate(jobs):
+            _, frames[j], hashes[j] = _pack_shard(job)
+    payload = [f for fr in frames for f in fr]
+    names = [corpus.entry_name(first + i) for i in range(n_entries)]
+    arch = container.assemble(names, payload, [size] * n_entries, np.concatenate(hashes), [2] * n_entries)
+    return arch
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ reference arm (CPU)
+def cpu_unpack_throughput(arch, d, n_sample, threads, repeat=1):
+    """The reference's own zpack_read_file (oracle/_ref) — or the port when _ref is absent — over
+    `n_sample` entries split across `threads` host threads, one dctx each (lib/zpack.h:335-341).
+    The per-entry loop runs in C (oracle/ref_driver.c); Python only starts the threads."""
+    import ctypes as C
+    from oracle import oracle as O
+    n_sample = min(n_sample, len(d))
+    threads = max(1, min(threads, n_sample))
+    use_ref = O.have_ref() and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_driver.so"))
+    size = int(d.uncomp_size[:n_sample].max())
+    outs = [np.empty(size, np.uint8) for _ in range(threads)]
+    bad = [0] * threads
+    if use_ref:
+        rd = O.RefReader(arch)
+        drv = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_driver.so"))
+        drv.ref_unpack_range.restype = C.c_long
+        drv.ref_unpack_range.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p,
+                                         C.c_size_t, C.c_int, C.c_void_p]
+        ents = C.cast(rd.r.file_entries, C.c_void_p)
+
+        def work(t):
+            bad[t] = drv.ref_unpack_range(C.byref(rd.r), ents, t, n_sample, threads, outs[t].ctypes.data, size, 2, None)
+    else:
+        lib = O.port()
+        lib.orc_unpack_range.restype = C.c_long
+        lib.orc_unpack_range.argtypes = [C.c_void_p] * 6 + [C.c_size_t] * 3 + [C.c_void_p, C.c_size_t, C.c_void_p]
+        cols = [np.ascontiguousarray(x) for x in (d.offset, d.comp_size, d.uncomp_size, d.hash, d.method)]
+
+        def work(t):
+            bad[t] = lib.orc_unpack_range(arch.ctypes.data, *[c.ctypes.data for c in cols], t, n_sample, threads,
+                                          outs[t].ctypes.data, size, None)
+    best = None
+    for _ in range(repeat):
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        t0 = time.perf_counter()
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    if use_ref:
+        rd.close()
+    assert sum(bad) == 0, f"CPU baseline: {sum(bad)} entries failed to verify"
+    nbytes = float(d.uncomp_size[:n_sample].sum())
+    return nbytes / best / 1e9, best, ("reference" if use_ref else "port")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from zpack_b200 import container
+    cores = os.cpu_count() or 1
+    n_sample = args.ref_entries
+    arch = build_archive(n_sample, ENTRY_SIZE, independent=False)
+    d = container.parse(arch)
+    for _ in range(args.warmup):
+        cpu_unpack_throughput(arch, d, min(n_sample, 512), cores)
+    t_best, vals = None, []
+    for _ in range(args.steps):
+        v, dt, kind = cpu_unpack_throughput(arch, d, n_sample, cores)
+        vals.append(v)
+        t_best = dt if t_best is None else min(t_best, dt)
+    value = float(np.mean(vals))
+    line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * float(d.uncomp_size.sum()) / (value * 1e9),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "impl": "reference",
+            "config": {"workload": f"C2 sample: LZ4 unpack + XXH3 verify of {n_sample} x 128 KiB entries "
+                                   "(zpk-synth-v1), reference zpack_read_file on host cores"},
+            "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": kind,
+                             "sample": f"{n_sample} entries x 128 KiB per step, {cores} threads, one dctx each"},
+            "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import zpack_b200
+    from zpack_b200 import container
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n_per_gpu = args.entries  # weak scaling: every GPU unpacks its own shard of `entries` entries
+    t_prep = time.time()
+    arch = build_archive(n_per_gpu, ENTRY_SIZE, first=rank * n_per_gpu, independent=args.independent,
+                         workers=max(1, (os.cpu_count() or 1) // world))
+    d = container.parse(arch)
+    entries = d.entries()
+    out_size = int(entries["dst_off"][-1] + entries["dst_cap"][-1])
+    comp_bytes, uncomp_bytes = int(d.comp_size.sum()), int(d.uncomp_size.sum())
+    prep_s = time.time() - t_prep
+
+    ctx = zpack_b200.Context(local)
+    if args.group:
+        ctx.set_tuning(group_lanes=args.group)
+    h_arch = torch.from_numpy(arch).pin_memory()
+    d_arch = h_arch.cuda(non_blocking=False)
+    d_out = torch.empty(out_size, dtype=torch.uint8, device="cuda")
+    h_out = torch.empty(out_size, dtype=torch.uint8).pin_memory() if args.e2e else None
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device():
+        status, digest = ctx.unpack_device(d_arch, len(arch), d_out, out_size, entries, stream)
+        return status, digest
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        status, digest = step_device()
+    assert (status == 0).all() and np.array_equal(digest, d.hash), "parity gate failed before timing"
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    kernel_ms = []
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        status, digest = step_device()
+        kernel_ms.append(ctx.last_kernel_ms()["unpack_ms"])
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0
+    assert (status == 0).all() and np.array_equal(digest, d.hash)
+
+    # end-to-end through the host-buffer C-ABI call (pinned host archive -> H2D -> kernel -> D2H output)
+    e2e = None
+    if args.e2e:
+        h_arch_np, h_out_np = h_arch.numpy(), h_out.numpy()
+        ctx.unpack_host(h_arch_np, len(arch), h_out_np, out_size, entries)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            st2, dg2 = ctx.unpack_host(h_arch_np, len(arch), h_out_np, out_size, entries)
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+        assert (st2 == 0).all()
+        e2e = e2e_s
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([ms_total, float(np.mean(kernel_ms)), e2e or 0.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, kern_ms, e2e_s = [float(x) for x in t.cpu()]
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        ms_step = ms_total / args.steps
+        value = world * uncomp_bytes / (ms_step * 1e-3) / 1e9
+        algo_bytes = comp_bytes + uncomp_bytes
+        achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+        cores = os.cpu_count() or 1
+        line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": f"C2: LZ4 unpack + XXH3-64 verify, {n_per_gpu} entries x 128 KiB per GPU "
+                                       f"({uncomp_bytes / 2**30:.2f} GiB uncompressed, ratio {uncomp_bytes / comp_bytes:.3f}), "
+                                       f"zpk-synth-v1, {'independent' if args.independent else 'reference-format linked'} 64 KB blocks",
+                           "entries_per_gpu": n_per_gpu, "entry_bytes": ENTRY_SIZE, "sharding": f"entries x{world}, no collective",
+                           "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)",
+                           "group_lanes": args.group or int(os.environ.get("ZPB_GROUP", "8")), "archive_prep_s": round(prep_s, 1)},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "kernel": "unpack_kernel", "kernel_ms": kern_ms,
+                             "algorithmic_bytes_per_launch": algo_bytes},
+                "gpu_launches": int(launches), "clocks": clocks}
+        if args.e2e:
+            line["e2e"] = {"value": world * uncomp_bytes / e2e_s / 1e9, "unit": "GB/s",
+                           "h2d_bytes_per_step": comp_bytes + entries.nbytes, "d2h_bytes_per_step": uncomp_bytes + 12 * len(entries)}
+        if not args.no_cpu:
+            n_s = min(args.cpu_entries, len(d))
+            v, dt, kind = cpu_unpack_throughput(arch, d, n_s, cores)
+            v1, dt1, _ = cpu_unpack_throughput(arch, d, min(n_s, 2048), 1)
+            line["cpu_baseline"] = {"value": v, "unit": "GB/s", "cores": cores, "kind": kind,
+                                    "sample": f"first {n_s} entries of the same archive, {cores} threads; "
+                                              f"single-thread: {v1:.3f} GB/s"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--entries", type=int, default=65536, help="entries per GPU (C2: 65536 x 128 KiB = 8 GiB)")
+    ap.add_argument("--independent", action="store_true", help="archive with B.Indep=1 frames (what the GPU packer writes)")
+    ap.add_argument("--group", type=int, default=0)
+    ap.add_argument("--no-e2e", dest="e2e", action="store_false")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-entries", type=int, default=32768)
+    ap.add_argument("--ref-entries", type=int, default=16384)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

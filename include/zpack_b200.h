@@ -1,0 +1,136 @@
+/* include/zpack_b200.h — the thin C-ABI between ZPack's host library and the sm_100a kernels.
+ *
+ * Plain C: pointers and sizes only, no torch / C++ types.  This is the layer that the
+ * per-entry loops of the reference host library are rerouted through:
+ *
+ *   zpack_read_file        (/root/reference/lib/zpack_read.c:326-471)   -> zpb_unpack_host  (batch of 1)
+ *   zpack_read_file_stream (/root/reference/lib/zpack_read.c:515-640)   -> zpb_unpack_host  (+ host doling)
+ *   zpack_write_files      (/root/reference/lib/zpack_write.c:280-343)  -> zpb_pack_host
+ *   zpack_compress_file    (/root/reference/lib/zpack_write.c:161-224)  -> zpb_pack_host    (per entry)
+ *   XXH3_64bits call sites (zpack_read.c:466, zpack_write.c:256, zpack_stream.c) -> zpb_xxh3_*
+ *
+ * The *_device variants are the same operations with the archive / corpus already resident in
+ * HBM (the configuration BASELINE.json's metric is quoted on).  Every function returns 0
+ * (ZPB_OK) or a negative ZPB_E_* library error; per-entry outcomes are reported in `status[]`
+ * using the reference's `enum zpack_result` numbering (lib/zpack.h:189-218).
+ *
+ * There is no CPU fallback: without a CUDA device zpb_create() fails and nothing else works.
+ */
+#ifndef ZPACK_B200_H
+#define ZPACK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZPB_ABI_VERSION 1
+
+/* library-level return codes */
+#define ZPB_OK              0
+#define ZPB_E_NO_DEVICE    -1   /* no CUDA device / driver                   */
+#define ZPB_E_CUDA         -2   /* a CUDA call failed; see zpb_last_error()  */
+#define ZPB_E_ARG          -3   /* bad argument (NULL, misaligned, overflow) */
+#define ZPB_E_NOMEM        -4   /* device or pinned allocation failed        */
+
+/* compression methods — values of zpack_compression_method (lib/zpack.h:60-66) */
+#define ZPB_METHOD_NONE 0
+#define ZPB_METHOD_ZSTD 1
+#define ZPB_METHOD_LZ4  2
+
+/* per-entry status: the subset of enum zpack_result the hot path can produce */
+#define ZPB_ST_OK                  0
+#define ZPB_ST_BUFFER_TOO_SMALL   12
+#define ZPB_ST_DECOMPRESS_FAILED  13
+#define ZPB_ST_COMPRESS_FAILED    14
+#define ZPB_ST_HASH_MISMATCH      15
+#define ZPB_ST_OFFSET_INVALID     16
+#define ZPB_ST_FILE_INCOMPLETE    17
+#define ZPB_ST_FILE_SIZE_INVALID  18
+#define ZPB_ST_METHOD_INVALID     19
+#define ZPB_ST_NOT_AVAILABLE      24
+
+/* One archive entry to unpack: the hot-path view of zpack_file_entry (lib/zpack.h:71-80)
+ * plus where its output goes.  64 bytes, uploaded to the device as-is. */
+typedef struct zpb_entry {
+    uint64_t src_off;      /* entry.offset: byte offset of the compressed bytes in the archive */
+    uint64_t comp_size;    /* entry.comp_size                                                  */
+    uint64_t dst_off;      /* where to put the output inside the output buffer (16 B aligned)  */
+    uint64_t dst_cap;      /* max_size of zpack_read_file (>= uncomp_size or BUFFER_TOO_SMALL)  */
+    uint64_t uncomp_size;  /* entry.uncomp_size: the digest covers dst[0 .. uncomp_size)       */
+    uint64_t hash;         /* entry.hash: expected XXH3-64                                     */
+    uint32_t method;       /* entry.comp_method                                                */
+    uint32_t flags;        /* ZPB_F_*                                                          */
+    uint64_t reserved;
+} zpb_entry;
+
+#define ZPB_F_NO_VERIFY 1u  /* compute the digest but do not compare it (raw / hash-only use) */
+
+/* One file to pack: the hot-path view of zpack_file (lib/zpack.h:125-134). */
+typedef struct zpb_file {
+    uint64_t src_off;      /* offset of the file's bytes inside the input buffer (16 B aligned) */
+    uint64_t size;         /* zpack_file.size                                                   */
+    uint64_t dst_off;      /* offset of this file's output slot in the output buffer            */
+    uint64_t dst_cap;      /* slot capacity, >= zpb_pack_bound(method, size)                    */
+    uint32_t method;       /* options->method                                                   */
+    int32_t  level;        /* options->level (LZ4: < 3 = fast path, negative = acceleration)    */
+    uint64_t reserved[3];
+} zpb_file;
+
+typedef struct zpb_ctx zpb_ctx;
+
+/* lifecycle ------------------------------------------------------------------------------- */
+int         zpb_abi_version(void);
+zpb_ctx    *zpb_create(int device);              /* NULL on failure; zpb_last_error(NULL) says why */
+void        zpb_destroy(zpb_ctx *ctx);
+const char *zpb_last_error(const zpb_ctx *ctx);  /* never NULL */
+int         zpb_device_info(const zpb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor);
+/* counts every kernel this library has launched on this context (bench "gpu_launches") */
+uint64_t    zpb_launch_count(const zpb_ctx *ctx);
+
+/* unpack + verify ------------------------------------------------------------------------- */
+/* Device-resident batch.  d_archive/d_out are device pointers; entries/status/digest are HOST
+ * arrays of n elements (descriptor upload and result download are part of the call).
+ * `stream` is a cudaStream_t (NULL = the context's own stream).  Synchronous on return. */
+int zpb_unpack_device(zpb_ctx *ctx, const uint8_t *d_archive, uint64_t archive_size,
+                      uint8_t *d_out, uint64_t out_size, const zpb_entry *entries, uint64_t n,
+                      int32_t *status, uint64_t *digest, void *stream);
+
+/* Same with host buffers: copies [lo,hi) of the archive that the entries touch to the device,
+ * unpacks, copies each entry's uncomp_size bytes back into h_out + dst_off. */
+int zpb_unpack_host(zpb_ctx *ctx, const uint8_t *h_archive, uint64_t archive_size,
+                    uint8_t *h_out, uint64_t out_size, const zpb_entry *entries, uint64_t n,
+                    int32_t *status, uint64_t *digest);
+
+/* XXH3-64 (seed 0) of n independent ranges ------------------------------------------------- */
+int zpb_xxh3_device(zpb_ctx *ctx, const uint8_t *d_data, const uint64_t *offsets,
+                    const uint64_t *lengths, uint64_t n, uint64_t *digest, void *stream);
+int zpb_xxh3_host(zpb_ctx *ctx, const uint8_t *h_data, uint64_t length, uint64_t *digest);
+
+/* pack ------------------------------------------------------------------------------------ */
+/* worst-case output bytes for one file (LZ4: frame header + per-block headers + EndMark) */
+uint64_t zpb_pack_bound(uint32_t method, uint64_t size);
+
+/* Compress n files that are resident in HBM into their slots; returns per-file compressed
+ * size, XXH3-64 of the input and status.  The compressed-size prefix sum / entry.offset
+ * assignment is the caller's (host) job, as in zpack_write_files. */
+int zpb_pack_device(zpb_ctx *ctx, const uint8_t *d_in, uint64_t in_size, uint8_t *d_out,
+                    uint64_t out_size, const zpb_file *files, uint64_t n, uint64_t *comp_size,
+                    uint64_t *digest, int32_t *status, void *stream);
+int zpb_pack_host(zpb_ctx *ctx, const uint8_t *h_in, uint64_t in_size, uint8_t *h_out,
+                  uint64_t out_size, const zpb_file *files, uint64_t n, uint64_t *comp_size,
+                  uint64_t *digest, int32_t *status);
+
+/* last kernel timing (CUDA events on the launching stream), for bench.py's roofline block */
+int zpb_last_kernel_ms(const zpb_ctx *ctx, float *unpack_ms, float *pack_ms);
+
+/* tuning knobs: lanes per dependency chain (4, 8, 16, 32; 0 = keep) and resident CTAs per SM
+ * (0 = occupancy API, -1 = keep).  Defaults can also come from ZPB_GROUP / ZPB_CTAS_PER_SM. */
+int zpb_set_tuning(zpb_ctx *ctx, int group_lanes, int ctas_per_sm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZPACK_B200_H */

@@ -1,0 +1,349 @@
+// zpb_api.cu — host side of the C-ABI in include/zpack_b200.h: context, scratch arenas,
+// work ordering, launches and CUDA-event timing.  No torch, no CPU codec: every entry is
+// (de)compressed and hashed on the device or the call fails.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/zpack_b200.h"
+#include "unpack_kernel.cuh"
+#include "pack_kernel.cuh"
+
+static thread_local std::string g_last_error = "";
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t n) {
+        if (n <= cap) return true;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(n, (size_t)4096);
+        if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; return false; }
+        cap = want;
+        return true;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t n) {
+        if (n <= cap) return true;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(n, (size_t)4096);
+        if (cudaMallocHost(&p, want) != cudaSuccess) { p = nullptr; return false; }
+        cap = want;
+        return true;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct zpb_ctx {
+    int device = 0;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    float unpack_ms = 0.f, pack_ms = 0.f;
+    int group = 8;        // lanes per chain (tunable: ZPB_GROUP)
+    int ctas_per_sm = 0;  // 0 = occupancy API
+    // descriptor / result scratch
+    DevBuf d_desc, d_order, d_res, d_counter;
+    PinBuf h_stage;
+    // staging arenas for the *_host entry points
+    DevBuf d_in, d_out;
+};
+
+#define CK(ctx, call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);               \
+            g_last_error = (ctx)->err;                                                     \
+            return ZPB_E_CUDA;                                                             \
+        }                                                                                  \
+    } while (0)
+
+static int fail(zpb_ctx *ctx, int code, const char *msg) {
+    if (ctx) ctx->err = msg;
+    g_last_error = msg;
+    return code;
+}
+
+extern "C" int zpb_abi_version(void) { return ZPB_ABI_VERSION; }
+
+extern "C" const char *zpb_last_error(const zpb_ctx *ctx) {
+    return ctx ? ctx->err.c_str() : g_last_error.c_str();
+}
+
+extern "C" zpb_ctx *zpb_create(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_last_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        return nullptr;
+    }
+    if (device < 0 || device >= count) { g_last_error = "device index out of range"; return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { g_last_error = "cudaSetDevice failed"; return nullptr; }
+    zpb_ctx *ctx = new zpb_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        g_last_error = "cudaGetDeviceProperties failed"; delete ctx; return nullptr;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        xxh3_upload_tables() != cudaSuccess) {
+        g_last_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
+        delete ctx; return nullptr;
+    }
+    if (const char *s = getenv("ZPB_GROUP")) {
+        int v = atoi(s);
+        if (v == 4 || v == 8 || v == 16 || v == 32) ctx->group = v;
+    }
+    if (const char *s = getenv("ZPB_CTAS_PER_SM")) ctx->ctas_per_sm = atoi(s);
+    return ctx;
+}
+
+extern "C" void zpb_destroy(zpb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ctx->d_desc.release(); ctx->d_order.release(); ctx->d_res.release(); ctx->d_counter.release();
+    ctx->d_in.release(); ctx->d_out.release(); ctx->h_stage.release();
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int zpb_device_info(const zpb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor) {
+    if (!ctx) return ZPB_E_ARG;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    return ZPB_OK;
+}
+
+extern "C" uint64_t zpb_launch_count(const zpb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int zpb_set_tuning(zpb_ctx *ctx, int group_lanes, int ctas_per_sm) {
+    if (!ctx) return ZPB_E_ARG;
+    if (group_lanes) {
+        if (group_lanes != 4 && group_lanes != 8 && group_lanes != 16 && group_lanes != 32)
+            return fail(ctx, ZPB_E_ARG, "group_lanes must be 4, 8, 16 or 32");
+        ctx->group = group_lanes;
+    }
+    if (ctas_per_sm >= 0) ctx->ctas_per_sm = ctas_per_sm;
+    return ZPB_OK;
+}
+
+extern "C" int zpb_last_kernel_ms(const zpb_ctx *ctx, float *unpack_ms, float *pack_ms) {
+    if (!ctx) return ZPB_E_ARG;
+    if (unpack_ms) *unpack_ms = ctx->unpack_ms;
+    if (pack_ms) *pack_ms = ctx->pack_ms;
+    return ZPB_OK;
+}
+
+// ------------------------------------------------------------------------------------ unpack
+template <int G>
+static cudaError_t launch_unpack(zpb_ctx *ctx, cudaStream_t s, const u8 *arch, u64 asz, u8 *out,
+                                 const zpb_entry *d_e, const u32 *d_order, u32 n, u32 *d_counter,
+                                 int *d_status, u64 *d_digest) {
+    int per_sm = ctx->ctas_per_sm;
+    if (per_sm <= 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, unpack_kernel<G>, 256, 0);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+    }
+    u64 groups_per_cta = 256 / G;
+    u64 want = (n + groups_per_cta - 1) / groups_per_cta;
+    u32 grid = (u32)std::min<u64>((u64)ctx->sm_count * per_sm, std::max<u64>(want, 1));
+    unpack_kernel<G><<<grid, 256, 0, s>>>(arch, asz, out, d_e, d_order, n, d_counter, d_status,
+                                          d_digest, nullptr);
+    return cudaGetLastError();
+}
+
+// Expensive entries first: compressed LZ4/zstd bytes are a good proxy for sequence count;
+// stored-ish entries (ratio ~1) and raw copies are cheap per byte, so they go last.
+static void build_order(const zpb_entry *e, u64 n, u32 *order) {
+    std::iota(order, order + n, 0u);
+    auto cost = [&](u32 i) -> u64 {
+        const zpb_entry &x = e[i];
+        if (x.method == ZPB_METHOD_NONE) return x.comp_size / 16;
+        if (x.comp_size >= x.uncomp_size) return x.comp_size / 16;
+        return x.comp_size;
+    };
+    std::stable_sort(order, order + n, [&](u32 a, u32 b) { return cost(a) > cost(b); });
+}
+
+static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_size, u8 *d_out,
+                              u64 out_size, const zpb_entry *entries, u64 n, int32_t *status,
+                              u64 *digest, cudaStream_t s) {
+    if (n == 0) return ZPB_OK;
+    if (n > 0x7fffffffull) return fail(ctx, ZPB_E_ARG, "too many entries in one batch");
+    for (u64 i = 0; i < n; ++i) {
+        const zpb_entry &e = entries[i];
+        if (e.comp_size == 0) continue;
+        if (e.dst_off > out_size || e.dst_cap > out_size - e.dst_off)
+            return fail(ctx, ZPB_E_ARG, "entry output slot exceeds the output buffer");
+    }
+    size_t desc_b = n * sizeof(zpb_entry), ord_b = n * sizeof(u32);
+    size_t res_b = n * (sizeof(int) + sizeof(u64));
+    if (!ctx->d_desc.ensure(desc_b) || !ctx->d_order.ensure(ord_b) || !ctx->d_res.ensure(res_b + 64) ||
+        !ctx->d_counter.ensure(256) || !ctx->h_stage.ensure(desc_b + ord_b + res_b + 64))
+        return fail(ctx, ZPB_E_NOMEM, "scratch allocation failed");
+
+    u8 *hs = (u8 *)ctx->h_stage.p;
+    zpb_entry *h_desc = (zpb_entry *)hs;
+    u32 *h_order = (u32 *)(hs + desc_b);
+    memcpy(h_desc, entries, desc_b);
+    build_order(entries, n, h_order);
+    u64 *d_digest = (u64 *)ctx->d_res.p;
+    int *d_status = (int *)((u8 *)ctx->d_res.p + n * sizeof(u64));
+
+    CK(ctx, cudaMemcpyAsync(ctx->d_desc.p, h_desc, desc_b, cudaMemcpyHostToDevice, s));
+    CK(ctx, cudaMemcpyAsync(ctx->d_order.p, h_order, ord_b, cudaMemcpyHostToDevice, s));
+    CK(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, 256, s));
+    CK(ctx, cudaEventRecord(ctx->ev0, s));
+    cudaError_t le;
+    switch (ctx->group) {
+    case 4:  le = launch_unpack<4>(ctx, s, d_archive, archive_size, d_out, (zpb_entry *)ctx->d_desc.p, (u32 *)ctx->d_order.p, (u32)n, (u32 *)ctx->d_counter.p, d_status, d_digest); break;
+    case 16: le = launch_unpack<16>(ctx, s, d_archive, archive_size, d_out, (zpb_entry *)ctx->d_desc.p, (u32 *)ctx->d_order.p, (u32)n, (u32 *)ctx->d_counter.p, d_status, d_digest); break;
+    case 32: le = launch_unpack<32>(ctx, s, d_archive, archive_size, d_out, (zpb_entry *)ctx->d_desc.p, (u32 *)ctx->d_order.p, (u32)n, (u32 *)ctx->d_counter.p, d_status, d_digest); break;
+    default: le = launch_unpack<8>(ctx, s, d_archive, archive_size, d_out, (zpb_entry *)ctx->d_desc.p, (u32 *)ctx->d_order.p, (u32)n, (u32 *)ctx->d_counter.p, d_status, d_digest); break;
+    }
+    CK(ctx, le);
+    ctx->launches += 1;
+    CK(ctx, cudaEventRecord(ctx->ev1, s));
+    u8 *h_res = hs + desc_b + ord_b;
+    CK(ctx, cudaMemcpyAsync(h_res, ctx->d_res.p, res_b, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaStreamSynchronize(s));
+    CK(ctx, cudaEventElapsedTime(&ctx->unpack_ms, ctx->ev0, ctx->ev1));
+    if (digest) memcpy(digest, h_res, n * sizeof(u64));
+    if (status) memcpy(status, h_res + n * sizeof(u64), n * sizeof(int));
+    return ZPB_OK;
+}
+
+extern "C" int zpb_unpack_device(zpb_ctx *ctx, const uint8_t *d_archive, uint64_t archive_size,
+                                 uint8_t *d_out, uint64_t out_size, const zpb_entry *entries,
+                                 uint64_t n, int32_t *status, uint64_t *digest, void *stream) {
+    if (!ctx || (!entries && n) || (!d_archive && archive_size) || (!d_out && out_size))
+        return fail(ctx, ZPB_E_ARG, "null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    return unpack_device_impl(ctx, d_archive, archive_size, d_out, out_size, entries, n, status, digest, s);
+}
+
+extern "C" int zpb_unpack_host(zpb_ctx *ctx, const uint8_t *h_archive, uint64_t archive_size,
+                               uint8_t *h_out, uint64_t out_size, const zpb_entry *entries,
+                               uint64_t n, int32_t *status, uint64_t *digest) {
+    if (!ctx || (!entries && n) || (!h_archive && archive_size) || (!h_out && out_size))
+        return fail(ctx, ZPB_E_ARG, "null argument");
+    if (n == 0) return ZPB_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    // the byte range of the archive the batch touches, and of the output it owns
+    u64 lo = ~0ull, hi = 0, olo = ~0ull, ohi = 0;
+    for (u64 i = 0; i < n; ++i) {
+        const zpb_entry &e = entries[i];
+        if (e.comp_size == 0) continue;
+        if (e.src_off > archive_size || e.comp_size > archive_size - e.src_off) continue;  // flagged on device
+        if (e.dst_off > out_size || e.dst_cap > out_size - e.dst_off)
+            return fail(ctx, ZPB_E_ARG, "entry output slot exceeds the output buffer");
+        lo = std::min(lo, e.src_off); hi = std::max(hi, e.src_off + e.comp_size);
+        olo = std::min(olo, e.dst_off); ohi = std::max(ohi, e.dst_off + e.dst_cap);
+    }
+    if (hi <= lo) { lo = hi = 0; }
+    if (ohi <= olo) { olo = ohi = 0; }
+    lo &= ~15ull; olo &= ~15ull;  // keep device layout congruent to the host layout mod 16
+    if (!ctx->d_in.ensure(hi - lo + 64) || !ctx->d_out.ensure(ohi - olo + 64))
+        return fail(ctx, ZPB_E_NOMEM, "device staging allocation failed");
+    std::vector<zpb_entry> rel(entries, entries + n);
+    for (auto &e : rel) {
+        if (e.comp_size == 0) continue;
+        if (e.src_off > archive_size || e.comp_size > archive_size - e.src_off) {
+            e.src_off = ~0ull;  // stays invalid after rebasing
+            continue;
+        }
+        e.src_off -= lo;
+        e.dst_off -= olo;
+    }
+    if (hi > lo) CK(ctx, cudaMemcpyAsync(ctx->d_in.p, h_archive + lo, hi - lo, cudaMemcpyHostToDevice, s));
+    int rc = unpack_device_impl(ctx, (const u8 *)ctx->d_in.p, hi - lo, (u8 *)ctx->d_out.p, ohi - olo,
+                                rel.data(), n, status, digest, s);
+    if (rc != ZPB_OK) return rc;
+    // copy back maximal runs of adjacent output slots (a slot's whole dst_cap belongs to its entry)
+    std::vector<u32> by_dst;
+    by_dst.reserve(n);
+    for (u64 i = 0; i < n; ++i)
+        if (entries[i].comp_size && rel[i].src_off != ~0ull && entries[i].dst_cap >= entries[i].uncomp_size)
+            by_dst.push_back((u32)i);
+    std::sort(by_dst.begin(), by_dst.end(), [&](u32 a, u32 b) { return entries[a].dst_off < entries[b].dst_off; });
+    size_t k = 0;
+    while (k < by_dst.size()) {
+        u64 start = entries[by_dst[k]].dst_off;
+        u64 end = start + entries[by_dst[k]].uncomp_size, own = start + entries[by_dst[k]].dst_cap;
+        size_t m = k + 1;
+        while (m < by_dst.size() && entries[by_dst[m]].dst_off <= own) {
+            end = std::max(end, entries[by_dst[m]].dst_off + entries[by_dst[m]].uncomp_size);
+            own = std::max(own, entries[by_dst[m]].dst_off + entries[by_dst[m]].dst_cap);
+            ++m;
+        }
+        if (end > start)
+            CK(ctx, cudaMemcpyAsync(h_out + start, (u8 *)ctx->d_out.p + (start - olo), end - start,
+                                    cudaMemcpyDeviceToHost, s));
+        k = m;
+    }
+    CK(ctx, cudaStreamSynchronize(s));
+    return ZPB_OK;
+}
+
+// ------------------------------------------------------------------------------------ xxh3
+extern "C" int zpb_xxh3_device(zpb_ctx *ctx, const uint8_t *d_data, const uint64_t *offsets,
+                               const uint64_t *lengths, uint64_t n, uint64_t *digest, void *stream) {
+    if (!ctx || !offsets || !lengths || !digest) return fail(ctx, ZPB_E_ARG, "null argument");
+    if (n == 0) return ZPB_OK;
+    if (n > 0x7fffffffull) return fail(ctx, ZPB_E_ARG, "too many ranges");
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    size_t b = n * sizeof(u64);
+    if (!ctx->d_desc.ensure(2 * b) || !ctx->d_res.ensure(b) || !ctx->d_counter.ensure(256) ||
+        !ctx->h_stage.ensure(3 * b))
+        return fail(ctx, ZPB_E_NOMEM, "scratch allocation failed");
+    u64 *h = (u64 *)ctx->h_stage.p;
+    memcpy(h, offsets, b);
+    memcpy(h + n, lengths, b);
+    CK(ctx, cudaMemcpyAsync(ctx->d_desc.p, h, 2 * b, cudaMemcpyHostToDevice, s));
+    CK(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, 256, s));
+    u32 grid = (u32)std::min<u64>((u64)ctx->sm_count * 8, (n + 7) / 8);
+    xxh3_kernel<32><<<grid, 256, 0, s>>>(d_data, (u64 *)ctx->d_desc.p, (u64 *)ctx->d_desc.p + n, (u32)n,
+                                         (u32 *)ctx->d_counter.p, (u64 *)ctx->d_res.p);
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    CK(ctx, cudaMemcpyAsync(h + 2 * n, ctx->d_res.p, b, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaStreamSynchronize(s));
+    memcpy(digest, h + 2 * n, b);
+    return ZPB_OK;
+}
+
+extern "C" int zpb_xxh3_host(zpb_ctx *ctx, const uint8_t *h_data, uint64_t length, uint64_t *digest) {
+    if (!ctx || (!h_data && length) || !digest) return fail(ctx, ZPB_E_ARG, "null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->d_in.ensure(length + 64)) return fail(ctx, ZPB_E_NOMEM, "device staging allocation failed");
+    if (length) CK(ctx, cudaMemcpyAsync(ctx->d_in.p, h_data, length, cudaMemcpyHostToDevice, ctx->stream));
+    u64 off = 0;
+    return zpb_xxh3_device(ctx, (const u8 *)ctx->d_in.p, &off, &length, 1, digest, ctx->stream);
+}
+
+// ------------------------------------------------------------------------------------ pack
+#include "pack_api.inl"

@@ -1,0 +1,200 @@
+"""ctypes binding of include/zpack_b200.h — the C-ABI the reference's host loops are rerouted to.
+
+Mirrors the argument meaning of the reference calls it stands in for
+(/root/reference/lib/zpack_read.c:326 zpack_read_file, lib/zpack_write.c:280 zpack_write_files).
+Fails loudly when the CUDA library has not been built or no GPU is present: there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzpack_b200.so")
+
+METHOD_NONE, METHOD_ZSTD, METHOD_LZ4 = 0, 1, 2
+F_NO_VERIFY = 1
+
+# enum zpack_result values the hot path can return (/root/reference/lib/zpack.h:189-218)
+ST_OK = 0
+ST_BUFFER_TOO_SMALL = 12
+ST_DECOMPRESS_FAILED = 13
+ST_COMPRESS_FAILED = 14
+ST_HASH_MISMATCH = 15
+ST_OFFSET_INVALID = 16
+ST_FILE_INCOMPLETE = 17
+ST_FILE_SIZE_INVALID = 18
+ST_METHOD_INVALID = 19
+ST_NOT_AVAILABLE = 24
+
+#: numpy dtype of `struct zpb_entry` (64 bytes)
+Entry = np.dtype(
+    [("src_off", "<u8"), ("comp_size", "<u8"), ("dst_off", "<u8"), ("dst_cap", "<u8"),
+     ("uncomp_size", "<u8"), ("hash", "<u8"), ("method", "<u4"), ("flags", "<u4"), ("reserved", "<u8")]
+)
+#: numpy dtype of `struct zpb_file` (64 bytes)
+File = np.dtype(
+    [("src_off", "<u8"), ("size", "<u8"), ("dst_off", "<u8"), ("dst_cap", "<u8"),
+     ("method", "<u4"), ("level", "<i4"), ("reserved", "<u8", (3,))]
+)
+assert Entry.itemsize == 64 and File.itemsize == 64
+
+EXPORTS = [
+    "zpb_abi_version", "zpb_create", "zpb_destroy", "zpb_last_error", "zpb_device_info",
+    "zpb_launch_count", "zpb_unpack_device", "zpb_unpack_host", "zpb_xxh3_device", "zpb_xxh3_host",
+    "zpb_pack_bound", "zpb_pack_device", "zpb_pack_host", "zpb_last_kernel_ms", "zpb_set_tuning",
+]
+
+
+class ZpbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    """dlopen the CUDA library; raises if it is missing (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise ZpbError(f"{path} not built — run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(path)
+    vp, u64, i32p, u64p = C.c_void_p, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)
+    lib.zpb_abi_version.restype = C.c_int
+    lib.zpb_create.restype = vp
+    lib.zpb_create.argtypes = [C.c_int]
+    lib.zpb_destroy.argtypes = [vp]
+    lib.zpb_last_error.restype = C.c_char_p
+    lib.zpb_last_error.argtypes = [vp]
+    lib.zpb_device_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.zpb_launch_count.restype = u64
+    lib.zpb_launch_count.argtypes = [vp]
+    lib.zpb_set_tuning.argtypes = [vp, C.c_int, C.c_int]
+    lib.zpb_unpack_device.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, vp, vp]
+    lib.zpb_unpack_host.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, vp]
+    lib.zpb_xxh3_device.argtypes = [vp, vp, vp, vp, u64, vp, vp]
+    lib.zpb_xxh3_host.argtypes = [vp, vp, u64, vp]
+    lib.zpb_pack_bound.restype = u64
+    lib.zpb_pack_bound.argtypes = [C.c_uint32, u64]
+    lib.zpb_pack_device.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, vp, vp, vp]
+    lib.zpb_pack_host.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, vp, vp]
+    lib.zpb_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    _lib = lib
+    return lib
+
+
+def _ptr(a) -> int:
+    """address of a numpy array / torch tensor / raw int pointer"""
+    if a is None:
+        return 0
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+class Context:
+    """One GPU context (`zpb_ctx`): scratch arenas, a stream, CUDA-event timers."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.h = self.lib.zpb_create(device)
+        if not self.h:
+            raise ZpbError("zpb_create failed: " + self.lib.zpb_last_error(None).decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.zpb_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise ZpbError(f"zpb error {rc}: {self.lib.zpb_last_error(self.h).decode()}")
+
+    def device_info(self):
+        sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.lib.zpb_device_info(self.h, C.byref(sm), C.byref(ma), C.byref(mi)))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value)}
+
+    def set_tuning(self, group_lanes: int = 0, ctas_per_sm: int = -1):
+        self._check(self.lib.zpb_set_tuning(self.h, group_lanes, ctas_per_sm))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.zpb_launch_count(self.h))
+
+    def last_kernel_ms(self):
+        a, b = C.c_float(), C.c_float()
+        self.lib.zpb_last_kernel_ms(self.h, C.byref(a), C.byref(b))
+        return {"unpack_ms": a.value, "pack_ms": b.value}
+
+    # ---- unpack + verify -------------------------------------------------------------------
+    def unpack_device(self, d_archive, archive_size: int, d_out, out_size: int, entries: np.ndarray,
+                      stream: int = 0):
+        """Archive and output resident in HBM (torch tensors or raw device pointers)."""
+        assert entries.dtype == Entry and entries.flags.c_contiguous
+        n = len(entries)
+        status = np.empty(n, np.int32)
+        digest = np.empty(n, np.uint64)
+        self._check(self.lib.zpb_unpack_device(self.h, _ptr(d_archive), archive_size, _ptr(d_out), out_size,
+                                               _ptr(entries), n, _ptr(status), _ptr(digest), stream))
+        return status, digest
+
+    def unpack_host(self, h_archive, archive_size: int, h_out, out_size: int, entries: np.ndarray):
+        """Host buffers in, host buffers out (H2D + kernels + D2H inside the call)."""
+        assert entries.dtype == Entry and entries.flags.c_contiguous
+        n = len(entries)
+        status = np.empty(n, np.int32)
+        digest = np.empty(n, np.uint64)
+        self._check(self.lib.zpb_unpack_host(self.h, _ptr(h_archive), archive_size, _ptr(h_out), out_size,
+                                             _ptr(entries), n, _ptr(status), _ptr(digest)))
+        return status, digest
+
+    # ---- digest ------------------------------------------------------------------------------
+    def xxh3_host(self, data) -> int:
+        buf = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else data
+        out = C.c_uint64()
+        self._check(self.lib.zpb_xxh3_host(self.h, _ptr(buf) if len(buf) else 0, len(buf), C.byref(out)))
+        return out.value
+
+    def xxh3_device(self, d_data, offsets: Sequence[int], lengths: Sequence[int], stream: int = 0):
+        off = np.ascontiguousarray(offsets, np.uint64)
+        ln = np.ascontiguousarray(lengths, np.uint64)
+        out = np.empty(len(off), np.uint64)
+        self._check(self.lib.zpb_xxh3_device(self.h, _ptr(d_data), _ptr(off), _ptr(ln), len(off), _ptr(out), stream))
+        return out
+
+    # ---- pack --------------------------------------------------------------------------------
+    def pack_bound(self, method: int, size: int) -> int:
+        return int(self.lib.zpb_pack_bound(method, size))
+
+    def pack_device(self, d_in, in_size: int, d_out, out_size: int, files: np.ndarray, stream: int = 0):
+        assert files.dtype == File and files.flags.c_contiguous
+        n = len(files)
+        comp = np.empty(n, np.uint64)
+        digest = np.empty(n, np.uint64)
+        status = np.empty(n, np.int32)
+        self._check(self.lib.zpb_pack_device(self.h, _ptr(d_in), in_size, _ptr(d_out), out_size, _ptr(files), n,
+                                             _ptr(comp), _ptr(digest), _ptr(status), stream))
+        return comp, digest, status
+
+    def pack_host(self, h_in, in_size: int, h_out, out_size: int, files: np.ndarray):
+        assert files.dtype == File and files.flags.c_contiguous
+        n = len(files)
+        comp = np.empty(n, np.uint64)
+        digest = np.empty(n, np.uint64)
+        status = np.empty(n, np.int32)
+        self._check(self.lib.zpb_pack_host(self.h, _ptr(h_in), in_size, _ptr(h_out), out_size, _ptr(files), n,
+                                           _ptr(comp), _ptr(digest), _ptr(status)))
+        return comp, digest, status
