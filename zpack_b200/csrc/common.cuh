@@ -57,7 +57,7 @@ template <int G>
 ZPB_DEVINL void group_copy(const Group<G> &g, u8 *dst, const u8 *src, u32 n) {
     if (n >= 16u * G + 32u) {
         u32 head = (u32)(-(intptr_t)dst) & 15u;
-        if (g.l < (int)head) dst[g.l] = src[g.l];
+        for (u32 i = g.l; i < head; i += G) dst[i] = src[i];
         dst += head; src += head; n -= head;
         u32 chunks = n >> 4;
         const u32 *s4 = reinterpret_cast<const u32 *>((uintptr_t)src & ~(uintptr_t)3);
