@@ -126,6 +126,12 @@ int zpb_pack_host(zpb_ctx *ctx, const uint8_t *h_in, uint64_t in_size, uint8_t *
 /* last kernel timing (CUDA events on the launching stream), for bench.py's roofline block */
 int zpb_last_kernel_ms(const zpb_ctx *ctx, float *unpack_ms, float *pack_ms);
 
+/* per-stage device time of the last unpack (ms): scan, parse, exec, general-fallback */
+int zpb_last_stage_ms(const zpb_ctx *ctx, float *ms4);
+/* 1 (default): LZ4 / stored entries go through the scan -> parse -> exec pipeline and only what it
+ * declines reaches the general decoder; 0: general decoder for everything (A/B and test use). */
+int zpb_set_fast_path(zpb_ctx *ctx, int enabled);
+
 /* tuning knobs: lanes per dependency chain (4, 8, 16, 32; 0 = keep) and resident CTAs per SM
  * (0 = occupancy API, -1 = keep).  Defaults can also come from ZPB_GROUP / ZPB_CTAS_PER_SM. */
 int zpb_set_tuning(zpb_ctx *ctx, int group_lanes, int ctas_per_sm);

@@ -13,6 +13,15 @@ pytestmark = pytest.mark.gpu
 GOLD_HASHES = [0x7874CBA47D02B07D, 0x15F25C0F24DD8E52]
 
 
+@pytest.fixture(autouse=True, params=["fast", "general"])
+def _decode_path(request, gpu_ctx):
+    """Every test runs twice: through the scan/parse/exec pipeline (default) and with every entry
+    forced through the general decoder."""
+    gpu_ctx.set_fast_path(request.param == "fast")
+    yield
+    gpu_ctx.set_fast_path(True)
+
+
 def _unpack_all(ctx, arch, d, cap_extra=0, host=True):
     caps = d.uncomp_size + np.uint64(cap_extra)
     e = d.entries(dst_cap=caps)

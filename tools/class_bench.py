@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""Developer microbenchmark: unpack+verify throughput per corpus class (random / text / runs /
+records) and per tuning, device-resident.  Not the contract bench (that is bench.py) — this is
+what tells which class bounds the kernel.  Prints one JSON line per (class, tuning)."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _pack(args):
+    cls, lo, hi, size, indep = args
+    from zpack_b200 import corpus
+    from oracle import oracle as O
+    fr, hs = [], np.empty(hi - lo, np.uint64)
+    for k, i in enumerate(range(lo, hi)):
+        b = corpus.entry_bytes(4 * i + cls if cls >= 0 else i, size)
+        fr.append(O.lz4f_encode_port(b, 0, indep))
+        hs[k] = O.xxh3_port(b)
+    return fr, hs
+
+
+def build(cls, n, size, indep):
+    import multiprocessing as mp
+    from zpack_b200 import container
+    w = min(os.cpu_count() or 1, 64)
+    step = max(1, n // (4 * w))
+    jobs = [(cls, a, min(a + step, n), size, indep) for a in range(0, n, step)]
+    with mp.get_context("fork").Pool(w) as pool:
+        res = pool.map(_pack, jobs, chunksize=1)
+    frames = [f for fr, _ in res for f in fr]
+    hashes = np.concatenate([h for _, h in res])
+    return container.assemble([f"{i}" for i in range(n)], frames, [size] * n, hashes, [2] * n)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--entries", type=int, default=4096)
+    ap.add_argument("--size", type=int, default=131072)
+    ap.add_argument("--groups", default="4,8,16,32")
+    ap.add_argument("--classes", default="0,1,2,3,-1")
+    ap.add_argument("--independent", action="store_true")
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--fast", type=int, default=1)
+    args = ap.parse_args()
+    import torch
+    import zpack_b200
+    from zpack_b200 import container
+    ctx = zpack_b200.Context(0)
+    ctx.set_fast_path(bool(args.fast))
+    names = {0: "random", 1: "text", 2: "runs", 3: "records", -1: "mixed"}
+    for cls in [int(c) for c in args.classes.split(",")]:
+        arch = build(cls, args.entries, args.size, args.independent)
+        d = container.parse(arch)
+        e = d.entries()
+        out_size = int(e["dst_off"][-1] + e["dst_cap"][-1])
+        d_arch = torch.from_numpy(arch).cuda()
+        d_out = torch.empty(out_size, dtype=torch.uint8, device="cuda")
+        comp, unc = int(d.comp_size.sum()), int(d.uncomp_size.sum())
+        for g in [int(x) for x in args.groups.split(",")]:
+            ctx.set_tuning(group_lanes=g)
+            ms = []
+            for r in range(args.reps + 2):
+                st, dg = ctx.unpack_device(d_arch, len(arch), d_out, out_size, e)
+                if r >= 2:
+                    ms.append(ctx.last_kernel_ms()["unpack_ms"])
+            assert (st == 0).all() and np.array_equal(dg, d.hash)
+            t = float(np.median(ms))
+            print(json.dumps({"class": names[cls], "group": g, "kernel_ms": round(t, 4),
+                              "uncomp_GBps": round(unc / t / 1e6, 1), "traffic_GBps": round((comp + unc) / t / 1e6, 1),
+                              "ratio": round(unc / comp, 3), "entries": args.entries,
+                              "stages": {k: round(v, 4) for k, v in ctx.last_stage_ms().items()}}), flush=True)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

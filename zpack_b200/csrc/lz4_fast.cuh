@@ -1,0 +1,750 @@
+// lz4_fast.cuh — the throughput path for LZ4 entries: scan -> parse -> execute (kernels K0/K1/K2).
+//
+// Same contract as the LZ4 arm of zpack_read_file (/root/reference/lib/zpack_read.c:396-468:
+// LZ4F_decompress loop, then XXH3_64bits over uncomp_size bytes), split so that the one
+// inherently serial part of LZ4 — finding where each sequence starts — costs a thread, not a warp:
+//
+//   K0 scan   one thread per entry   frame header (lz4frame.c:1113-1205) + block-header chain
+//                                    (lz4frame.c:1503-1531) -> a table of blocks.
+//   K1 parse  one thread per block   walks token / length / offset bytes only (the control half of
+//                                    LZ4_decompress_generic, lz4.c:1797-2151), validates them, and
+//                                    emits one 32-bit descriptor per sequence:
+//                                    token position | output position << 16 (both block-relative).
+//                                    The compressed stream is staged per lane through shared memory
+//                                    with cp.async (LDGSTS), four 64-byte chunks ahead of the cursor,
+//                                    so the serial walk never waits on HBM.
+//   K2 exec   one warp per entry     32 sequences at a time, one per lane: every lane re-reads its own
+//                                    token, copies its literals and its match.  Output is assembled in
+//                                    a 4 KiB shared-memory ring per warp; each finished 1 KiB goes out
+//                                    as 16-byte coalesced stores and is folded into XXH3-64 from the
+//                                    same registers (the digest never re-reads HBM).  Near matches read
+//                                    the ring, far matches read flushed output back through L2.
+//
+// K0/K1 only ACCEPT: anything unusual (checksummed or multi-frame entries, > 64 KB blocks, any
+// malformed byte, sizes that do not add up) is handed to the general decoder in lz4_decode.cuh,
+// which reproduces the reference's exact error classes.  The fast path therefore only ever
+// reports OK or HASH_MISMATCH.
+#pragma once
+#include "common.cuh"
+#include "xxh3.cuh"
+#include "lz4_decode.cuh"
+
+#define FAST_RING      4096u
+#define FAST_RMASK     4095u
+#define FAST_LONG      32u     // lit or match >= this: executed cooperatively by the whole warp
+#define FAST_SCR       48u     // per-lane staging for a far match: 3 x 16 B covers 15 + 31 bytes
+#define FAST_WARP_SMEM (FAST_RING + 32u * FAST_SCR)
+
+#define FE_DONE    0u   // status already final (guards, unsupported method)
+#define FE_FAST    1u   // block table filled, goes through K1/K2
+#define FE_GENERAL 2u   // handed to the general kernel
+
+#define FB_STORED  1u
+#define FB_BAD     2u
+#define FB_PARSED  4u
+
+struct FastAux {      // host -> device, per entry
+    u64 desc_base;    // first descriptor slot of this entry (multiple of 4)
+    u32 slot_base;    // first FastBlock slot
+    u32 nslots;
+};
+struct FastEntry {    // K0 -> K2
+    u32 first_slot, nblocks, state, linked;
+};
+struct FastBlock {    // K0 -> K1 -> K2, 32 bytes
+    u64 src;          // archive offset of the block payload
+    u64 desc_off;     // index of its first descriptor (multiple of 4)
+    u32 bsz;          // payload bytes
+    u32 flags;        // FB_* | max backward reach before the block start << 8
+    u32 nseq;         // K1
+    u32 out_size;     // K1 (stored: = bsz)
+};
+
+// ------------------------------------------------------------------------------------------ K0
+// Returns true when the entry has the shape the fast path handles and the block table is filled.
+__device__ __noinline__ bool fast_scan_lz4(const u8 *src, u64 n, const zpb_entry &e, const FastAux &a,
+                                           FastEntry &f, FastBlock *fb) {
+    if (n < 11 || e.uncomp_size >= 0x7fffffffull) return false;
+    if (ld32u(src) != LZ4F_MAGIC) return false;
+    u32 flg = ld8(src + 4);
+    if (((flg >> 1) & 1) || ((flg >> 6) & 3) != 1) return false;
+    bool indep = (flg >> 5) & 1, bsum = (flg >> 4) & 1, has_size = (flg >> 3) & 1, csum = (flg >> 2) & 1,
+         has_dict = flg & 1;
+    if (bsum || csum) return false;
+    u32 hsize = 7 + (has_size ? 8 : 0) + (has_dict ? 4 : 0);
+    if (n < (u64)hsize + 4) return false;
+    u32 bd = ld8(src + 5);
+    if ((bd >> 7) || ((bd >> 4) & 7) != 4 || (bd & 15)) return false;  // 64 KB blocks only
+    if (((xxh32_dev(src + 4, hsize - 5, 0) >> 8) & 0xFF) != ld8(src + hsize - 1)) return false;
+    if (has_size && ld64u(src + 6) != e.uncomp_size) return false;
+    u64 ip = hsize;
+    u32 nb = 0;
+    for (;;) {
+        if (n - ip < 4) return false;
+        u32 bh = ld32u(src + ip);
+        ip += 4;
+        if (bh == 0) break;
+        u32 bsz = bh & 0x7FFFFFFFu;
+        if (bsz == 0 || bsz > 65536u || bsz > n - ip || nb == a.nslots) return false;
+        FastBlock b;
+        b.src = e.src_off + ip;
+        b.desc_off = a.desc_base + (((ip / 3) + 12ull * nb + 3ull) & ~3ull);
+        b.bsz = bsz;
+        b.flags = (bh >> 31) ? FB_STORED : 0u;
+        b.nseq = 0;
+        b.out_size = (bh >> 31) ? bsz : 0u;
+        fb[a.slot_base + nb] = b;
+        ip += bsz;
+        ++nb;
+    }
+    if (ip != n) return false;  // trailing bytes: another frame or garbage -> general path decides
+    f.nblocks = nb;
+    f.linked = indep ? 0u : 1u;
+    return true;
+}
+
+__global__ void __launch_bounds__(256)
+lz4_fast_scan_kernel(const u8 *__restrict__ archive, u64 asz, const zpb_entry *__restrict__ entries,
+                     const u32 *__restrict__ order, u32 n, const FastAux *__restrict__ aux, FastEntry *fe,
+                     FastBlock *fb, u32 *parse_list, u32 *counters, u32 *general_list, int *status,
+                     u64 *digest) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    u32 idx = order ? order[t] : t;
+    const zpb_entry e = entries[idx];
+    const FastAux a = aux[idx];
+    FastEntry f;
+    f.first_slot = a.slot_base; f.nblocks = 0; f.state = FE_DONE; f.linked = 0;
+    int st = ST_OK;
+    if (e.comp_size == 0) {
+        st = ST_OK;                                            // zpack_read.c:328
+    } else if (e.dst_cap < e.uncomp_size) {
+        st = ST_TOO_SMALL;                                     // :329
+    } else if (e.src_off > asz || e.comp_size > asz - e.src_off) {
+        st = ST_OFFSET_INVALID;                                // memory-safety form of :331
+    } else if (e.method == ZPB_METHOD_NONE) {                  // :352-368 — one stored "block"
+        if (e.uncomp_size > e.comp_size) st = ST_SIZE_INVALID;
+        else if (e.uncomp_size >= 0x7fffffffull || a.nslots == 0) f.state = FE_GENERAL;
+        else {
+            FastBlock b;
+            b.src = e.src_off; b.desc_off = a.desc_base; b.bsz = (u32)e.uncomp_size;
+            b.flags = FB_STORED; b.nseq = 0; b.out_size = (u32)e.uncomp_size;
+            fb[a.slot_base] = b;
+            f.nblocks = 1;
+            f.state = FE_FAST;
+        }
+    } else if (e.method == ZPB_METHOD_LZ4) {
+        f.state = fast_scan_lz4(archive + e.src_off, e.comp_size, e, a, f, fb) ? FE_FAST : FE_GENERAL;
+    } else {
+        f.state = FE_GENERAL;                                  // zstd / unknown: the general kernel answers
+    }
+    if (f.state == FE_DONE) {
+        status[idx] = st;
+        digest[idx] = 0;
+    } else if (f.state == FE_GENERAL) {
+        general_list[atomicAdd(&counters[1], 1u)] = idx;
+    } else {
+        for (u32 b = 0; b < f.nblocks; ++b)
+            if (!(fb[a.slot_base + b].flags & FB_STORED))
+                parse_list[atomicAdd(&counters[0], 1u)] = a.slot_base + b;
+    }
+    fe[idx] = f;
+}
+
+// ------------------------------------------------------------------------------------------ smem helpers
+// 32-bit shared-window addresses + inline PTX: keeps the byte loops at load / store / compare.
+ZPB_DEVINL u32 lds8(u32 a) { u32 v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+ZPB_DEVINL void sts8(u32 a, u32 v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+template <int OFF> ZPB_DEVINL u32 lds8o(u32 a) {
+    u32 v; asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF) : "memory"); return v;
+}
+template <int OFF> ZPB_DEVINL void sts8o(u32 a, u32 v) {
+    asm volatile("st.shared.u8 [%0+%2], %1;" ::"r"(a), "r"(v), "n"(OFF) : "memory");
+}
+template <int OFF> ZPB_DEVINL u32 ldg8nc(const u8 *p) {  // read-only data (the archive), explicit addressing
+    u32 v; asm volatile("ld.global.nc.u8 %0, [%1+%2];" : "=r"(v) : "l"(p), "n"(OFF)); return v;
+}
+ZPB_DEVINL uint4 lds128(u32 a) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a) : "memory");
+    return r;
+}
+ZPB_DEVINL void sts128(u32 a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------ K1
+#define K1_THREADS 256
+#define K1_ROW     272u   // 256-byte staging ring per lane + 16 bytes of bank skew
+
+ZPB_DEVINL void cp_async16(u32 smem_addr, const void *gptr, u32 src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "r"(src_bytes)
+                 : "memory");
+}
+ZPB_DEVINL void cp_async64(u32 s, const void *g) {  // one whole 64-byte chunk, no bounds to honour
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n\t"
+                 "cp.async.ca.shared.global [%0+16], [%1+16], 16;\n\t"
+                 "cp.async.ca.shared.global [%0+32], [%1+32], 16;\n\t"
+                 "cp.async.ca.shared.global [%0+48], [%1+48], 16;" ::"r"(s), "l"(g) : "memory");
+}
+ZPB_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+ZPB_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+ZPB_DEVINL void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// Per-lane view of one block's compressed bytes through a 256-byte staging ring.  Positions are
+// "ring coordinates" q = block position + skew, so that q & 255 is both the ring slot and the low
+// byte of the global address (16-byte alignment of every cp.async piece follows).
+struct LaneStage {
+    const u8 *gbase;     // global address of ring coordinate 0 (256-byte aligned; may precede the block)
+    const u8 *glo, *ghi; // readable range of the archive
+    u32 row_s;           // this lane's ring, shared-window address
+    u32 nreq;            // chunks [.., nreq) have been requested
+    u32 klo, khi;        // chunks in [klo, khi) lie wholly inside the archive
+
+    ZPB_DEVINL u32 open(const u8 *archive, u64 asz, u64 src, u32 row_shared) {
+        const u8 *p = archive + src;
+        u32 skew = (u32)((uintptr_t)p & 255u);
+        gbase = p - skew;
+        glo = archive; ghi = archive + asz;
+        row_s = row_shared;
+        nreq = 0;
+        klo = gbase >= glo ? 0u : (u32)((glo - gbase + 63) >> 6);
+        u64 span = (u64)(ghi - gbase) >> 6;
+        khi = span > 0x7fffffffull ? 0x7fffffffu : (u32)span;
+        return skew;
+    }
+    ZPB_DEVINL void request(u32 k) {
+        const u8 *g = gbase + ((u64)k << 6);
+        u32 s = row_s + ((k << 6) & 255u);
+        if (k >= klo && k < khi) { cp_async64(s, g); return; }
+#pragma unroll 1
+        for (u32 j = 0; j < 4; ++j) {
+            const u8 *gj = g + 16 * j;
+            if (gj >= glo && gj < ghi) {
+                u64 left = (u64)(ghi - gj);
+                cp_async16(s + 16 * j, gj, left < 16 ? (u32)left : 16u);
+            }
+        }
+    }
+    // afterwards ring coordinates [q & ~63, (q & ~63) + 192) are readable
+    ZPB_DEVINL void ensure(u32 q) {
+        u32 c = q >> 6;
+        if (c + 4 > nreq) refill(c);
+    }
+    ZPB_DEVINL void refill(u32 c) {
+        u32 lo = nreq > c ? nreq : c;
+        for (u32 k = lo; k < c + 4; ++k) request(k);
+        cp_async_commit();
+        nreq = c + 4;
+        if (c + 4 - lo > 1) cp_async_wait_all(); else cp_async_wait_1();
+    }
+    ZPB_DEVINL u32 rd(u32 q) const { return lds8(row_s + (q & 255u)); }
+};
+
+__global__ void __launch_bounds__(K1_THREADS)
+lz4_fast_parse_kernel(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, const u32 *__restrict__ parse_list,
+                      const u32 *__restrict__ counters, u32 *work_counter, u32 *desc) {
+    extern __shared__ uint4 k1_smem[];
+    const int lane = threadIdx.x & 31;
+    const u32 row_s = (u32)__cvta_generic_to_shared(k1_smem) + threadIdx.x * K1_ROW;
+    const u32 nitems = counters[0];
+    bool active = false, exhausted = false;
+    LaneStage sg;
+    // all positions below are ring coordinates (block position + skew)
+    u32 slot = 0, skew = 0, qend = 0, q = 0, op = 0, nseq = 0, reach = 0, last_ms = 0;
+    bool had_match = false;
+    u32 b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    u32 *dout = nullptr;
+
+    for (;;) {
+        u32 idle = __ballot_sync(0xffffffffu, !active);
+        if (idle) {
+            if (!exhausted) {
+                u32 base = 0;
+                int leader = __ffs(idle) - 1;
+                if (lane == leader) base = atomicAdd(work_counter, (u32)__popc(idle));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (base + __popc(idle) > nitems) exhausted = true;
+                if (!active) {
+                    u32 w = base + __popc(idle & ((1u << lane) - 1u));
+                    if (w < nitems) {
+                        slot = parse_list[w];
+                        FastBlock B = fb[slot];
+                        dout = desc + B.desc_off;
+                        skew = sg.open(archive, asz, B.src, row_s);
+                        q = skew; qend = B.bsz + skew;
+                        op = 0; nseq = 0; reach = 0; last_ms = 0; had_match = false;
+                        active = true;
+                    }
+                }
+            }
+            if (__ballot_sync(0xffffffffu, active) == 0) break;
+            if (!active) continue;
+        }
+
+        // ---- one sequence (control bytes only; mirrors lz4.c:1797-2151 + the spec's end rules)
+        bool bad = false, fin = false;
+        sg.ensure(q);
+        const u32 token = sg.rd(q);
+        const u32 lim = (q & ~63u) + 192u;   // readable without another ensure
+        u32 p = q + 1;
+        u32 lit = token >> 4;
+        if (lit == 15) {
+            u32 b = 0;
+            do {
+                if (p >= qend) { bad = true; break; }
+                sg.ensure(p);
+                b = sg.rd(p++);
+                lit += b;
+            } while (b == 255 && lit < 0x100000u);
+            if (b == 255) bad = true;
+        }
+        if (lit > qend - p) bad = true;
+        if (!bad) {
+            const u32 d = (q - skew) | (op << 16);
+            b0 = b1; b1 = b2; b2 = b3; b3 = d;
+            ++nseq;
+            if ((nseq & 3u) == 0) *reinterpret_cast<uint4 *>(dout + nseq - 4) = make_uint4(b0, b1, b2, b3);
+            p += lit; op += lit;
+            if (op > 65536u) bad = true;
+            else if (p == qend) {
+                // final sequence: literals only.  Spec end rules (lz4_Block_format.md:108-137) as
+                // sufficient conditions for the reference's capacity-based checks (lz4.c:2055-2077,2139).
+                if (had_match && (lit < 5 || op - last_ms < 12)) bad = true;
+                fin = true;
+            } else if (p + 8 > qend) {
+                bad = true;                                   // lz4.c:2055: must have been the last
+            } else {
+                if (p + 2 > lim) sg.ensure(p);
+                u32 off = sg.rd(p) | (sg.rd(p + 1) << 8);
+                p += 2;
+                u32 ml = token & 15;
+                if (ml == 15) {
+                    u32 b = 0;
+                    do {
+                        if (p >= qend) { bad = true; break; }
+                        sg.ensure(p);
+                        b = sg.rd(p++);
+                        ml += b;
+                    } while (b == 255 && ml < 0x100000u);
+                    if (b == 255) bad = true;
+                }
+                ml += 4;
+                if (off == 0) bad = true;
+                if (off > op && off - op > reach) reach = off - op;
+                last_ms = op;
+                had_match = true;
+                op += ml;
+                if (op > 65536u || p >= qend) bad = true;
+                q = p;
+            }
+        }
+        if (bad || fin) {
+            if (!bad) {
+                u32 r = nseq & 3u;  // descriptors still in the shift register
+                if (r == 1) dout[nseq - 1] = b3;
+                else if (r == 2) { dout[nseq - 2] = b2; dout[nseq - 1] = b3; }
+                else if (r == 3) { dout[nseq - 3] = b1; dout[nseq - 2] = b2; dout[nseq - 1] = b3; }
+            }
+            fb[slot].nseq = nseq;
+            fb[slot].out_size = op;
+            fb[slot].flags = (bad ? FB_BAD : FB_PARSED) | (reach << 8);
+            cp_async_wait_all();
+            active = false;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K2
+ZPB_DEVINL uint4 ldg128_coherent(const void *p) {  // plain ld.global (never .nc): the buffer is written by this kernel
+    uint4 r;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+ZPB_DEVINL u32 ldg8_coherent(const u8 *p) {
+    u32 r;
+    asm volatile("ld.global.u8 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return r;
+}
+
+#define FAST_LT 16u   // literal runs up to this go one-lane-per-sequence; longer ones warp-wide
+#define FAST_MT 16u   // same for matches
+
+struct FastExec {
+    u32 rb;         // this warp's output ring (shared-window address): position p lives at rb + (p & FAST_RMASK)
+    u32 scr_s;      // this lane's far-match staging (shared-window address)
+    u8 *gout;       // the entry's final place in HBM (16-byte aligned)
+    u32 done;       // every byte below is final (in the ring and/or in HBM)
+    u32 flushed;    // HBM holds [0, flushed); multiple of 1024 until the very end
+    u32 rbase;      // ring content below this position is stale (direct stored path went around it)
+    u32 total, full_blocks;
+    u64 acc0, acc1; // XXH3 accumulators of pair j = lane & 3
+    int lane;
+
+    ZPB_DEVINL u32 ring_lo(u32 hi) const {
+        u32 w = hi > FAST_RING ? hi - FAST_RING : 0u;
+        return w > rbase ? w : rbase;
+    }
+    ZPB_DEVINL u32 ra(u32 pos) const { return rb + (pos & FAST_RMASK); }
+    ZPB_DEVINL u32 rd(u32 pos, u32 lo) const { return pos >= lo ? lds8(ra(pos)) : ldg8_coherent(gout + pos); }
+
+    ZPB_DEVINL void hash_init() {
+        int j = lane & 3;
+        acc0 = j == 0 ? (u64)XXH_P32_3 : j == 1 ? XXH_P64_2 : j == 2 ? XXH_P64_4 : XXH_P64_5;
+        acc1 = j == 0 ? XXH_P64_1 : j == 1 ? XXH_P64_3 : j == 2 ? (u64)XXH_P32_2 : (u64)XXH_P32_1;
+    }
+    ZPB_DEVINL void hash_fold_scramble(u64 s0, u64 s1) {
+#pragma unroll
+        for (int m = 4; m < 32; m <<= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, m);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+        }
+        int j = lane & 3;
+        u64 a0 = acc0 + s0, a1 = acc1 + s1;
+        a0 ^= a0 >> 47; a0 ^= c_xxh3_key[16 + 2 * j]; a0 *= XXH_P32_1;
+        a1 ^= a1 >> 47; a1 ^= c_xxh3_key[16 + 2 * j + 1]; a1 *= XXH_P32_1;
+        acc0 = a0; acc1 = a1;
+    }
+    // one full 1 KiB block: ring -> HBM (16 B per lane, coalesced) and -> XXH3 from the same registers
+    ZPB_DEVINL void flush_kib() {
+        u32 a = rb + (flushed & FAST_RMASK) + lane * 16;
+        int j = lane & 3;
+        u64 s0 = 0, s1 = 0;
+        uint4 v0 = lds128(a), v1 = lds128(a + 512);
+        stg128(gout + flushed + lane * 16, v0);
+        stg128(gout + flushed + 512 + lane * 16, v1);
+        u32 s = lane >> 2;
+        Xxh3Stream<32>::piece(s0, s1, v0, c_xxh3_key[s + 2 * j], c_xxh3_key[s + 2 * j + 1]);
+        Xxh3Stream<32>::piece(s0, s1, v1, c_xxh3_key[s + 8 + 2 * j], c_xxh3_key[s + 8 + 2 * j + 1]);
+        hash_fold_scramble(s0, s1);
+        flushed += 1024;
+    }
+    // callers have finished writing [.., done); flushes every hashable full block below done
+    ZPB_DEVINL void flush_full() {
+        __syncwarp();
+        if (flushed + 1024 <= done && (flushed >> 10) < full_blocks) {
+            do flush_kib(); while (flushed + 1024 <= done && (flushed >> 10) < full_blocks);
+            __syncwarp();
+        }
+    }
+    ZPB_DEVINL u32 room() const { return flushed + FAST_RING - done; }
+
+    // warp-wide: ring[O + i] = sp[i], i < L (inside a segment: no flush)
+    ZPB_DEVINL void coop_lit(u32 O, const u8 *__restrict__ sp, u32 L) const {
+        for (u32 i = lane; i < L; i += 32) sts8(ra(O + i), sp[i]);
+    }
+    // warp-wide match: out[MO + i] = out[MO + i - OF], i < ML, everything below MO final
+    ZPB_DEVINL void coop_match(u32 MO, u32 OF, u32 ML, u32 lo) const {
+        if (OF >= ML) {
+            for (u32 i = lane; i < ML; i += 32) sts8(ra(MO + i), rd(MO - OF + i, lo));
+        } else {  // periodic with period OF: byte i is byte (i mod OF) of the OF bytes before MO
+            u32 k = (u32)lane < OF ? (u32)lane : (u32)lane % OF;
+            u32 step = OF > 32 ? 32u : 32u % OF;
+            for (u32 i = lane; i < ML; i += 32) {
+                sts8(ra(MO + i), rd(MO - OF + k, lo));
+                k += step;
+                if (k >= OF) k -= OF;
+            }
+        }
+    }
+    // the same, for runs too long for the ring: piecewise with flushes in between
+    ZPB_DEVINL void stream_lit(const u8 *__restrict__ sp, u32 L) {
+        while (L) {
+            u32 piece = L < room() ? L : room();
+            coop_lit(done, sp, piece);
+            sp += piece; L -= piece; done += piece;
+            flush_full();
+        }
+    }
+    ZPB_DEVINL void stream_match(u32 OF, u32 ML) {
+        while (ML) {
+            u32 piece = ML < room() ? ML : room();
+            coop_match(done, OF, piece, ring_lo(done + piece));
+            ML -= piece; done += piece;
+            flush_full();
+        }
+    }
+};
+
+// unaligned 16-byte global load assembled from 4-byte-aligned words
+ZPB_DEVINL uint4 ldg128_unaligned(const u8 *p) {
+    const u32 *s = reinterpret_cast<const u32 *>((uintptr_t)p & ~(uintptr_t)3);
+    u32 sh = ((u32)(uintptr_t)p & 3u) * 8u;
+    u32 w0 = s[0], w1 = s[1], w2 = s[2], w3 = s[3];
+    if (sh == 0) return make_uint4(w0, w1, w2, w3);
+    u32 w4 = s[4];
+    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                      __funnelshift_r(w3, w4, sh));
+}
+
+#define FAST_BYTE4(LD, ST, n, i)                                                        \
+    {                                                                                   \
+        u32 v0_ = 0, v1_ = 0, v2_ = 0, v3_ = 0;                                                       \
+        const bool p0_ = (i) + 0 < (n), p1_ = (i) + 1 < (n), p2_ = (i) + 2 < (n), p3_ = (i) + 3 < (n); \
+        if (p0_) v0_ = LD(0); if (p1_) v1_ = LD(1); if (p2_) v2_ = LD(2); if (p3_) v3_ = LD(3);       \
+        if (p0_) ST(0, v0_); if (p1_) ST(1, v1_); if (p2_) ST(2, v2_); if (p3_) ST(3, v3_);           \
+    }
+
+__global__ void __launch_bounds__(256, 3)
+lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_entry *__restrict__ entries,
+                     const u32 *__restrict__ order, u32 n, u32 *counter, const FastEntry *__restrict__ fe,
+                     const FastBlock *__restrict__ fb, const u32 *__restrict__ desc, u32 *counters,
+                     u32 *general_list, int *status, u64 *digest) {
+    extern __shared__ uint4 k2_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    FastExec x;
+    x.lane = lane;
+    x.rb = (u32)__cvta_generic_to_shared(k2_smem) + warp * FAST_WARP_SMEM;
+    x.scr_s = x.rb + FAST_RING + lane * FAST_SCR;
+    const u8 *arch_end = archive + asz;
+
+    for (;;) {
+        u32 wslot = 0;
+        if (lane == 0) wslot = atomicAdd(counter, 1u);
+        wslot = __shfl_sync(0xffffffffu, wslot, 0);
+        if (wslot >= n) break;
+        const u32 idx = order ? order[wslot] : wslot;
+        const FastEntry f = fe[idx];
+        if (f.state != FE_FAST) continue;
+        const zpb_entry e = entries[idx];
+
+        // ---- K1 verdicts: every block parsed clean, window reach legal, sizes add up exactly
+        bool ok = true;
+        {
+            u64 before = 0;
+            for (u32 b = 0; b < f.nblocks; ++b) {
+                const FastBlock B = fb[f.first_slot + b];
+                if (!(B.flags & FB_STORED)) {
+                    if (!(B.flags & FB_PARSED) || (B.flags & FB_BAD)) ok = false;
+                    u32 reach = (B.flags >> 8) & 0xFFFFu;
+                    if (reach > (f.linked ? before : 0ull)) ok = false;   // lz4.c:2093 with the frame's prefix
+                }
+                before += B.out_size;
+            }
+            if (before != e.uncomp_size) ok = false;
+        }
+        if (!ok) {
+            if (lane == 0) general_list[atomicAdd(&counters[1], 1u)] = idx;
+            continue;
+        }
+
+        x.gout = out + e.dst_off;
+        x.done = x.flushed = x.rbase = 0;
+        x.total = (u32)e.uncomp_size;
+        x.full_blocks = x.total > 240 ? (x.total - 1) >> 10 : 0;
+        x.hash_init();
+
+        for (u32 b = 0; b < f.nblocks; ++b) {
+            const FastBlock B = fb[f.first_slot + b];
+            const u8 *__restrict__ src = archive + B.src;
+            if (B.flags & FB_STORED) {
+                // ---- stored block / NONE entry (lz4frame.c:1534-1572, zpack_read.c:352-368)
+                u32 len = B.bsz;
+                if (x.done == x.flushed && (x.done & 1023u) == 0) {
+                    // direct: HBM -> registers -> XXH3 + HBM, no ring
+                    while (len >= 1024 && (x.flushed >> 10) < x.full_blocks && src + 1024 + 16 <= arch_end) {
+                        int j = lane & 3;
+                        u64 s0 = 0, s1 = 0;
+                        uint4 v0 = ldg128_unaligned(src + lane * 16);
+                        uint4 v1 = ldg128_unaligned(src + 512 + lane * 16);
+                        stg128(x.gout + x.flushed + lane * 16, v0);
+                        stg128(x.gout + x.flushed + 512 + lane * 16, v1);
+                        u32 s = lane >> 2;
+                        Xxh3Stream<32>::piece(s0, s1, v0, c_xxh3_key[s + 2 * j], c_xxh3_key[s + 2 * j + 1]);
+                        Xxh3Stream<32>::piece(s0, s1, v1, c_xxh3_key[s + 8 + 2 * j], c_xxh3_key[s + 8 + 2 * j + 1]);
+                        x.hash_fold_scramble(s0, s1);
+                        x.flushed += 1024; src += 1024; len -= 1024;
+                    }
+                    x.done = x.flushed;
+                    x.rbase = x.done;
+                    __syncwarp();
+                }
+                x.stream_lit(src, len);
+                continue;
+            }
+
+            // ---- compressed block: 32 sequences per step, one per lane
+            const u32 *__restrict__ dp = desc + B.desc_off;
+            const u32 obase = x.done;
+            const u32 bsz = B.bsz;
+            u32 dnext = (u32)lane < B.nseq ? dp[lane] : 0u;
+            for (u32 s0i = 0; s0i < B.nseq; s0i += 32) {
+                const bool have = s0i + lane < B.nseq;
+                const u32 d = dnext;
+                if (s0i + 32 < B.nseq) dnext = s0i + 32 + lane < B.nseq ? dp[s0i + 32 + lane] : 0u;
+                u32 lit = 0, lsrc = 0, off = 0, ml = 0, o = 0;
+                if (have) {
+                    u32 tok = d & 0xFFFFu;
+                    o = obase + (d >> 16);
+                    const u8 *tp = src + tok;
+                    u32 t = tp[0];
+                    u32 p = tok + 1;
+                    lit = t >> 4;
+                    if (lit == 15) { u32 bb; do { bb = src[p++]; lit += bb; } while (bb == 255); }
+                    lsrc = p;
+                    p += lit;
+                    if (p < bsz) {
+                        off = (u32)src[p] | ((u32)src[p + 1] << 8);
+                        p += 2;
+                        ml = t & 15;
+                        if (ml == 15) { u32 bb; do { bb = src[p++]; ml += bb; } while (bb == 255); }
+                        ml += 4;
+                    }
+                }
+                const u32 sz = lit + ml;
+                const u32 mo = o + lit, msrc = mo - off;
+                const u8 *__restrict__ sp = src + lsrc;
+                u32 todo = __ballot_sync(0xffffffffu, have);
+                while (todo) {
+                    const int first = __ffs(todo) - 1;
+                    const bool fits = ((todo >> lane) & 1u) && (o + sz <= x.flushed + FAST_RING);
+                    const u32 seg = __ballot_sync(0xffffffffu, fits);   // o + sz is monotone: a prefix of todo
+                    if (!((seg >> first) & 1u)) {
+                        // ---- one sequence larger than the ring: streamed, whole warp
+                        u32 L = __shfl_sync(0xffffffffu, lit, first), S = __shfl_sync(0xffffffffu, lsrc, first);
+                        u32 O = __shfl_sync(0xffffffffu, off, first), ML = __shfl_sync(0xffffffffu, ml, first);
+                        x.stream_lit(src + S, L);
+                        if (ML) x.stream_match(O, ML);
+                        todo &= ~(1u << first);
+                        continue;
+                    }
+                    // ---- a run of sequences that fits the ring: literals (independent), then matches in rounds
+                    const bool in = (seg >> lane) & 1u;
+                    const int last_lane = 31 - __clz(seg);
+                    const u32 seg_end = __shfl_sync(0xffffffffu, o + sz, last_lane);
+                    const u32 lo = x.ring_lo(seg_end);
+                    {
+                        const u32 da = x.ra(o);
+                        const bool lane_lit = in && lit <= FAST_LT && (o & FAST_RMASK) + lit <= FAST_RING;
+                        const u32 mylit = lane_lit ? lit : 0u;
+                        const u32 maxlit = __reduce_max_sync(0xffffffffu, mylit);
+#define LDL(u) ldg8nc<u>(spi)
+#define STL(u, v) sts8o<u>(dai, v)
+                        for (u32 i = 0; i < maxlit; i += 4) {
+                            const u8 *spi = sp + i;
+                            const u32 dai = da + i;
+                            FAST_BYTE4(LDL, STL, mylit, i)
+                        }
+#undef LDL
+#undef STL
+                        u32 cm = __ballot_sync(0xffffffffu, in && lit > 0 && !lane_lit);
+                        while (cm) {
+                            int r = __ffs(cm) - 1;
+                            cm &= cm - 1;
+                            u32 O = __shfl_sync(0xffffffffu, o, r), S = __shfl_sync(0xffffffffu, lsrc, r),
+                                L = __shfl_sync(0xffffffffu, lit, r);
+                            x.coop_lit(O, src + S, L);
+                        }
+                    }
+                    const bool has_m = in && ml > 0;
+                    const u32 abase = msrc & ~15u;
+                    const bool far_all = msrc + ml <= lo;
+                    if (has_m && msrc < lo && ml <= FAST_MT + 15u) {  // behind the ring: stage the flushed bytes
+                        u32 units = ((msrc - abase) + ml + 15u) >> 4;
+#pragma unroll
+                        for (u32 u = 0; u < 3; ++u)
+                            if (u < units && abase + 16 * u < x.flushed)
+                                sts128(x.scr_s + 16 * u, ldg128_coherent(x.gout + abase + 16 * u));
+                    }
+                    // one-lane-per-match is possible when source and destination are linear in shared memory
+                    const bool near_lin = msrc >= lo && (msrc & FAST_RMASK) + ml <= FAST_RING;
+                    const bool lane_ok = has_m && ml <= FAST_MT && (mo & FAST_RMASK) + ml <= FAST_RING &&
+                                         (far_all || near_lin);
+                    const u32 sa = far_all ? x.scr_s + (msrc - abase) : x.ra(msrc);
+                    const u32 dm = x.ra(mo);
+                    const u32 send = msrc + ml < mo ? msrc + ml : mo;   // own overlap is handled in lane order
+                    __syncwarp();
+                    u32 pend = __ballot_sync(0xffffffffu, has_m);
+                    while (pend) {
+                        const int fl = __ffs(pend) - 1;
+                        const u32 front = __shfl_sync(0xffffffffu, mo, fl);
+                        const bool ready = ((pend >> lane) & 1u) && (lane == fl || send <= front);
+                        const u32 rmask = __ballot_sync(0xffffffffu, ready);
+                        const bool el = ready && lane_ok;
+                        const u32 elmask = __ballot_sync(0xffffffffu, el);
+                        u32 cm = rmask;
+                        if (__popc(elmask) >= 3) {
+                            cm = rmask & ~elmask;
+                            const u32 myml = el ? ml : 0u;
+                            const u32 maxml = __reduce_max_sync(0xffffffffu, myml);
+                            if (!__any_sync(0xffffffffu, el && off < 4)) {
+#define LDM(u) lds8o<u>(sai)
+#define STM(u, v) sts8o<u>(dmi, v)
+                                for (u32 i = 0; i < maxml; i += 4) {
+                                    const u32 sai = sa + i, dmi = dm + i;
+                                    FAST_BYTE4(LDM, STM, myml, i)
+                                }
+#undef LDM
+#undef STM
+                            } else {
+                                for (u32 i = 0; i < maxml; ++i)
+                                    if (i < myml) sts8(dm + i, lds8(sa + i));
+                            }
+                        }
+                        while (cm) {
+                            int r = __ffs(cm) - 1;
+                            cm &= cm - 1;
+                            u32 MO = __shfl_sync(0xffffffffu, mo, r), OF = __shfl_sync(0xffffffffu, off, r),
+                                ML = __shfl_sync(0xffffffffu, ml, r);
+                            x.coop_match(MO, OF, ML, lo);
+                        }
+                        __syncwarp();
+                        pend &= ~rmask;
+                    }
+                    x.done = seg_end;
+                    todo &= ~seg;
+                    x.flush_full();
+                }
+            }
+        }
+
+        // ---- finish: last bytes to HBM, XXH3 tail (xxhash.h:3701-3747) from the ring, verdict
+        __syncwarp();
+        u64 dg;
+        {
+            u32 span = x.total - x.flushed;
+            for (u32 p = x.flushed + 16 * lane; p + 16 <= x.total; p += 512) stg128(x.gout + p, lds128(x.ra(p)));
+            for (u32 p = x.flushed + (span & ~15u) + lane; p < x.total; p += 32) x.gout[p] = (u8)lds8(x.ra(p));
+        }
+        if (x.total <= 240) {
+            __syncwarp();
+            dg = xxh3_small(x.gout, x.total);
+        } else {
+            const u32 lo = x.ring_lo(x.total);
+            const int j = lane & 3;
+            const u32 tail_start = x.full_blocks << 10;
+            const u32 tail_stripes = ((x.total - 1) - tail_start) >> 6;
+            u64 s0 = 0, s1 = 0;
+            for (u32 s = lane >> 2; s < tail_stripes; s += 8) {
+                u32 p = tail_start + 64 * s + 16 * j;
+                uint4 v = p >= lo ? lds128(x.ra(p)) : ldg128_coherent(x.gout + p);
+                Xxh3Stream<32>::piece(s0, s1, v, c_xxh3_key[s + 2 * j], c_xxh3_key[s + 2 * j + 1]);
+            }
+            if (lane < 4) {
+                u32 p = x.total - 64 + 16 * j;
+                u32 w[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    w[k] = x.rd(p + 4 * k, lo) | (x.rd(p + 4 * k + 1, lo) << 8) | (x.rd(p + 4 * k + 2, lo) << 16) |
+                           (x.rd(p + 4 * k + 3, lo) << 24);
+                Xxh3Stream<32>::piece(s0, s1, make_uint4(w[0], w[1], w[2], w[3]), c_xxh3_key_last[2 * j],
+                                      c_xxh3_key_last[2 * j + 1]);
+            }
+#pragma unroll
+            for (int m = 4; m < 32; m <<= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, m);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+            }
+            u64 a0 = x.acc0 + s0, a1 = x.acc1 + s1;
+            u64 m = xxh_fold128(a0 ^ xxh_sec64(11 + 16 * j), a1 ^ xxh_sec64(19 + 16 * j));
+            m += __shfl_xor_sync(0xffffffffu, m, 1);
+            m += __shfl_xor_sync(0xffffffffu, m, 2);
+            dg = xxh3_avalanche((u64)x.total * XXH_P64_1 + m);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            status[idx] = (!(e.flags & ZPB_F_NO_VERIFY) && dg != e.hash) ? ST_HASH_MISMATCH : ST_OK;
+            digest[idx] = dg;
+        }
+    }
+}

@@ -63,9 +63,10 @@ ZPB_DEVINL void unpack_one(const Group<G> &g, const u8 *archive, u64 archive_siz
 template <int G>
 __global__ void __launch_bounds__(256)
 unpack_kernel(const u8 *__restrict__ archive, u64 archive_size, u8 *__restrict__ out,
-              const zpb_entry *__restrict__ entries, const u32 *__restrict__ order, u32 n,
+              const zpb_entry *__restrict__ entries, const u32 *order, u32 n, const u32 *n_ptr,
               u32 *counter, int *status, u64 *digest, u64 *produced) {
     Group<G> g;
+    if (n_ptr) n = *n_ptr;  // device-side count: the entries the fast path handed over
     for (;;) {
         u32 slot = 0;
         if (g.l == 0) slot = atomicAdd(counter, 1u);

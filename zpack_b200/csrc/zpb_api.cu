@@ -11,6 +11,7 @@
 
 #include "../../include/zpack_b200.h"
 #include "unpack_kernel.cuh"
+#include "lz4_fast.cuh"
 #include "pack_kernel.cuh"
 
 static thread_local std::string g_last_error = "";
@@ -52,8 +53,12 @@ struct zpb_ctx {
     std::string err;
     uint64_t launches = 0;
     float unpack_ms = 0.f, pack_ms = 0.f;
-    int group = 8;        // lanes per chain (tunable: ZPB_GROUP)
+    int group = 32;       // lanes per chain in the general kernel (tunable: ZPB_GROUP)
     int ctas_per_sm = 0;  // 0 = occupancy API
+    int fast = 1;         // scan/parse/exec pipeline for LZ4 + stored entries (ZPB_FAST=0: general kernel only)
+    float stage_ms[4] = {0, 0, 0, 0};
+    DevBuf d_aux, d_fe, d_fb, d_plist, d_glist, d_fdesc;
+    cudaEvent_t evs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     // descriptor / result scratch
     DevBuf d_desc, d_order, d_res, d_counter;
     PinBuf h_stage;
@@ -112,6 +117,16 @@ extern "C" zpb_ctx *zpb_create(int device) {
         if (v == 4 || v == 8 || v == 16 || v == 32) ctx->group = v;
     }
     if (const char *s = getenv("ZPB_CTAS_PER_SM")) ctx->ctas_per_sm = atoi(s);
+    if (const char *s = getenv("ZPB_FAST")) ctx->fast = atoi(s);
+    for (auto &ev : ctx->evs)
+        if (cudaEventCreate(&ev) != cudaSuccess) { g_last_error = "event setup failed"; delete ctx; return nullptr; }
+    if (cudaFuncSetAttribute(lz4_fast_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(K1_THREADS * K1_ROW)) != cudaSuccess ||
+        cudaFuncSetAttribute(lz4_fast_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(8 * FAST_WARP_SMEM)) != cudaSuccess) {
+        g_last_error = std::string("kernel attribute setup failed: ") + cudaGetErrorString(cudaGetLastError());
+        delete ctx; return nullptr;
+    }
     return ctx;
 }
 
@@ -120,6 +135,9 @@ extern "C" void zpb_destroy(zpb_ctx *ctx) {
     cudaSetDevice(ctx->device);
     ctx->d_desc.release(); ctx->d_order.release(); ctx->d_res.release(); ctx->d_counter.release();
     ctx->d_in.release(); ctx->d_out.release(); ctx->h_stage.release();
+    ctx->d_aux.release(); ctx->d_fe.release(); ctx->d_fb.release(); ctx->d_plist.release();
+    ctx->d_glist.release(); ctx->d_fdesc.release();
+    for (auto &ev : ctx->evs) if (ev) cudaEventDestroy(ev);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -147,6 +165,18 @@ extern "C" int zpb_set_tuning(zpb_ctx *ctx, int group_lanes, int ctas_per_sm) {
     return ZPB_OK;
 }
 
+extern "C" int zpb_last_stage_ms(const zpb_ctx *ctx, float *ms4) {
+    if (!ctx || !ms4) return ZPB_E_ARG;
+    for (int k = 0; k < 4; ++k) ms4[k] = ctx->stage_ms[k];
+    return ZPB_OK;
+}
+
+extern "C" int zpb_set_fast_path(zpb_ctx *ctx, int enabled) {
+    if (!ctx) return ZPB_E_ARG;
+    ctx->fast = enabled ? 1 : 0;
+    return ZPB_OK;
+}
+
 extern "C" int zpb_last_kernel_ms(const zpb_ctx *ctx, float *unpack_ms, float *pack_ms) {
     if (!ctx) return ZPB_E_ARG;
     if (unpack_ms) *unpack_ms = ctx->unpack_ms;
@@ -168,8 +198,22 @@ static cudaError_t launch_unpack(zpb_ctx *ctx, cudaStream_t s, const u8 *arch, u
     u64 groups_per_cta = 256 / G;
     u64 want = (n + groups_per_cta - 1) / groups_per_cta;
     u32 grid = (u32)std::min<u64>((u64)ctx->sm_count * per_sm, std::max<u64>(want, 1));
-    unpack_kernel<G><<<grid, 256, 0, s>>>(arch, asz, out, d_e, d_order, n, d_counter, d_status,
+    unpack_kernel<G><<<grid, 256, 0, s>>>(arch, asz, out, d_e, d_order, n, nullptr, d_counter, d_status,
                                           d_digest, nullptr);
+    return cudaGetLastError();
+}
+
+// the general kernel over a device-side list (entries the fast path declined); full persistent grid
+template <int G>
+static cudaError_t launch_general_list(zpb_ctx *ctx, cudaStream_t s, const u8 *arch, u64 asz, u8 *out,
+                                       const zpb_entry *d_e, const u32 *d_list, const u32 *d_count,
+                                       u32 *d_counter, int *d_status, u64 *d_digest) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, unpack_kernel<G>, 256, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    unpack_kernel<G><<<ctx->sm_count * per_sm, 256, 0, s>>>(arch, asz, out, d_e, d_list, 0, d_count, d_counter,
+                                                            d_status, d_digest, nullptr);
     return cudaGetLastError();
 }
 
@@ -200,7 +244,7 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
     size_t desc_b = n * sizeof(zpb_entry), ord_b = n * sizeof(u32);
     size_t res_b = n * (sizeof(int) + sizeof(u64));
     if (!ctx->d_desc.ensure(desc_b) || !ctx->d_order.ensure(ord_b) || !ctx->d_res.ensure(res_b + 64) ||
-        !ctx->d_counter.ensure(256) || !ctx->h_stage.ensure(desc_b + ord_b + res_b + 64))
+        !ctx->d_counter.ensure(256) || !ctx->h_stage.ensure(desc_b + ord_b + res_b + 64 + n * sizeof(FastAux)))
         return fail(ctx, ZPB_E_NOMEM, "scratch allocation failed");
 
     u8 *hs = (u8 *)ctx->h_stage.p;
@@ -214,6 +258,70 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
     CK(ctx, cudaMemcpyAsync(ctx->d_desc.p, h_desc, desc_b, cudaMemcpyHostToDevice, s));
     CK(ctx, cudaMemcpyAsync(ctx->d_order.p, h_order, ord_b, cudaMemcpyHostToDevice, s));
     CK(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, 256, s));
+    if (ctx->fast) {
+        // ---- scan -> parse -> exec (lz4_fast.cuh), then the general kernel over whatever they declined
+        size_t aux_b = n * sizeof(FastAux);
+        FastAux *h_aux = (FastAux *)(hs + desc_b + ord_b + res_b + 64);
+        u64 slots = 0, ndesc = 0;
+        for (u64 i = 0; i < n; ++i) {
+            const zpb_entry &e = entries[i];
+            u32 ns = 0; u64 nd = 0;
+            if (e.uncomp_size < 0x7fffffffull && e.comp_size) {
+                if (e.method == ZPB_METHOD_NONE) ns = 1;
+                else if (e.method == ZPB_METHOD_LZ4) {
+                    ns = (u32)(e.uncomp_size >> 16) + 2;
+                    nd = ((e.comp_size / 3 + 12ull * ns + 8) + 3) & ~3ull;
+                }
+            }
+            h_aux[i].desc_base = ndesc; h_aux[i].slot_base = (u32)slots; h_aux[i].nslots = ns;
+            slots += ns; ndesc += nd;
+        }
+        if (slots > 0x7fffffffull) return fail(ctx, ZPB_E_ARG, "too many blocks in one batch");
+        if (!ctx->d_aux.ensure(aux_b) || !ctx->d_fe.ensure(n * sizeof(FastEntry)) ||
+            !ctx->d_fb.ensure((slots + 1) * sizeof(FastBlock)) || !ctx->d_plist.ensure((slots + 1) * 4) ||
+            !ctx->d_glist.ensure(n * 4) || !ctx->d_fdesc.ensure((ndesc + 4) * 4))
+            return fail(ctx, ZPB_E_NOMEM, "fast-path scratch allocation failed");
+        CK(ctx, cudaMemcpyAsync(ctx->d_aux.p, h_aux, aux_b, cudaMemcpyHostToDevice, s));
+        u32 *cnt = (u32 *)ctx->d_counter.p;  // [0] parse items [1] general items [2..4] work counters (zeroed above)
+        const zpb_entry *d_e = (const zpb_entry *)ctx->d_desc.p;
+        const u32 *d_ord = (const u32 *)ctx->d_order.p;
+        CK(ctx, cudaEventRecord(ctx->evs[0], s));
+        lz4_fast_scan_kernel<<<(u32)((n + 255) / 256), 256, 0, s>>>(
+            d_archive, archive_size, d_e, d_ord, (u32)n, (const FastAux *)ctx->d_aux.p, (FastEntry *)ctx->d_fe.p,
+            (FastBlock *)ctx->d_fb.p, (u32 *)ctx->d_plist.p, cnt, (u32 *)ctx->d_glist.p, d_status, d_digest);
+        CK(ctx, cudaGetLastError());
+        CK(ctx, cudaEventRecord(ctx->evs[1], s));
+        int k1_ctas = ctx->ctas_per_sm > 0 ? ctx->ctas_per_sm : 3;
+        lz4_fast_parse_kernel<<<ctx->sm_count * k1_ctas, K1_THREADS, K1_THREADS * K1_ROW, s>>>(
+            d_archive, archive_size, (FastBlock *)ctx->d_fb.p, (const u32 *)ctx->d_plist.p, cnt, cnt + 2,
+            (u32 *)ctx->d_fdesc.p);
+        CK(ctx, cudaGetLastError());
+        CK(ctx, cudaEventRecord(ctx->evs[2], s));
+        lz4_fast_exec_kernel<<<ctx->sm_count * 3, 256, 8 * FAST_WARP_SMEM, s>>>(
+            d_archive, archive_size, d_out, d_e, d_ord, (u32)n, cnt + 3, (const FastEntry *)ctx->d_fe.p,
+            (const FastBlock *)ctx->d_fb.p, (const u32 *)ctx->d_fdesc.p, cnt, (u32 *)ctx->d_glist.p, d_status,
+            d_digest);
+        CK(ctx, cudaGetLastError());
+        CK(ctx, cudaEventRecord(ctx->evs[3], s));
+        cudaError_t ge;
+        switch (ctx->group) {
+        case 4:  ge = launch_general_list<4>(ctx, s, d_archive, archive_size, d_out, d_e, (u32 *)ctx->d_glist.p, cnt + 1, cnt + 4, d_status, d_digest); break;
+        case 8:  ge = launch_general_list<8>(ctx, s, d_archive, archive_size, d_out, d_e, (u32 *)ctx->d_glist.p, cnt + 1, cnt + 4, d_status, d_digest); break;
+        case 16: ge = launch_general_list<16>(ctx, s, d_archive, archive_size, d_out, d_e, (u32 *)ctx->d_glist.p, cnt + 1, cnt + 4, d_status, d_digest); break;
+        default: ge = launch_general_list<32>(ctx, s, d_archive, archive_size, d_out, d_e, (u32 *)ctx->d_glist.p, cnt + 1, cnt + 4, d_status, d_digest); break;
+        }
+        CK(ctx, ge);
+        CK(ctx, cudaEventRecord(ctx->evs[4], s));
+        ctx->launches += 4;
+        u8 *h_res = hs + desc_b + ord_b;
+        CK(ctx, cudaMemcpyAsync(h_res, ctx->d_res.p, res_b, cudaMemcpyDeviceToHost, s));
+        CK(ctx, cudaStreamSynchronize(s));
+        CK(ctx, cudaEventElapsedTime(&ctx->unpack_ms, ctx->evs[0], ctx->evs[4]));
+        for (int k = 0; k < 4; ++k) CK(ctx, cudaEventElapsedTime(&ctx->stage_ms[k], ctx->evs[k], ctx->evs[k + 1]));
+        if (digest) memcpy(digest, h_res, n * sizeof(u64));
+        if (status) memcpy(status, h_res + n * sizeof(u64), n * sizeof(int));
+        return ZPB_OK;
+    }
     CK(ctx, cudaEventRecord(ctx->ev0, s));
     cudaError_t le;
     switch (ctx->group) {

@@ -46,6 +46,7 @@ EXPORTS = [
     "zpb_abi_version", "zpb_create", "zpb_destroy", "zpb_last_error", "zpb_device_info",
     "zpb_launch_count", "zpb_unpack_device", "zpb_unpack_host", "zpb_xxh3_device", "zpb_xxh3_host",
     "zpb_pack_bound", "zpb_pack_device", "zpb_pack_host", "zpb_last_kernel_ms", "zpb_set_tuning",
+    "zpb_last_stage_ms", "zpb_set_fast_path",
 ]
 
 
@@ -84,6 +85,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.zpb_pack_device.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, vp, vp, vp]
     lib.zpb_pack_host.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, vp, vp]
     lib.zpb_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.zpb_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.zpb_set_fast_path.argtypes = [vp, C.c_int]
     _lib = lib
     return lib
 
@@ -129,6 +132,15 @@ class Context:
 
     def set_tuning(self, group_lanes: int = 0, ctas_per_sm: int = -1):
         self._check(self.lib.zpb_set_tuning(self.h, group_lanes, ctas_per_sm))
+
+    def set_fast_path(self, enabled: bool):
+        """False: every entry goes through the general decoder (A/B runs, tests of that kernel)."""
+        self._check(self.lib.zpb_set_fast_path(self.h, int(enabled)))
+
+    def last_stage_ms(self):
+        a = (C.c_float * 4)()
+        self.lib.zpb_last_stage_ms(self.h, a)
+        return {"scan_ms": a[0], "parse_ms": a[1], "exec_ms": a[2], "general_ms": a[3]}
 
     @property
     def launch_count(self) -> int:
