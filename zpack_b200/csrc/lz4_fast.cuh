@@ -287,56 +287,87 @@ lz4_fast_parse_kernel(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, co
         sg.ensure(q);
         const u32 token = sg.rd(q);
         const u32 lim = (q & ~63u) + 192u;   // readable without another ensure
-        u32 p = q + 1;
-        u32 lit = token >> 4;
-        if (lit == 15) {
-            u32 b = 0;
-            do {
-                if (p >= qend) { bad = true; break; }
-                sg.ensure(p);
-                b = sg.rd(p++);
-                lit += b;
-            } while (b == 255 && lit < 0x100000u);
-            if (b == 255) bad = true;
-        }
-        if (lit > qend - p) bad = true;
-        if (!bad) {
-            const u32 d = (q - skew) | (op << 16);
-            b0 = b1; b1 = b2; b2 = b3; b3 = d;
-            ++nseq;
-            if ((nseq & 3u) == 0) *reinterpret_cast<uint4 *>(dout + nseq - 4) = make_uint4(b0, b1, b2, b3);
-            p += lit; op += lit;
-            if (op > 65536u) bad = true;
-            else if (p == qend) {
-                // final sequence: literals only.  Spec end rules (lz4_Block_format.md:108-137) as
-                // sufficient conditions for the reference's capacity-based checks (lz4.c:2055-2077,2139).
-                if (had_match && (lit < 5 || op - last_ms < 12)) bad = true;
-                fin = true;
-            } else if (p + 8 > qend) {
-                bad = true;                                   // lz4.c:2055: must have been the last
-            } else {
-                if (p + 2 > lim) sg.ensure(p);
-                u32 off = sg.rd(p) | (sg.rd(p + 1) << 8);
-                p += 2;
-                u32 ml = token & 15;
-                if (ml == 15) {
-                    u32 b = 0;
-                    do {
-                        if (p >= qend) { bad = true; break; }
-                        sg.ensure(p);
-                        b = sg.rd(p++);
-                        ml += b;
-                    } while (b == 255 && ml < 0x100000u);
-                    if (b == 255) bad = true;
+        // Common shape first, branch-free: at most one length-extension byte each, offset inside the
+        // staged window, not the block's last sequences.  Everything else takes the general walk below.
+        bool fast = false;
+        {
+            const u32 l0 = token >> 4, m0 = token & 15;
+            const bool lx = l0 == 15, mx = m0 == 15;
+            const u32 e1 = sg.rd(q + 1);                      // inside the window; ignored unless lx
+            const u32 lit = lx ? 15 + e1 : l0;
+            const u32 pq = q + (lx ? 2u : 1u) + lit;          // where the offset bytes are
+            if (!(lx && e1 == 255) && pq + 3 <= lim && pq + 8 <= qend) {
+                const u32 off = sg.rd(pq) | (sg.rd(pq + 1) << 8);
+                const u32 e2 = sg.rd(pq + 2);
+                if (!(mx && e2 == 255)) {
+                    fast = true;
+                    const u32 ml = m0 + 4 + (mx ? e2 : 0u);
+                    const u32 d = (q - skew) | (op << 16);
+                    b0 = b1; b1 = b2; b2 = b3; b3 = d;
+                    ++nseq;
+                    if ((nseq & 3u) == 0) *reinterpret_cast<uint4 *>(dout + nseq - 4) = make_uint4(b0, b1, b2, b3);
+                    op += lit;
+                    if (off > op && off - op > reach) reach = off - op;
+                    last_ms = op;
+                    had_match = true;
+                    op += ml;
+                    q = pq + (mx ? 3u : 2u);
+                    if (off == 0 || op > 65536u || q >= qend) bad = true;
                 }
-                ml += 4;
-                if (off == 0) bad = true;
-                if (off > op && off - op > reach) reach = off - op;
-                last_ms = op;
-                had_match = true;
-                op += ml;
-                if (op > 65536u || p >= qend) bad = true;
-                q = p;
+            }
+        }
+        if (!fast) {
+            u32 p = q + 1;
+            u32 lit = token >> 4;
+            if (lit == 15) {
+                u32 b = 0;
+                do {
+                    if (p >= qend) { bad = true; break; }
+                    sg.ensure(p);
+                    b = sg.rd(p++);
+                    lit += b;
+                } while (b == 255 && lit < 0x100000u);
+                if (b == 255) bad = true;
+            }
+            if (lit > qend - p) bad = true;
+            if (!bad) {
+                const u32 d = (q - skew) | (op << 16);
+                b0 = b1; b1 = b2; b2 = b3; b3 = d;
+                ++nseq;
+                if ((nseq & 3u) == 0) *reinterpret_cast<uint4 *>(dout + nseq - 4) = make_uint4(b0, b1, b2, b3);
+                p += lit; op += lit;
+                if (op > 65536u) bad = true;
+                else if (p == qend) {
+                    // final sequence: literals only.  Spec end rules (lz4_Block_format.md:108-137) as
+                    // sufficient conditions for the reference's capacity-based checks (lz4.c:2055-2077,2139).
+                    if (had_match && (lit < 5 || op - last_ms < 12)) bad = true;
+                    fin = true;
+                } else if (p + 8 > qend) {
+                    bad = true;                                   // lz4.c:2055: must have been the last
+                } else {
+                    sg.ensure(p);
+                    u32 off = sg.rd(p) | (sg.rd(p + 1) << 8);
+                    p += 2;
+                    u32 ml = token & 15;
+                    if (ml == 15) {
+                        u32 b = 0;
+                        do {
+                            if (p >= qend) { bad = true; break; }
+                            sg.ensure(p);
+                            b = sg.rd(p++);
+                            ml += b;
+                        } while (b == 255 && ml < 0x100000u);
+                        if (b == 255) bad = true;
+                    }
+                    ml += 4;
+                    if (off == 0) bad = true;
+                    if (off > op && off - op > reach) reach = off - op;
+                    last_ms = op;
+                    had_match = true;
+                    op += ml;
+                    if (op > 65536u || p >= qend) bad = true;
+                    q = p;
+                }
             }
         }
         if (bad || fin) {
@@ -435,6 +466,38 @@ struct FastExec {
     }
     // warp-wide match: out[MO + i] = out[MO + i - OF], i < ML, everything below MO final
     ZPB_DEVINL void coop_match(u32 MO, u32 OF, u32 ML, u32 lo) const {
+        if (OF == 1 && ML >= 64 && (MO & FAST_RMASK) + ML <= FAST_RING) {
+            // run of one byte (lz4.c:1917-1921 pattern case): aligned 16-byte fills
+            u32 v = rd(MO - 1, lo) * 0x01010101u;
+            u32 a = ra(MO), head = (0u - a) & 15u;
+            if ((u32)lane < head) sts8(a + lane, v);
+            a += head;
+            u32 n16 = (ML - head) >> 4;
+            for (u32 c = lane; c < n16; c += 32) sts128(a + 16 * c, make_uint4(v, v, v, v));
+            u32 donev = head + (n16 << 4);
+            if ((u32)lane < ML - donev) sts8(ra(MO) + donev + lane, v);
+            return;
+        }
+        if (MO - OF >= lo) {
+            // whole source still in the ring (the usual dependent match): no HBM select per byte
+            if (OF >= 32) {
+                // 32-byte steps never read what they write; later steps may read earlier ones
+                for (u32 b = 0; b < ML; b += 32) {
+                    const u32 i = b + lane;
+                    if (i < ML) sts8(ra(MO + i), lds8(ra(MO - OF + i)));
+                    if (OF < ML) __syncwarp();
+                }
+            } else {  // period OF < 32: byte i is byte (i mod OF) of the OF bytes before MO
+                u32 k = (u32)lane < OF ? (u32)lane : (u32)lane % OF;
+                const u32 step = 32u % OF;
+                for (u32 i = lane; i < ML; i += 32) {
+                    sts8(ra(MO + i), lds8(ra(MO - OF + k)));
+                    k += step;
+                    if (k >= OF) k -= OF;
+                }
+            }
+            return;
+        }
         if (OF >= ML) {
             for (u32 i = lane; i < ML; i += 32) sts8(ra(MO + i), rd(MO - OF + i, lo));
         } else {  // periodic with period OF: byte i is byte (i mod OF) of the OF bytes before MO
@@ -567,17 +630,21 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
             const u32 *__restrict__ dp = desc + B.desc_off;
             const u32 obase = x.done;
             const u32 bsz = B.bsz;
-            u32 dnext = (u32)lane < B.nseq ? dp[lane] : 0u;
-            for (u32 s0i = 0; s0i < B.nseq; s0i += 32) {
-                const bool have = s0i + lane < B.nseq;
-                const u32 d = dnext;
-                if (s0i + 32 < B.nseq) dnext = s0i + 32 + lane < B.nseq ? dp[s0i + 32 + lane] : 0u;
+            const u32 nseq = B.nseq;
+            // two steps of descriptors and one step of token bytes are kept in flight
+            u32 d0 = (u32)lane < nseq ? dp[lane] : 0u;
+            u32 d1 = 32u + lane < nseq ? dp[32 + lane] : 0u;
+            u32 t0 = (u32)lane < nseq ? (u32)src[d0 & 0xFFFFu] : 0u;
+            for (u32 s0i = 0; s0i < nseq; s0i += 32) {
+                const bool have = s0i + lane < nseq;
+                const u32 d = d0, t = t0;
+                d0 = d1;
+                d1 = s0i + 64 + lane < nseq ? dp[s0i + 64 + lane] : 0u;
+                t0 = s0i + 32 + lane < nseq ? (u32)src[d0 & 0xFFFFu] : 0u;
                 u32 lit = 0, lsrc = 0, off = 0, ml = 0, o = 0;
                 if (have) {
                     u32 tok = d & 0xFFFFu;
                     o = obase + (d >> 16);
-                    const u8 *tp = src + tok;
-                    u32 t = tp[0];
                     u32 p = tok + 1;
                     lit = t >> 4;
                     if (lit == 15) { u32 bb; do { bb = src[p++]; lit += bb; } while (bb == 255); }
@@ -594,6 +661,16 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
                 const u32 sz = lit + ml;
                 const u32 mo = o + lit, msrc = mo - off;
                 const u8 *__restrict__ sp = src + lsrc;
+                // short matches whose whole source is already in HBM: fetch it now (2 x 16 B cover any
+                // alignment of <= 16 bytes), park it in this lane's scratch after the literal phase
+                const u32 abase = msrc & ~15u;
+                const bool staged = have && ml > 0 && ml <= FAST_MT && msrc + ml <= x.flushed;
+                uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+                if (staged) {
+                    q0 = ldg128_coherent(x.gout + abase);
+                    if ((msrc - abase) + ml > 16) q1 = ldg128_coherent(x.gout + abase + 16);
+                }
+                bool parked = false;
                 u32 todo = __ballot_sync(0xffffffffu, have);
                 while (todo) {
                     const int first = __ffs(todo) - 1;
@@ -608,7 +685,7 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
                         todo &= ~(1u << first);
                         continue;
                     }
-                    // ---- a run of sequences that fits the ring: literals (independent), then matches in rounds
+                    // ---- a run of sequences that fits the ring: literals first (they depend on nothing) ...
                     const bool in = (seg >> lane) & 1u;
                     const int last_lane = 31 - __clz(seg);
                     const u32 seg_end = __shfl_sync(0xffffffffu, o + sz, last_lane);
@@ -636,35 +713,27 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
                             x.coop_lit(O, src + S, L);
                         }
                     }
-                    const bool has_m = in && ml > 0;
-                    const u32 abase = msrc & ~15u;
-                    const bool far_all = msrc + ml <= lo;
-                    if (has_m && msrc < lo && ml <= FAST_MT + 15u) {  // behind the ring: stage the flushed bytes
-                        u32 units = ((msrc - abase) + ml + 15u) >> 4;
-#pragma unroll
-                        for (u32 u = 0; u < 3; ++u)
-                            if (u < units && abase + 16 * u < x.flushed)
-                                sts128(x.scr_s + 16 * u, ldg128_coherent(x.gout + abase + 16 * u));
+                    if (!parked) {
+                        if (staged) { sts128(x.scr_s, q0); sts128(x.scr_s + 16, q1); }
+                        parked = true;
                     }
-                    // one-lane-per-match is possible when source and destination are linear in shared memory
+                    // ... then matches: one parallel round for everything whose source is final already
+                    // (one lane per match, linear shared-memory addresses), the rest warp-wide in order
+                    const bool has_m = in && ml > 0;
                     const bool near_lin = msrc >= lo && (msrc & FAST_RMASK) + ml <= FAST_RING;
                     const bool lane_ok = has_m && ml <= FAST_MT && (mo & FAST_RMASK) + ml <= FAST_RING &&
-                                         (far_all || near_lin);
-                    const u32 sa = far_all ? x.scr_s + (msrc - abase) : x.ra(msrc);
+                                         (staged || near_lin);
+                    const u32 sa = staged ? x.scr_s + (msrc - abase) : x.ra(msrc);
                     const u32 dm = x.ra(mo);
                     const u32 send = msrc + ml < mo ? msrc + ml : mo;   // own overlap is handled in lane order
                     __syncwarp();
-                    u32 pend = __ballot_sync(0xffffffffu, has_m);
-                    while (pend) {
+                    const u32 pend = __ballot_sync(0xffffffffu, has_m);
+                    if (pend) {
                         const int fl = __ffs(pend) - 1;
                         const u32 front = __shfl_sync(0xffffffffu, mo, fl);
-                        const bool ready = ((pend >> lane) & 1u) && (lane == fl || send <= front);
-                        const u32 rmask = __ballot_sync(0xffffffffu, ready);
-                        const bool el = ready && lane_ok;
+                        const bool el = lane_ok && (lane == fl || send <= front);
                         const u32 elmask = __ballot_sync(0xffffffffu, el);
-                        u32 cm = rmask;
-                        if (__popc(elmask) >= 3) {
-                            cm = rmask & ~elmask;
+                        if (elmask) {
                             const u32 myml = el ? ml : 0u;
                             const u32 maxml = __reduce_max_sync(0xffffffffu, myml);
                             if (!__any_sync(0xffffffffu, el && off < 4)) {
@@ -680,16 +749,28 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
                                 for (u32 i = 0; i < maxml; ++i)
                                     if (i < myml) sts8(dm + i, lds8(sa + i));
                             }
+                            __syncwarp();
                         }
-                        while (cm) {
-                            int r = __ffs(cm) - 1;
-                            cm &= cm - 1;
-                            u32 MO = __shfl_sync(0xffffffffu, mo, r), OF = __shfl_sync(0xffffffffu, off, r),
-                                ML = __shfl_sync(0xffffffffu, ml, r);
-                            x.coop_match(MO, OF, ML, lo);
+                        u32 rest = pend & ~elmask;
+                        const u32 pk = off | (ml << 16);
+                        while (rest) {
+                            int r = __ffs(rest) - 1;
+                            rest &= rest - 1;
+                            const u32 MO = __shfl_sync(0xffffffffu, mo, r), PK = __shfl_sync(0xffffffffu, pk, r);
+                            const u32 OF = PK & 0xFFFFu, ML = PK >> 16;
+                            if (ML <= 64 && OF >= ML && MO - OF >= lo) {
+                                // the common dependent case: short, source still in the ring, no self-overlap
+                                const u32 a = MO - OF + lane, dd = MO + lane;
+                                u32 v0 = 0, v1 = 0;
+                                if ((u32)lane < ML) v0 = lds8(x.ra(a));
+                                if ((u32)lane + 32 < ML) v1 = lds8(x.ra(a + 32));
+                                if ((u32)lane < ML) sts8(x.ra(dd), v0);
+                                if ((u32)lane + 32 < ML) sts8(x.ra(dd + 32), v1);
+                            } else {
+                                x.coop_match(MO, OF, ML, lo);
+                            }
+                            __syncwarp();
                         }
-                        __syncwarp();
-                        pend &= ~rmask;
                     }
                     x.done = seg_end;
                     todo &= ~seg;

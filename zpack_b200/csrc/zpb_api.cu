@@ -220,14 +220,17 @@ static cudaError_t launch_general_list(zpb_ctx *ctx, cudaStream_t s, const u8 *a
 // Expensive entries first: compressed LZ4/zstd bytes are a good proxy for sequence count;
 // stored-ish entries (ratio ~1) and raw copies are cheap per byte, so they go last.
 static void build_order(const zpb_entry *e, u64 n, u32 *order) {
-    std::iota(order, order + n, 0u);
-    auto cost = [&](u32 i) -> u64 {
+    // counting sort on a coarse cost key (descending): O(n), stable, no comparisons
+    auto key = [&](u64 i) -> u32 {
         const zpb_entry &x = e[i];
-        if (x.method == ZPB_METHOD_NONE) return x.comp_size / 16;
-        if (x.comp_size >= x.uncomp_size) return x.comp_size / 16;
-        return x.comp_size;
+        u64 c = (x.method == ZPB_METHOD_NONE || x.comp_size >= x.uncomp_size) ? x.comp_size / 16 : x.comp_size;
+        c >>= 9;  // 512-byte cost buckets
+        return c > 1023 ? 0u : 1023u - (u32)c;
     };
-    std::stable_sort(order, order + n, [&](u32 a, u32 b) { return cost(a) > cost(b); });
+    std::vector<u32> head(1025, 0);
+    for (u64 i = 0; i < n; ++i) ++head[key(i) + 1];
+    for (u32 k = 0; k < 1024; ++k) head[k + 1] += head[k];
+    for (u64 i = 0; i < n; ++i) order[head[key(i)]++] = (u32)i;
 }
 
 static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_size, u8 *d_out,
