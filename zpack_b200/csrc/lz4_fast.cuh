@@ -670,6 +670,14 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
                     q0 = ldg128_coherent(x.gout + abase);
                     if ((msrc - abase) + ml > 16) q1 = ldg128_coherent(x.gout + abase + 16);
                 }
+                else if (have && ml > 0 && msrc < x.flushed) {
+                    // longer match reaching back into flushed output: pull its lines towards L1 now, the
+                    // warp-wide copy that needs them runs later in this step
+                    u32 pe = msrc + ml < x.flushed ? msrc + ml : x.flushed;
+                    if (pe > msrc + 512) pe = msrc + 512;
+                    for (u32 a = msrc & ~127u; a < pe; a += 128)
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(x.gout + a));
+                }
                 bool parked = false;
                 u32 todo = __ballot_sync(0xffffffffu, have);
                 while (todo) {
