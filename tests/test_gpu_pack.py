@@ -1,0 +1,125 @@
+"""GPU pack path (zpb_pack_*): GPU-written LZ4 frames must be valid for the oracle's frame decoder and for
+the UNMODIFIED reference reader, round-trip bit-exactly, carry the right XXH3-64, and compress about as
+well as the reference at the same level (compressed bytes themselves are unpinned: tests/write_archive.c
+only checks return codes)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from zpack_b200 import container, corpus
+from zpack_b200 import lib as zlib
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [0, 1, 5, 12, 13, 14, 64, 1000, 4095, 65535, 65536, 65537, 131072, 200001, 262144]
+
+
+def _files(ctx, sizes, method=2, level=0, first=0):
+    bufs = [corpus.entry_bytes(first + i, s) for i, s in enumerate(sizes)]
+    f = np.zeros(len(bufs), zlib.File)
+    in_off = out_off = 0
+    for i, b in enumerate(bufs):
+        f["src_off"][i], f["size"][i] = in_off, len(b)
+        cap = ctx.pack_bound(method, len(b))
+        f["dst_off"][i], f["dst_cap"][i] = out_off, cap
+        f["method"][i], f["level"][i] = method, level
+        in_off += (len(b) + 15) & ~15
+        out_off += (cap + 15) & ~15
+    h_in = np.zeros(max(in_off, 16), np.uint8)
+    for i, b in enumerate(bufs):
+        h_in[int(f["src_off"][i]):int(f["src_off"][i]) + len(b)] = b
+    return bufs, f, h_in, max(out_off, 16)
+
+
+def _pack(ctx, sizes, host=True, **kw):
+    bufs, f, h_in, out_size = _files(ctx, sizes, **kw)
+    if host:
+        h_out = np.zeros(out_size, np.uint8)
+        comp, digest, status = ctx.pack_host(h_in, len(h_in), h_out, out_size, f)
+    else:
+        import torch
+        d_in = torch.from_numpy(h_in).cuda()
+        d_out = torch.zeros(out_size, dtype=torch.uint8, device="cuda")
+        comp, digest, status = ctx.pack_device(d_in, len(h_in), d_out, out_size, f)
+        h_out = d_out.cpu().numpy()
+    frames = [h_out[int(f["dst_off"][i]):int(f["dst_off"][i] + comp[i])].copy() for i in range(len(bufs))]
+    return bufs, frames, comp, digest, status
+
+
+@pytest.mark.parametrize("host", [True, False])
+def test_gpu_frames_decode_with_the_oracle(gpu_ctx, oracle, host):
+    bufs, frames, comp, digest, status = _pack(gpu_ctx, SIZES * 2, host=host)
+    assert (status == 0).all(), status
+    for i, (b, fr) in enumerate(zip(bufs, frames)):
+        assert len(fr) <= gpu_ctx.pack_bound(2, len(b))
+        assert bytes(fr[:6]) == bytes([0x04, 0x22, 0x4D, 0x18, 0x60, 0x40])   # B.Indep frames, 64 KB blocks
+        rc, out = oracle.lz4f_decode_port(fr, len(b))
+        assert rc == 0 and np.array_equal(out, b), (i, len(b))
+        assert int(digest[i]) == oracle.xxh3_port(b)
+    assert len(frames[0]) == 11                                                # empty file: header + EndMark
+
+
+def test_gpu_written_archive_round_trips_through_the_reference_reader(gpu_ctx, oracle, tmp_path):
+    """The validity gate of BASELINE config C3: reference zpack_read_file (and its CLI `t`) accept every entry."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not present")
+    n, size = 128, 131072
+    bufs, frames, comp, digest, status = _pack(gpu_ctx, [size] * n, host=False)
+    assert (status == 0).all()
+    names = [corpus.entry_name(i) for i in range(n)]
+    arch = container.assemble(names, frames, [size] * n, digest, [2] * n)       # offsets: host prefix sum
+    rd = oracle.RefReader(arch)
+    assert rd.count == n
+    for i in range(n):
+        rc, out = rd.read(i)
+        assert rc == 0, (i, rc)                                                 # decode OK and XXH3 verified by the reference
+        assert np.array_equal(out, bufs[i])
+    rd.close()
+    p = tmp_path / "gpu.zpk"
+    arch.tofile(p)
+    r = subprocess.run([oracle.REF_CLI, "t", str(p)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"Corrupted files: 0/{n}" in r.stdout, r.stdout[-300:]
+
+
+def test_ratio_against_the_reference_level0(gpu_ctx, oracle):
+    n, size = 256, 131072
+    bufs, frames, comp, digest, status = _pack(gpu_ctx, [size] * n, host=False)
+    assert (status == 0).all()
+    ours = float(comp.sum())
+    ref = float(sum(len(oracle.lz4f_encode_port(b, 0, independent=True)) for b in bufs))
+    ratio_ours, ratio_ref = n * size / ours, n * size / ref
+    print(f"\nLZ4 level-0 ratio on zpk-synth-v1: GPU {ratio_ours:.3f} vs reference-algorithm {ratio_ref:.3f}")
+    assert ratio_ours > 0.85 * ratio_ref
+
+
+def test_pack_then_unpack_on_gpu(gpu_ctx):
+    sizes = [131072] * 64 + SIZES
+    bufs, frames, comp, digest, status = _pack(gpu_ctx, sizes, host=False, first=100)
+    assert (status == 0).all()
+    arch = container.assemble([f"f{i}" for i in range(len(bufs))], frames, [len(b) for b in bufs], digest, [2] * len(bufs))
+    d = container.parse(arch)
+    e = d.entries()
+    out = np.zeros(int((e["dst_off"] + e["dst_cap"]).max()), np.uint8)
+    st, dg = gpu_ctx.unpack_host(arch, len(arch), out, len(out), e)
+    assert (st == 0).all(), st
+    for i, b in enumerate(bufs):
+        o = int(e["dst_off"][i])
+        assert np.array_equal(out[o:o + len(b)], b), i
+
+
+def test_none_method_and_error_statuses(gpu_ctx, oracle):
+    bufs, frames, comp, digest, status = _pack(gpu_ctx, [0, 7, 70000], method=0)
+    assert (status == 0).all()
+    for b, fr, dg in zip(bufs, frames, digest):
+        assert np.array_equal(fr, b) and int(dg) == oracle.xxh3_port(b)
+    _, _, _, _, status = _pack(gpu_ctx, [1000], method=1)          # zstd compressor: not built
+    assert list(status) == [24]
+    _, _, _, _, status = _pack(gpu_ctx, [1000], method=9)
+    assert list(status) == [19]
+    bufs, f, h_in, out_size = _files(gpu_ctx, [5000])
+    f["dst_cap"][0] = 100                                            # slot smaller than the bound
+    comp, digest, status = gpu_ctx.pack_host(h_in, len(h_in), np.zeros(out_size, np.uint8), out_size, f)
+    assert list(status) == [14]

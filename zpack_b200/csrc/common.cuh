@@ -59,7 +59,7 @@ ZPB_DEVINL void group_copy(const Group<G> &g, u8 *dst, const u8 *src, u32 n) {
         u32 head = (u32)(-(intptr_t)dst) & 15u;
         for (u32 i = g.l; i < head; i += G) dst[i] = src[i];
         dst += head; src += head; n -= head;
-        u32 chunks = n >> 4;
+        u32 chunks = (n - 4) >> 4;  // leave >= 4 bytes for the byte loop: the funnel's 5th word stays inside src[0..n)
         const u32 *s4 = reinterpret_cast<const u32 *>((uintptr_t)src & ~(uintptr_t)3);
         u32 sh = ((u32)(uintptr_t)src & 3u) * 8u;
         if (sh == 0) {
