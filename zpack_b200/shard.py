@@ -1,0 +1,47 @@
+"""Static partition of an archive's entries across the GPUs of one box.
+
+Entries are independent (own frame(s), own digest), so there is no data-path collective: every rank
+gets a contiguous range of entries (in archive order) balanced by decoded bytes, reads only the byte
+range of the archive that range touches, and writes only its own outputs.  The only cross-rank values
+are O(entries) scalars the host already owns (comp_size[] for the offset prefix sum when packing,
+status[] / digest[] when unpacking)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def partition(uncomp_size, world: int):
+    """-> list of (first, last_exclusive) per rank: contiguous, covering, balanced on sum(uncomp_size)."""
+    u = np.asarray(uncomp_size, np.float64)
+    n = len(u)
+    if world <= 1 or n == 0:
+        return [(0, n)] + [(n, n)] * max(0, world - 1)
+    cum = np.cumsum(u)
+    total = cum[-1] if n else 0.0
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r / world
+        k = int(np.searchsorted(cum, target, side="left")) + 1 if total > 0 else (n * r) // world
+        k = max(cuts[-1], min(n, k))
+        # pick the nearer boundary
+        if k > cuts[-1] + 1 and abs(cum[k - 2] - target) < abs(cum[k - 1] - target):
+            k -= 1
+        cuts.append(k)
+    cuts.append(n)
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
+def byte_range(offset, comp_size, first: int, last: int):
+    """[lo, hi) of the archive that entries [first, last) touch (what this rank copies to its GPU)."""
+    if last <= first:
+        return 0, 0
+    off = np.asarray(offset[first:last], np.uint64)
+    cs = np.asarray(comp_size[first:last], np.uint64)
+    return int(off.min()), int((off + cs).max())
+
+
+def pack_offsets(comp_size, data_start: int = 10):
+    """entry.offset for GPU-packed entries: exclusive prefix sum of comp_size from the data start
+    (header 6 + data signature 4; /root/reference/lib/zpack.h:41-42, lib/zpack_write.c:338)."""
+    c = np.asarray(comp_size, np.uint64)
+    return (np.uint64(data_start) + np.concatenate([[0], np.cumsum(c)[:-1]]).astype(np.uint64)) if len(c) else c
