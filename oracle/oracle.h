@@ -67,6 +67,10 @@ size_t orc_lz4f_bound(size_t src_len);
  * Returns ORC_OK / ORC_DECOMPRESS_FAILED / ORC_BUFFER_TOO_SMALL. */
 int orc_zstd_decode(const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap,
                     size_t *out_len);
+/* the same with a caller-owned context of orc_zstd_ctx_size() bytes (one per thread) */
+int orc_zstd_decode_ctx(void *ctx, const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap,
+                        size_t *out_len);
+size_t orc_zstd_ctx_size(void);
 
 /* One ZPack entry, exactly as zpack_read_file (lib/zpack_read.c:326-471) would treat it:
  * dispatch on method (0 none, 1 zstd, 2 lz4), decode, then XXH3 verify.  *digest gets the
