@@ -128,6 +128,8 @@ int zpb_last_kernel_ms(const zpb_ctx *ctx, float *unpack_ms, float *pack_ms);
 
 /* per-stage device time of the last unpack (ms): scan, parse, exec, general-fallback */
 int zpb_last_stage_ms(const zpb_ctx *ctx, float *ms4);
+/* device time of zstd_unpack_kernel in the last unpack (ms; 0 when the batch had no zstd entry) */
+int zpb_last_zstd_ms(const zpb_ctx *ctx, float *ms);
 /* 1 (default): LZ4 / stored entries go through the scan -> parse -> exec pipeline and only what it
  * declines reaches the general decoder; 0: general decoder for everything (A/B and test use). */
 int zpb_set_fast_path(zpb_ctx *ctx, int enabled);

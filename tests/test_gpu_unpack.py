@@ -38,7 +38,7 @@ def _unpack_all(ctx, arch, d, cap_extra=0, host=True):
     return e, status, digest, out
 
 
-@pytest.mark.parametrize("kind", ["none", "lz4"])
+@pytest.mark.parametrize("kind", ["none", "lz4", "zstd"])
 @pytest.mark.parametrize("host", [True, False])
 def test_golden_archives(gpu_ctx, golden_dir, kind, host):
     """tests/read_archive.c:23-30: 350-byte buffers, memcmp against the plaintext, digest accepted."""

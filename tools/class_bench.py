@@ -14,28 +14,28 @@ sys.path.insert(0, ROOT)
 
 
 def _pack(args):
-    cls, lo, hi, size, indep = args
+    cls, lo, hi, size, indep, method = args
     from zpack_b200 import corpus
     from oracle import oracle as O
     fr, hs = [], np.empty(hi - lo, np.uint64)
     for k, i in enumerate(range(lo, hi)):
         b = corpus.entry_bytes(4 * i + cls if cls >= 0 else i, size)
-        fr.append(O.lz4f_encode_port(b, 0, indep))
+        fr.append(O.zstd_compress_ref(b, 3) if method == 1 else O.lz4f_encode_port(b, 0, indep))
         hs[k] = O.xxh3_port(b)
     return fr, hs
 
 
-def build(cls, n, size, indep):
+def build(cls, n, size, indep, method=2):
     import multiprocessing as mp
     from zpack_b200 import container
     w = min(os.cpu_count() or 1, 64)
     step = max(1, n // (4 * w))
-    jobs = [(cls, a, min(a + step, n), size, indep) for a in range(0, n, step)]
+    jobs = [(cls, a, min(a + step, n), size, indep, method) for a in range(0, n, step)]
     with mp.get_context("fork").Pool(w) as pool:
         res = pool.map(_pack, jobs, chunksize=1)
     frames = [f for fr, _ in res for f in fr]
     hashes = np.concatenate([h for _, h in res])
-    return container.assemble([f"{i}" for i in range(n)], frames, [size] * n, hashes, [2] * n)
+    return container.assemble([f"{i}" for i in range(n)], frames, [size] * n, hashes, [method] * n)
 
 
 def main():
@@ -47,6 +47,8 @@ def main():
     ap.add_argument("--independent", action="store_true")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--fast", type=int, default=1)
+    ap.add_argument("--method", default="lz4", choices=["lz4", "zstd"],
+                    help="zstd: frames written by the unmodified reference (oracle/_ref), level 3")
     args = ap.parse_args()
     import torch
     import zpack_b200
@@ -55,7 +57,7 @@ def main():
     ctx.set_fast_path(bool(args.fast))
     names = {0: "random", 1: "text", 2: "runs", 3: "records", -1: "mixed"}
     for cls in [int(c) for c in args.classes.split(",")]:
-        arch = build(cls, args.entries, args.size, args.independent)
+        arch = build(cls, args.entries, args.size, args.independent, 1 if args.method == 'zstd' else 2)
         d = container.parse(arch)
         e = d.entries()
         out_size = int(e["dst_off"][-1] + e["dst_cap"][-1])
@@ -71,7 +73,7 @@ def main():
                     ms.append(ctx.last_kernel_ms()["unpack_ms"])
             assert (st == 0).all() and np.array_equal(dg, d.hash)
             t = float(np.median(ms))
-            print(json.dumps({"class": names[cls], "group": g, "kernel_ms": round(t, 4),
+            print(json.dumps({"method": args.method, "class": names[cls], "group": g, "kernel_ms": round(t, 4),
                               "uncomp_GBps": round(unc / t / 1e6, 1), "traffic_GBps": round((comp + unc) / t / 1e6, 1),
                               "ratio": round(unc / comp, 3), "entries": args.entries,
                               "stages": {k: round(v, 4) for k, v in ctx.last_stage_ms().items()}}), flush=True)

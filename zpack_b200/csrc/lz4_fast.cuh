@@ -38,6 +38,7 @@
 #define FE_DONE    0u   // status already final (guards, unsupported method)
 #define FE_FAST    1u   // block table filled, goes through K1/K2
 #define FE_GENERAL 2u   // handed to the general kernel
+#define FE_ZSTD    3u   // handed to the zstd kernel (zstd_decode.cuh)
 
 #define FB_STORED  1u
 #define FB_BAD     2u
@@ -106,8 +107,8 @@ __device__ __noinline__ bool fast_scan_lz4(const u8 *src, u64 n, const zpb_entry
 __global__ void __launch_bounds__(256)
 lz4_fast_scan_kernel(const u8 *__restrict__ archive, u64 asz, const zpb_entry *__restrict__ entries,
                      const u32 *__restrict__ order, u32 n, const FastAux *__restrict__ aux, FastEntry *fe,
-                     FastBlock *fb, u32 *parse_list, u32 *counters, u32 *general_list, int *status,
-                     u64 *digest) {
+                     FastBlock *fb, u32 *parse_list, u32 *counters, u32 *general_list, u32 *zstd_list,
+                     int *status, u64 *digest) {
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     u32 idx = order ? order[t] : t;
@@ -135,14 +136,18 @@ lz4_fast_scan_kernel(const u8 *__restrict__ archive, u64 asz, const zpb_entry *_
         }
     } else if (e.method == ZPB_METHOD_LZ4) {
         f.state = fast_scan_lz4(archive + e.src_off, e.comp_size, e, a, f, fb) ? FE_FAST : FE_GENERAL;
+    } else if (e.method == ZPB_METHOD_ZSTD) {
+        f.state = FE_ZSTD;                                     // guards passed: the zstd kernel decodes it
     } else {
-        f.state = FE_GENERAL;                                  // zstd / unknown: the general kernel answers
+        f.state = FE_GENERAL;                                  // unknown method: the general kernel answers
     }
     if (f.state == FE_DONE) {
         status[idx] = st;
         digest[idx] = 0;
     } else if (f.state == FE_GENERAL) {
         general_list[atomicAdd(&counters[1], 1u)] = idx;
+    } else if (f.state == FE_ZSTD) {
+        zstd_list[atomicAdd(&counters[5], 1u)] = idx;
     } else {
         for (u32 b = 0; b < f.nblocks; ++b)
             if (!(fb[a.slot_base + b].flags & FB_STORED))

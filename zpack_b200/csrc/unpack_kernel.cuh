@@ -13,7 +13,7 @@
 template <int G>
 ZPB_DEVINL void unpack_one(const Group<G> &g, const u8 *archive, u64 archive_size, u8 *out,
                            const zpb_entry &e, int *status, u64 *digest, u64 *produced_out,
-                           u32 idx) {
+                           u32 idx, u32 *zstd_list, u32 *zstd_count) {
     int st = ST_OK;
     u64 dg = 0, produced = 0;
     if (e.comp_size == 0) {
@@ -42,9 +42,9 @@ ZPB_DEVINL void unpack_one(const Group<G> &g, const u8 *archive, u64 archive_siz
         case ZPB_METHOD_LZ4:  // :396-453
             st = lz4f_decode_entry<G>(g, src, e.comp_size, dst, e.dst_cap, hs, &produced);
             break;
-        case ZPB_METHOD_ZSTD:
-            st = ST_NOT_AVAILABLE;
-            break;
+        case ZPB_METHOD_ZSTD:  // :370-390 — guards passed: queue it for zstd_unpack_kernel, which reports
+            if (g.l == 0) zstd_list[atomicAdd(zstd_count, 1u)] = idx;
+            return;
         default:
             st = ST_METHOD_INVALID;  // :459-461
         }
@@ -64,7 +64,7 @@ template <int G>
 __global__ void __launch_bounds__(256)
 unpack_kernel(const u8 *__restrict__ archive, u64 archive_size, u8 *__restrict__ out,
               const zpb_entry *__restrict__ entries, const u32 *order, u32 n, const u32 *n_ptr,
-              u32 *counter, int *status, u64 *digest, u64 *produced) {
+              u32 *counter, int *status, u64 *digest, u64 *produced, u32 *zstd_list, u32 *zstd_count) {
     Group<G> g;
     if (n_ptr) n = *n_ptr;  // device-side count: the entries the fast path handed over
     for (;;) {
@@ -74,7 +74,7 @@ unpack_kernel(const u8 *__restrict__ archive, u64 archive_size, u8 *__restrict__
         if (slot >= n) break;
         u32 idx = order ? order[slot] : slot;
         zpb_entry e = entries[idx];
-        unpack_one<G>(g, archive, archive_size, out, e, status, digest, produced, idx);
+        unpack_one<G>(g, archive, archive_size, out, e, status, digest, produced, idx, zstd_list, zstd_count);
     }
 }
 

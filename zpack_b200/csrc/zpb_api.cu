@@ -13,6 +13,7 @@
 #include "unpack_kernel.cuh"
 #include "lz4_fast.cuh"
 #include "pack_kernel.cuh"
+#include "zstd_decode.cuh"
 
 static thread_local std::string g_last_error = "";
 
@@ -58,7 +59,10 @@ struct zpb_ctx {
     int fast = 1;         // scan/parse/exec pipeline for LZ4 + stored entries (ZPB_FAST=0: general kernel only)
     float stage_ms[4] = {0, 0, 0, 0};
     DevBuf d_aux, d_fe, d_fb, d_plist, d_glist, d_fdesc;
-    cudaEvent_t evs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    DevBuf d_zlist, d_zlit;  // zstd work list, per-warp literal buffers
+    int zs_grid = 0;         // persistent grid of zstd_unpack_kernel (CTAs)
+    float zstd_ms = 0.f;
+    cudaEvent_t evs[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // descriptor / result scratch
     DevBuf d_desc, d_order, d_res, d_counter;
     PinBuf h_stage;
@@ -127,6 +131,17 @@ extern "C" zpb_ctx *zpb_create(int device) {
         g_last_error = std::string("kernel attribute setup failed: ") + cudaGetErrorString(cudaGetLastError());
         delete ctx; return nullptr;
     }
+    {
+        int per_sm = 0;
+        const int smem = (int)(ZS_WARPS * sizeof(ZstdShared));
+        if (cudaFuncSetAttribute(zstd_unpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zstd_unpack_kernel, ZS_WARPS * 32, smem) != cudaSuccess ||
+            per_sm < 1) {
+            g_last_error = std::string("zstd kernel setup failed: ") + cudaGetErrorString(cudaGetLastError());
+            delete ctx; return nullptr;
+        }
+        ctx->zs_grid = ctx->sm_count * per_sm;
+    }
     return ctx;
 }
 
@@ -136,7 +151,7 @@ extern "C" void zpb_destroy(zpb_ctx *ctx) {
     ctx->d_desc.release(); ctx->d_order.release(); ctx->d_res.release(); ctx->d_counter.release();
     ctx->d_in.release(); ctx->d_out.release(); ctx->h_stage.release();
     ctx->d_aux.release(); ctx->d_fe.release(); ctx->d_fb.release(); ctx->d_plist.release();
-    ctx->d_glist.release(); ctx->d_fdesc.release();
+    ctx->d_glist.release(); ctx->d_fdesc.release(); ctx->d_zlist.release(); ctx->d_zlit.release();
     for (auto &ev : ctx->evs) if (ev) cudaEventDestroy(ev);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -171,6 +186,12 @@ extern "C" int zpb_last_stage_ms(const zpb_ctx *ctx, float *ms4) {
     return ZPB_OK;
 }
 
+extern "C" int zpb_last_zstd_ms(const zpb_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return ZPB_E_ARG;
+    *ms = ctx->zstd_ms;
+    return ZPB_OK;
+}
+
 extern "C" int zpb_set_fast_path(zpb_ctx *ctx, int enabled) {
     if (!ctx) return ZPB_E_ARG;
     ctx->fast = enabled ? 1 : 0;
@@ -199,7 +220,7 @@ static cudaError_t launch_unpack(zpb_ctx *ctx, cudaStream_t s, const u8 *arch, u
     u64 want = (n + groups_per_cta - 1) / groups_per_cta;
     u32 grid = (u32)std::min<u64>((u64)ctx->sm_count * per_sm, std::max<u64>(want, 1));
     unpack_kernel<G><<<grid, 256, 0, s>>>(arch, asz, out, d_e, d_order, n, nullptr, d_counter, d_status,
-                                          d_digest, nullptr);
+                                          d_digest, nullptr, (u32 *)ctx->d_zlist.p, d_counter + 5);
     return cudaGetLastError();
 }
 
@@ -213,7 +234,17 @@ static cudaError_t launch_general_list(zpb_ctx *ctx, cudaStream_t s, const u8 *a
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     unpack_kernel<G><<<ctx->sm_count * per_sm, 256, 0, s>>>(arch, asz, out, d_e, d_list, 0, d_count, d_counter,
-                                                            d_status, d_digest, nullptr);
+                                                            d_status, d_digest, nullptr, (u32 *)ctx->d_zlist.p,
+                                                            (u32 *)ctx->d_counter.p + 5);
+    return cudaGetLastError();
+}
+
+// zstd entries queued by the scan / general kernel: count at counters[5], work counter at counters[6]
+static cudaError_t launch_zstd(zpb_ctx *ctx, cudaStream_t s, const u8 *arch, u8 *out, const zpb_entry *d_e,
+                               int *d_status, u64 *d_digest) {
+    u32 *cnt = (u32 *)ctx->d_counter.p;
+    zstd_unpack_kernel<<<ctx->zs_grid, ZS_WARPS * 32, ZS_WARPS * sizeof(ZstdShared), s>>>(
+        arch, out, d_e, (const u32 *)ctx->d_zlist.p, cnt + 5, cnt + 6, (u8 *)ctx->d_zlit.p, d_status, d_digest);
     return cudaGetLastError();
 }
 
@@ -249,6 +280,13 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
     if (!ctx->d_desc.ensure(desc_b) || !ctx->d_order.ensure(ord_b) || !ctx->d_res.ensure(res_b + 64) ||
         !ctx->d_counter.ensure(256) || !ctx->h_stage.ensure(desc_b + ord_b + res_b + 64 + n * sizeof(FastAux)))
         return fail(ctx, ZPB_E_NOMEM, "scratch allocation failed");
+
+    bool any_zstd = false;
+    for (u64 i = 0; i < n && !any_zstd; ++i) any_zstd = entries[i].method == ZPB_METHOD_ZSTD;
+    if (any_zstd && (!ctx->d_zlist.ensure(n * 4) ||
+                     !ctx->d_zlit.ensure((size_t)ctx->zs_grid * ZS_WARPS * ZS_LIT_SCRATCH)))
+        return fail(ctx, ZPB_E_NOMEM, "zstd scratch allocation failed");
+    ctx->zstd_ms = 0.f;
 
     u8 *hs = (u8 *)ctx->h_stage.p;
     zpb_entry *h_desc = (zpb_entry *)hs;
@@ -291,7 +329,8 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
         CK(ctx, cudaEventRecord(ctx->evs[0], s));
         lz4_fast_scan_kernel<<<(u32)((n + 255) / 256), 256, 0, s>>>(
             d_archive, archive_size, d_e, d_ord, (u32)n, (const FastAux *)ctx->d_aux.p, (FastEntry *)ctx->d_fe.p,
-            (FastBlock *)ctx->d_fb.p, (u32 *)ctx->d_plist.p, cnt, (u32 *)ctx->d_glist.p, d_status, d_digest);
+            (FastBlock *)ctx->d_fb.p, (u32 *)ctx->d_plist.p, cnt, (u32 *)ctx->d_glist.p, (u32 *)ctx->d_zlist.p,
+            d_status, d_digest);
         CK(ctx, cudaGetLastError());
         CK(ctx, cudaEventRecord(ctx->evs[1], s));
         int k1_ctas = ctx->ctas_per_sm > 0 ? ctx->ctas_per_sm : 3;
@@ -316,11 +355,17 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
         CK(ctx, ge);
         CK(ctx, cudaEventRecord(ctx->evs[4], s));
         ctx->launches += 4;
+        if (any_zstd) {
+            CK(ctx, launch_zstd(ctx, s, d_archive, d_out, d_e, d_status, d_digest));
+            ctx->launches += 1;
+        }
+        CK(ctx, cudaEventRecord(ctx->evs[5], s));
         u8 *h_res = hs + desc_b + ord_b;
         CK(ctx, cudaMemcpyAsync(h_res, ctx->d_res.p, res_b, cudaMemcpyDeviceToHost, s));
         CK(ctx, cudaStreamSynchronize(s));
-        CK(ctx, cudaEventElapsedTime(&ctx->unpack_ms, ctx->evs[0], ctx->evs[4]));
+        CK(ctx, cudaEventElapsedTime(&ctx->unpack_ms, ctx->evs[0], ctx->evs[5]));
         for (int k = 0; k < 4; ++k) CK(ctx, cudaEventElapsedTime(&ctx->stage_ms[k], ctx->evs[k], ctx->evs[k + 1]));
+        CK(ctx, cudaEventElapsedTime(&ctx->zstd_ms, ctx->evs[4], ctx->evs[5]));
         if (digest) memcpy(digest, h_res, n * sizeof(u64));
         if (status) memcpy(status, h_res + n * sizeof(u64), n * sizeof(int));
         return ZPB_OK;
@@ -335,11 +380,18 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
     }
     CK(ctx, le);
     ctx->launches += 1;
+    if (any_zstd) {
+        CK(ctx, cudaEventRecord(ctx->evs[4], s));
+        CK(ctx, launch_zstd(ctx, s, d_archive, d_out, (const zpb_entry *)ctx->d_desc.p, d_status, d_digest));
+        ctx->launches += 1;
+        CK(ctx, cudaEventRecord(ctx->evs[5], s));
+    }
     CK(ctx, cudaEventRecord(ctx->ev1, s));
     u8 *h_res = hs + desc_b + ord_b;
     CK(ctx, cudaMemcpyAsync(h_res, ctx->d_res.p, res_b, cudaMemcpyDeviceToHost, s));
     CK(ctx, cudaStreamSynchronize(s));
     CK(ctx, cudaEventElapsedTime(&ctx->unpack_ms, ctx->ev0, ctx->ev1));
+    if (any_zstd) CK(ctx, cudaEventElapsedTime(&ctx->zstd_ms, ctx->evs[4], ctx->evs[5]));
     if (digest) memcpy(digest, h_res, n * sizeof(u64));
     if (status) memcpy(status, h_res + n * sizeof(u64), n * sizeof(int));
     return ZPB_OK;

@@ -46,7 +46,7 @@ EXPORTS = [
     "zpb_abi_version", "zpb_create", "zpb_destroy", "zpb_last_error", "zpb_device_info",
     "zpb_launch_count", "zpb_unpack_device", "zpb_unpack_host", "zpb_xxh3_device", "zpb_xxh3_host",
     "zpb_pack_bound", "zpb_pack_device", "zpb_pack_host", "zpb_last_kernel_ms", "zpb_set_tuning",
-    "zpb_last_stage_ms", "zpb_set_fast_path",
+    "zpb_last_stage_ms", "zpb_set_fast_path", "zpb_last_zstd_ms",
 ]
 
 
@@ -87,6 +87,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.zpb_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.zpb_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.zpb_set_fast_path.argtypes = [vp, C.c_int]
+    lib.zpb_last_zstd_ms.argtypes = [vp, C.POINTER(C.c_float)]
     _lib = lib
     return lib
 
@@ -140,7 +141,9 @@ class Context:
     def last_stage_ms(self):
         a = (C.c_float * 4)()
         self.lib.zpb_last_stage_ms(self.h, a)
-        return {"scan_ms": a[0], "parse_ms": a[1], "exec_ms": a[2], "general_ms": a[3]}
+        z = C.c_float()
+        self.lib.zpb_last_zstd_ms(self.h, C.byref(z))
+        return {"scan_ms": a[0], "parse_ms": a[1], "exec_ms": a[2], "general_ms": a[3], "zstd_ms": z.value}
 
     @property
     def launch_count(self) -> int:
