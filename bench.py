@@ -20,6 +20,14 @@ sys.path.insert(0, ROOT)
 
 METRIC = "lz4_unpack_xxh3_verify_uncompressed_GBps"
 ENTRY_SIZE = 131072
+# BASELINE.json configs that run on one GPU: C2 (the config the metric is quoted on; default) and C4
+WORKLOADS = {
+    "c2": {"method": 2, "metric": METRIC, "entries": 65536, "kernel": "lz4_fast_exec_kernel", "stage": "exec_ms",
+           "what": "C2: LZ4 unpack + XXH3-64 verify"},
+    "c4": {"method": 1, "metric": "zstd_unpack_xxh3_verify_uncompressed_GBps", "entries": 32768,
+           "kernel": "zstd_unpack_kernel", "stage": "zstd_ms",
+           "what": "C4: zstd level-3 unpack + XXH3-64 verify (frames written by the reference's ZSTD_compress)"},
+}
 
 
 def peaks():
@@ -33,25 +41,30 @@ def peaks():
 def _pack_shard(args):
     """Worker: generate entries [lo,hi) and pack them with the CPU checker's LZ4 frame writer.
     (Archive preparation only — the reference-format writer, never part of a timed region.)"""
-    lo, hi, size, independent = args
+    lo, hi, size, independent, method = args
     from zpack_b200 import corpus
     from oracle import oracle as O
     frames, hashes = [], np.empty(hi - lo, np.uint64)
     for k, i in enumerate(range(lo, hi)):
         b = corpus.entry_bytes(i, size)
-        frames.append(O.lz4f_encode_port(b, 0, independent))
+        # zstd: the unmodified reference's one-shot compressor, level 3 (what zpack_write_files calls)
+        frames.append(O.zstd_compress_ref(b, 3) if method == 1 else O.lz4f_encode_port(b, 0, independent))
         hashes[k] = O.xxh3_port(b)
     return lo, frames, hashes
 
 
-def build_archive(n_entries, size, first=0, independent=False, workers=None):
+def build_archive(n_entries, size, first=0, independent=False, workers=None, method=2):
     """zpk-synth-v1 corpus -> ZPack archive with reference-format LZ4 frames (linked 64 KB blocks =
     what zpack_write_files emits; byte-identical to the reference's frames, tests/test_oracle.py)."""
     import multiprocessing as mp
     from zpack_b200 import container, corpus
     workers = workers or min(os.cpu_count() or 1, 64)
     step = max(1, min(256, n_entries // (workers * 4) or 1))
-    jobs = [(first + a, first + min(a + step, n_entries), size, independent) for a in range(0, n_entries, step)]
+    if method == 1:
+        from oracle import oracle as O
+        if not O.have_ref():
+            raise RuntimeError("the C4 archive is packed by oracle/_ref (the reference's zstd compressor), which is absent")
+    jobs = [(first + a, first + min(a + step, n_entries), size, independent, method) for a in range(0, n_entries, step)]
     frames, hashes = [None] * len(jobs), [None] * len(jobs)
     if workers > 1 and len(jobs) > 1:
         with mp.get_context("fork").Pool(workers) as pool:
@@ -62,7 +75,7 @@ def build_archive(n_entries, size, first=0, independent=False, workers=None):
             _, frames[j], hashes[j] = _pack_shard(job)
     payload = [f for fr in frames for f in fr]
     names = [corpus.entry_name(first + i) for i in range(n_entries)]
-    arch = container.assemble(names, payload, [size] * n_entries, np.concatenate(hashes), [2] * n_entries)
+    arch = container.assemble(names, payload, [size] * n_entries, np.concatenate(hashes), [method] * n_entries)
     return arch
 
 
@@ -104,7 +117,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ reference arm (CPU)
-def cpu_unpack_throughput(arch, d, n_sample, threads, repeat=1):
+def cpu_unpack_throughput(arch, d, n_sample, threads, repeat=1, method=2):
     """The reference's own zpack_read_file (oracle/_ref) — or the port when _ref is absent — over
     `n_sample` entries split across `threads` host threads, one dctx each (lib/zpack.h:335-341).
     The per-entry loop runs in C (oracle/ref_driver.c); Python only starts the threads."""
@@ -113,6 +126,8 @@ def cpu_unpack_throughput(arch, d, n_sample, threads, repeat=1):
     n_sample = min(n_sample, len(d))
     threads = max(1, min(threads, n_sample))
     use_ref = O.have_ref() and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_driver.so"))
+    if not use_ref and method == 1:
+        threads = 1  # the port's zstd context is a single static object
     size = int(d.uncomp_size[:n_sample].max())
     outs = [np.empty(size, np.uint8) for _ in range(threads)]
     bad = [0] * threads
@@ -125,7 +140,7 @@ def cpu_unpack_throughput(arch, d, n_sample, threads, repeat=1):
         ents = C.cast(rd.r.file_entries, C.c_void_p)
 
         def work(t):
-            bad[t] = drv.ref_unpack_range(C.byref(rd.r), ents, t, n_sample, threads, outs[t].ctypes.data, size, 2, None)
+            bad[t] = drv.ref_unpack_range(C.byref(rd.r), ents, t, n_sample, threads, outs[t].ctypes.data, size, method, None)
     else:
         lib = O.port()
         lib.orc_unpack_range.restype = C.c_long
@@ -157,21 +172,22 @@ def run_reference(args):
     from zpack_b200 import container
     cores = os.cpu_count() or 1
     n_sample = args.ref_entries
-    arch = build_archive(n_sample, ENTRY_SIZE, independent=False)
+    wl = WORKLOADS[args.workload]
+    arch = build_archive(n_sample, ENTRY_SIZE, independent=False, method=wl["method"])
     d = container.parse(arch)
     for _ in range(args.warmup):
-        cpu_unpack_throughput(arch, d, min(n_sample, 512), cores)
+        cpu_unpack_throughput(arch, d, min(n_sample, 512), cores, method=wl["method"])
     t_best, vals = None, []
     for _ in range(args.steps):
-        v, dt, kind = cpu_unpack_throughput(arch, d, n_sample, cores)
+        v, dt, kind = cpu_unpack_throughput(arch, d, n_sample, cores, method=wl["method"])
         vals.append(v)
         t_best = dt if t_best is None else min(t_best, dt)
     value = float(np.mean(vals))
-    line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+    line = {"metric": wl["metric"], "value": value, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * float(d.uncomp_size.sum()) / (value * 1e9),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "impl": "reference",
-            "config": {"workload": f"C2 sample: LZ4 unpack + XXH3 verify of {n_sample} x 128 KiB entries "
+            "config": {"workload": f"{wl['what']}, sample of {n_sample} x 128 KiB entries "
                                    "(zpk-synth-v1), reference zpack_read_file on host cores"},
             "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": kind,
                              "sample": f"{n_sample} entries x 128 KiB per step, {cores} threads, one dctx each"},
@@ -193,10 +209,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    n_per_gpu = args.entries  # weak scaling: every GPU unpacks its own shard of `entries` entries
+    wl = WORKLOADS[args.workload]
+    n_per_gpu = args.entries or wl["entries"]  # weak scaling: every GPU unpacks its own shard of `entries` entries
     t_prep = time.time()
     arch = build_archive(n_per_gpu, ENTRY_SIZE, first=rank * n_per_gpu, independent=args.independent,
-                         workers=max(1, (os.cpu_count() or 1) // world))
+                         workers=max(1, (os.cpu_count() or 1) // world), method=wl["method"])
     d = container.parse(arch)
     entries = d.entries()
     out_size = int(entries["dst_off"][-1] + entries["dst_cap"][-1])
@@ -244,9 +261,10 @@ def run_ours(args):
     assert (status == 0).all() and np.array_equal(digest, d.hash)
 
     # end-to-end through the host-buffer C-ABI call (pinned host archive -> H2D -> kernel -> D2H output)
-    e2e = None
+    e2e, e2e_verify = None, None
     if args.e2e:
         h_arch_np, h_out_np = h_arch.numpy(), h_out.numpy()
+        h_out_np[:] = 0
         ctx.unpack_host(h_arch_np, len(arch), h_out_np, out_size, entries)
         barrier()
         t0 = time.perf_counter()
@@ -254,15 +272,31 @@ def run_ours(args):
             st2, dg2 = ctx.unpack_host(h_arch_np, len(arch), h_out_np, out_size, entries)
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-        assert (st2 == 0).all()
+        assert (st2 == 0).all() and np.array_equal(dg2, d.hash)
+        # the host copy really holds the decoded bytes: spot-check entries against the device-resident result
+        for i in (0, len(entries) // 2, len(entries) - 1):
+            o, sz = int(entries["dst_off"][i]), int(entries["uncomp_size"][i])
+            assert np.array_equal(h_out_np[o:o + sz], d_out[o:o + sz].cpu().numpy()), "e2e output mismatch"
         e2e = e2e_s
+        # verdict-only variant (`zpack t`): same call, entries flagged ZPB_F_DISCARD -> no D2H of the bytes
+        ev = entries.copy()
+        ev["flags"] |= 2
+        ctx.unpack_host(h_arch_np, len(arch), h_out_np, out_size, ev)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            st3, dg3 = ctx.unpack_host(h_arch_np, len(arch), h_out_np, out_size, ev)
+        torch.cuda.synchronize()
+        e2e_verify = (time.perf_counter() - t0) / args.e2e_steps
+        assert (st3 == 0).all() and np.array_equal(dg3, d.hash)
     clocks = sampler.stop() if rank == 0 else None
 
     stages = {k: float(np.mean([s[k] for s in stage_ms])) for k in stage_ms[0]}
-    t = torch.tensor([ms_total, float(np.mean(kernel_ms)), e2e or 0.0, stages["exec_ms"]], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms_total, float(np.mean(kernel_ms)), e2e or 0.0, stages[wl["stage"]], e2e_verify or 0.0],
+                     dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, all_kern_ms, e2e_s, kern_ms = [float(x) for x in t.cpu()]
+    ms_total, all_kern_ms, e2e_s, kern_ms, e2e_verify_s = [float(x) for x in t.cpu()]
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -271,29 +305,38 @@ def run_ours(args):
         algo_bytes = comp_bytes + uncomp_bytes
         achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
         cores = os.cpu_count() or 1
-        line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        line = {"metric": wl["metric"], "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": f"C2: LZ4 unpack + XXH3-64 verify, {n_per_gpu} entries x 128 KiB per GPU "
-                                       f"({uncomp_bytes / 2**30:.2f} GiB uncompressed, ratio {uncomp_bytes / comp_bytes:.3f}), "
-                                       f"zpk-synth-v1, {'independent' if args.independent else 'reference-format linked'} 64 KB blocks",
+                "config": {"workload": f"{wl['what']}, {n_per_gpu} entries x 128 KiB per GPU "
+                                       f"({uncomp_bytes / 2**30:.2f} GiB uncompressed, ratio {uncomp_bytes / comp_bytes:.3f}), zpk-synth-v1"
+                                       + (f", {'independent' if args.independent else 'reference-format linked'} 64 KB blocks"
+                                          if wl["method"] == 2 else ""),
                            "entries_per_gpu": n_per_gpu, "entry_bytes": ENTRY_SIZE, "sharding": f"entries x{world}, no collective",
                            "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)",
-                           "pipeline": "scan -> parse -> exec (+ general fallback), 4 launches per step", "archive_prep_s": round(prep_s, 1)},
+                           "pipeline": ("scan -> parse -> exec (+ general fallback), 4 launches per step" if wl["method"] == 2
+                                        else "scan -> zstd_unpack_kernel (warp per entry), 5 launches per step"),
+                           "archive_prep_s": round(prep_s, 1)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                             "kernel": "lz4_fast_exec_kernel", "kernel_ms": kern_ms,
+                             "kernel": wl["kernel"], "kernel_ms": kern_ms,
                              "algorithmic_bytes_per_launch": algo_bytes,
                              "all_kernels_ms": all_kern_ms, "all_kernels_frac": algo_bytes / (all_kern_ms * 1e-3) / 1e9 / peak,
                              "stages_ms": stages},
                 "gpu_launches": int(launches), "clocks": clocks}
         if args.e2e:
             line["e2e"] = {"value": world * uncomp_bytes / e2e_s / 1e9, "unit": "GB/s",
-                           "h2d_bytes_per_step": comp_bytes + entries.nbytes, "d2h_bytes_per_step": uncomp_bytes + 12 * len(entries)}
+                           "h2d_bytes_per_step": comp_bytes + entries.nbytes, "d2h_bytes_per_step": uncomp_bytes + 12 * len(entries),
+                           "how": "zpb_unpack_host, pinned host buffers: chunked H2D / kernels / D2H of every decoded byte, "
+                                  "overlapped on 3 streams; PCIe-bound"}
+            line["e2e_verify_only"] = {"value": world * uncomp_bytes / e2e_verify_s / 1e9, "unit": "GB/s",
+                                       "h2d_bytes_per_step": comp_bytes + entries.nbytes, "d2h_bytes_per_step": 12 * len(entries),
+                                       "how": "same call with ZPB_F_DISCARD (the `zpack t` integrity test): status + digest come back, "
+                                              "decoded bytes stay on the device"}
         if not args.no_cpu:
             n_s = min(args.cpu_entries, len(d))
-            v, dt, kind = cpu_unpack_throughput(arch, d, n_s, cores)
-            v1, dt1, _ = cpu_unpack_throughput(arch, d, min(n_s, 2048), 1)
+            v, dt, kind = cpu_unpack_throughput(arch, d, n_s, cores, method=wl["method"])
+            v1, dt1, _ = cpu_unpack_throughput(arch, d, min(n_s, 2048), 1, method=wl["method"])
             line["cpu_baseline"] = {"value": v, "unit": "GB/s", "cores": cores, "kind": kind,
                                     "sample": f"first {n_s} entries of the same archive, {cores} threads; "
                                               f"single-thread: {v1:.3f} GB/s"}
@@ -309,7 +352,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--entries", type=int, default=65536, help="entries per GPU (C2: 65536 x 128 KiB = 8 GiB)")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS),
+                    help="c2 (default): the config BASELINE.json's metric is quoted on; c4: zstd level-3 unpack")
+    ap.add_argument("--entries", type=int, default=0, help="entries per GPU (default: C2 65536 / C4 32768, x 128 KiB)")
     ap.add_argument("--independent", action="store_true", help="archive with B.Indep=1 frames (what the GPU packer writes)")
     ap.add_argument("--group", type=int, default=0)
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")

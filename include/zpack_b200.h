@@ -67,6 +67,8 @@ typedef struct zpb_entry {
 } zpb_entry;
 
 #define ZPB_F_NO_VERIFY 1u  /* compute the digest but do not compare it (raw / hash-only use) */
+#define ZPB_F_DISCARD   2u  /* zpb_unpack_host only: decode + verify on the device, do not copy the bytes back —
+                             * the archive integrity test (`zpack t`, programs/commands.c) needs the verdict only */
 
 /* One file to pack: the hot-path view of zpack_file (lib/zpack.h:125-134). */
 typedef struct zpb_file {
@@ -99,7 +101,9 @@ int zpb_unpack_device(zpb_ctx *ctx, const uint8_t *d_archive, uint64_t archive_s
                       int32_t *status, uint64_t *digest, void *stream);
 
 /* Same with host buffers: copies [lo,hi) of the archive that the entries touch to the device,
- * unpacks, copies each entry's uncomp_size bytes back into h_out + dst_off. */
+ * unpacks, copies each entry's uncomp_size bytes back into h_out + dst_off.  Batches of more than a few
+ * hundred MB are pipelined in chunks over several streams (H2D, kernels and D2H of different chunks
+ * overlap); pinned host buffers are needed for the copies to be asynchronous. */
 int zpb_unpack_host(zpb_ctx *ctx, const uint8_t *h_archive, uint64_t archive_size,
                     uint8_t *h_out, uint64_t out_size, const zpb_entry *entries, uint64_t n,
                     int32_t *status, uint64_t *digest);

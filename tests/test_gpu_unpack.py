@@ -207,3 +207,44 @@ def test_full_size_property_roundtrip(gpu_ctx, oracle):
     assert (status == 0).all()
     assert np.array_equal(digest, hashes)
     assert oracle.xxh3_port(out[:n * size]) == oracle.xxh3_port(np.concatenate(bufs))
+
+
+def test_pipelined_host_path_and_discard_flag(oracle, monkeypatch):
+    """zpb_unpack_host cuts big batches into chunks dealt to worker sub-contexts (H2D / kernels / D2H of
+    different chunks overlap).  Force tiny chunks so that a test-sized batch takes that path; results must be
+    identical to the single-shot path, in the caller's entry order.  ZPB_F_DISCARD keeps the bytes on the
+    device (the `zpack t` case): verdicts and digests still come back, the host buffer stays untouched."""
+    import zpack_b200
+    monkeypatch.setenv("ZPB_HOST_CHUNK_MB", "1")
+    monkeypatch.setenv("ZPB_HOST_WORKERS", "3")
+    ctx = zpack_b200.Context(0)
+    try:
+        n = 96
+        sizes = [131072 if i % 5 else 70001 for i in range(n)]
+        bufs = [corpus.entry_bytes(i, s) for i, s in enumerate(sizes)]
+        payload = [oracle.lz4f_encode_port(b, 0, independent=bool(i & 1)) for i, b in enumerate(bufs)]
+        hashes = np.array([oracle.xxh3_port(b) for b in bufs], np.uint64)
+        arch = container.assemble([f"{i}" for i in range(n)], payload, sizes, hashes, [2] * n)
+        d = container.parse(arch)
+        e = d.entries()
+        e["hash"][7] ^= np.uint64(1)
+        perm = np.random.default_rng(3).permutation(n)          # caller order != archive order
+        ep = np.ascontiguousarray(e[perm])
+        out_size = int((e["dst_off"] + e["dst_cap"]).max())
+        out = np.zeros(out_size, np.uint8)
+        status, digest = ctx.unpack_host(arch, len(arch), out, out_size, ep)
+        want = np.zeros(n, np.int32)
+        want[7] = 15
+        assert np.array_equal(status, want[perm])
+        assert np.array_equal(digest, hashes[perm])
+        for i, b in enumerate(bufs):
+            o = int(e["dst_off"][i])
+            assert np.array_equal(out[o:o + len(b)], b), i
+        ev = ep.copy()
+        ev["flags"] |= zlib.F_DISCARD
+        out2 = np.full(out_size, 0xEE, np.uint8)
+        status, digest = ctx.unpack_host(arch, len(arch), out2, out_size, ev)
+        assert np.array_equal(status, want[perm]) and np.array_equal(digest, hashes[perm])
+        assert (out2 == 0xEE).all()
+    finally:
+        ctx.close()

@@ -77,6 +77,14 @@ def main():
                               "uncomp_GBps": round(unc / t / 1e6, 1), "traffic_GBps": round((comp + unc) / t / 1e6, 1),
                               "ratio": round(unc / comp, 3), "entries": args.entries,
                               "stages": {k: round(v, 4) for k, v in ctx.last_stage_ms().items()}}), flush=True)
+            if hasattr(ctx.lib, "zpb_debug_zstd_profile"):  # developer build (-DZPB_ZS_PROFILE)
+                import ctypes as C
+                a = (C.c_uint64 * 8)()
+                ctx.lib.zpb_debug_zstd_profile(a)
+                tot = float(sum(a)) or 1.0
+                ph = ["literals", "seq_tables", "seq_decode", "exec_lit", "exec_par", "exec_order", "hash", "other"]
+                print(json.dumps({"zstd_phase_share": {p: round(a[i] / tot, 3) for i, p in enumerate(ph)},
+                                  "Mcycles_per_entry": round(tot / (args.reps + 2) / args.entries / 1e6, 3)}), flush=True)
     ctx.close()
 
 

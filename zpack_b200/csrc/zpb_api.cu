@@ -7,6 +7,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/zpack_b200.h"
@@ -68,6 +69,10 @@ struct zpb_ctx {
     PinBuf h_stage;
     // staging arenas for the *_host entry points
     DevBuf d_in, d_out;
+    // pipelined host path: private sub-contexts (own stream + scratch), one per worker thread
+    std::vector<zpb_ctx *> workers;
+    int host_workers = 3;              // ZPB_HOST_WORKERS
+    u64 host_chunk_bytes = 256u << 20; // decoded bytes per pipeline chunk (ZPB_HOST_CHUNK_MB)
 };
 
 #define CK(ctx, call)                                                                      \
@@ -122,6 +127,8 @@ extern "C" zpb_ctx *zpb_create(int device) {
     }
     if (const char *s = getenv("ZPB_CTAS_PER_SM")) ctx->ctas_per_sm = atoi(s);
     if (const char *s = getenv("ZPB_FAST")) ctx->fast = atoi(s);
+    if (const char *s = getenv("ZPB_HOST_WORKERS")) ctx->host_workers = std::max(1, std::min(8, atoi(s)));
+    if (const char *s = getenv("ZPB_HOST_CHUNK_MB")) ctx->host_chunk_bytes = (u64)std::max(1, atoi(s)) << 20;
     for (auto &ev : ctx->evs)
         if (cudaEventCreate(&ev) != cudaSuccess) { g_last_error = "event setup failed"; delete ctx; return nullptr; }
     if (cudaFuncSetAttribute(lz4_fast_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -147,6 +154,8 @@ extern "C" zpb_ctx *zpb_create(int device) {
 
 extern "C" void zpb_destroy(zpb_ctx *ctx) {
     if (!ctx) return;
+    for (zpb_ctx *w : ctx->workers) zpb_destroy(w);
+    ctx->workers.clear();
     cudaSetDevice(ctx->device);
     ctx->d_desc.release(); ctx->d_order.release(); ctx->d_res.release(); ctx->d_counter.release();
     ctx->d_in.release(); ctx->d_out.release(); ctx->h_stage.release();
@@ -191,6 +200,15 @@ extern "C" int zpb_last_zstd_ms(const zpb_ctx *ctx, float *ms) {
     *ms = ctx->zstd_ms;
     return ZPB_OK;
 }
+
+#ifdef ZPB_ZS_PROFILE
+// developer build only: read and clear the per-phase cycle counters of zstd_unpack_kernel
+extern "C" int zpb_debug_zstd_profile(unsigned long long *out8) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(out8, g_zs_prof, sizeof z) != cudaSuccess) return ZPB_E_CUDA;
+    return cudaMemcpyToSymbol(g_zs_prof, z, sizeof z) == cudaSuccess ? ZPB_OK : ZPB_E_CUDA;
+}
+#endif
 
 extern "C" int zpb_set_fast_path(zpb_ctx *ctx, int enabled) {
     if (!ctx) return ZPB_E_ARG;
@@ -407,11 +425,10 @@ extern "C" int zpb_unpack_device(zpb_ctx *ctx, const uint8_t *d_archive, uint64_
     return unpack_device_impl(ctx, d_archive, archive_size, d_out, out_size, entries, n, status, digest, s);
 }
 
-extern "C" int zpb_unpack_host(zpb_ctx *ctx, const uint8_t *h_archive, uint64_t archive_size,
-                               uint8_t *h_out, uint64_t out_size, const zpb_entry *entries,
-                               uint64_t n, int32_t *status, uint64_t *digest) {
-    if (!ctx || (!entries && n) || (!h_archive && archive_size) || (!h_out && out_size))
-        return fail(ctx, ZPB_E_ARG, "null argument");
+// One chunk, one stream: H2D of the touched archive range -> kernels -> D2H of every entry's output.
+static int unpack_host_chunk(zpb_ctx *ctx, const uint8_t *h_archive, uint64_t archive_size,
+                             uint8_t *h_out, uint64_t out_size, const zpb_entry *entries,
+                             uint64_t n, int32_t *status, uint64_t *digest) {
     if (n == 0) return ZPB_OK;
     CK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
@@ -449,7 +466,8 @@ extern "C" int zpb_unpack_host(zpb_ctx *ctx, const uint8_t *h_archive, uint64_t 
     std::vector<u32> by_dst;
     by_dst.reserve(n);
     for (u64 i = 0; i < n; ++i)
-        if (entries[i].comp_size && rel[i].src_off != ~0ull && entries[i].dst_cap >= entries[i].uncomp_size)
+        if (entries[i].comp_size && rel[i].src_off != ~0ull && entries[i].dst_cap >= entries[i].uncomp_size &&
+            !(entries[i].flags & ZPB_F_DISCARD))
             by_dst.push_back((u32)i);
     std::sort(by_dst.begin(), by_dst.end(), [&](u32 a, u32 b) { return entries[a].dst_off < entries[b].dst_off; });
     size_t k = 0;
@@ -468,6 +486,75 @@ extern "C" int zpb_unpack_host(zpb_ctx *ctx, const uint8_t *h_archive, uint64_t 
         k = m;
     }
     CK(ctx, cudaStreamSynchronize(s));
+    return ZPB_OK;
+}
+
+// Host buffers in, host buffers out.  Large batches are cut into chunks of ~host_chunk_bytes decoded bytes
+// (entries sorted by archive offset, so a chunk's compressed bytes are one contiguous H2D) and dealt to
+// `host_workers` threads, each driving a private sub-context: while one chunk's kernels run, the next
+// chunk's archive range is on its way in and the previous chunk's output on its way out (PCIe is full
+// duplex).  Small batches take the single-shot path.
+extern "C" int zpb_unpack_host(zpb_ctx *ctx, const uint8_t *h_archive, uint64_t archive_size,
+                               uint8_t *h_out, uint64_t out_size, const zpb_entry *entries,
+                               uint64_t n, int32_t *status, uint64_t *digest) {
+    if (!ctx || (!entries && n) || (!h_archive && archive_size) || (!h_out && out_size))
+        return fail(ctx, ZPB_E_ARG, "null argument");
+    if (n == 0) return ZPB_OK;
+    u64 total = 0;
+    for (u64 i = 0; i < n; ++i) total += entries[i].comp_size ? entries[i].uncomp_size : 0;
+    const int W = ctx->host_workers;
+    if (W <= 1 || total < 2 * ctx->host_chunk_bytes)
+        return unpack_host_chunk(ctx, h_archive, archive_size, h_out, out_size, entries, n, status, digest);
+
+    // ---- chunks over the entries in archive order
+    std::vector<u32> by_src(n);
+    std::iota(by_src.begin(), by_src.end(), 0u);
+    std::sort(by_src.begin(), by_src.end(), [&](u32 a, u32 b) { return entries[a].src_off < entries[b].src_off; });
+    std::vector<u64> cuts{0};
+    u64 acc = 0;
+    for (u64 k = 0; k < n; ++k) {
+        acc += entries[by_src[k]].comp_size ? entries[by_src[k]].uncomp_size : 0;
+        if (acc >= ctx->host_chunk_bytes && k + 1 < n) { cuts.push_back(k + 1); acc = 0; }
+    }
+    cuts.push_back(n);
+    const size_t nchunks = cuts.size() - 1;
+    while ((int)ctx->workers.size() < W) {
+        zpb_ctx *w = zpb_create(ctx->device);
+        if (!w) return fail(ctx, ZPB_E_CUDA, "pipeline sub-context creation failed");
+        w->fast = ctx->fast; w->group = ctx->group; w->ctas_per_sm = ctx->ctas_per_sm;
+        ctx->workers.push_back(w);
+    }
+    std::vector<int> rcs(W, ZPB_OK);
+    std::vector<std::string> errs(W);
+    auto body = [&](int t) {
+        zpb_ctx *w = ctx->workers[t];
+        w->fast = ctx->fast; w->group = ctx->group; w->ctas_per_sm = ctx->ctas_per_sm;
+        std::vector<zpb_entry> sub;
+        std::vector<int32_t> st;
+        std::vector<u64> dg;
+        for (size_t c = t; c < nchunks; c += W) {
+            const u64 a = cuts[c], b = cuts[c + 1], m = b - a;
+            sub.resize(m); st.resize(m); dg.resize(m);
+            for (u64 k = 0; k < m; ++k) sub[k] = entries[by_src[a + k]];
+            int rc = unpack_host_chunk(w, h_archive, archive_size, h_out, out_size, sub.data(), m, st.data(), dg.data());
+            if (rc != ZPB_OK) { rcs[t] = rc; errs[t] = w->err; return; }
+            for (u64 k = 0; k < m; ++k) {
+                if (status) status[by_src[a + k]] = st[k];
+                if (digest) digest[by_src[a + k]] = dg[k];
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < W; ++t) th.emplace_back(body, t);
+    body(0);
+    for (auto &x : th) x.join();
+    u64 launches = 0;
+    float ms = 0.f;
+    for (zpb_ctx *w : ctx->workers) { launches += w->launches; w->launches = 0; ms += w->unpack_ms; }
+    ctx->launches += launches;
+    ctx->unpack_ms = ms;
+    for (int t = 0; t < W; ++t)
+        if (rcs[t] != ZPB_OK) return fail(ctx, rcs[t], errs[t].c_str());
     return ZPB_OK;
 }
 

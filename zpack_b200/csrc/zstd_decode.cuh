@@ -54,16 +54,32 @@ struct ZWarp {
     void sync() const {}
     template <typename T> T bcast(T v, int) const { return v; }
 };
+#define ZS_TICK(w, k) do { } while (0)
 #else
 #include "common.cuh"
 #include "xxh3.cuh"
 #define ZS_CONST __device__ __constant__
 ZPB_DEVINL u32 zs_funnel_r(u32 lo, u32 hi, u32 sh) { return __funnelshift_r(lo, hi, sh); }
 ZPB_DEVINL int zs_highbit(u32 v) { return 31 - __clz(v); }
+#ifdef ZPB_ZS_PROFILE
+// developer build only (tools/zs_profile.sh): cycles per phase, summed over warps (lane 0's clock)
+__device__ unsigned long long g_zs_prof[8];
+#define ZS_TICK(w, k)                                                                        \
+    do {                                                                                     \
+        long long now_ = clock64();                                                          \
+        if ((w).l == 0) atomicAdd(&g_zs_prof[k], (unsigned long long)(now_ - (w).t_last));   \
+        (w).t_last = now_;                                                                   \
+    } while (0)
+#else
+#define ZS_TICK(w, k) do { } while (0)
+#endif
 struct ZWarp {
     static constexpr int W = 32;
     int l;
     Group<32> g;
+#ifdef ZPB_ZS_PROFILE
+    mutable long long t_last = 0;
+#endif
     ZPB_DEVINL ZWarp() : l(threadIdx.x & 31) {}
     ZPB_DEVINL void sync() const { __syncwarp(); }
     template <typename T> ZPB_DEVINL T bcast(T v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
@@ -82,9 +98,14 @@ struct ZWarp {
 #define ZS_ERR (-1)
 #define ZS_LIT_SCRATCH (ZS_BLOCK_MAX + 64u)  // per-warp literal buffer in global memory
 
+struct ZsCell { u32 x, y; };
+
 // Per-warp decoder state in shared memory.
 struct ZstdShared {
-    u32 fse[1280];   // LL [0,512) | OF [512,768) | ML [768,1280): base | sym << 16 | nbits << 24
+    // LL [0,512) | OF [512,768) | ML [768,1280).  One 8-byte cell carries everything a sequence needs from a
+    // state (the layout idea of ZSTD_seqSymbol, zstd_decompress_block.h): x = next-state base | nbits << 16 |
+    // extra bits << 24, y = base value (OF: 1 << code, so that value = y + extra bits in all three cases).
+    ZsCell fse[1280];
     u32 wfse[64];    // FSE table of the Huffman weights (tableLog <= 6)
     u16 huf[4096];   // sym | nbits << 8, indexed by the next huf_log bits
     u32 seq_ll[ZS_BATCH], seq_ml[ZS_BATCH], seq_off[ZS_BATCH];
@@ -97,7 +118,6 @@ struct ZstdShared {
     u32 huf_log;
     u32 rep[3];
     u32 huf_valid, seq_valid;
-    u32 mask_longlit, mask_par, mask_order;  // batch classification (bit j = sequence j)
 };
 
 ZS_CONST short ZS_LL_DEF[36] = {4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2,
@@ -136,7 +156,13 @@ struct ZsRBits {
     u64 win;
     int wpos;
 };
-ZPB_DEVINL u32 zs_rb_word(const ZsRBits &b, u32 i) { return i <= b.last_word ? b.w[i] : 0u; }
+ZPB_DEVINL u32 zs_rb_word(const ZsRBits &b, u32 i) {
+#ifdef ZPB_HOST_SIM
+    return i <= b.last_word ? b.w[i] : 0u;
+#else
+    return i <= b.last_word ? __ldg(b.w + i) : 0u;  // the archive is read-only for the whole kernel
+#endif
+}
 ZPB_DEVINL void zs_rb_refill(ZsRBits &b) {  // window <- stream bits [left-64, left), zeros below bit 0
     int pos = b.left - 64;
     u32 p = pos < 0 ? 0u : (u32)pos;
@@ -166,6 +192,20 @@ ZPB_DEVINL u32 zs_rb_read(ZsRBits &b, u32 n) {  // n <= 32
     return (u32)(b.win >> (u32)(b.left - b.wpos)) & (u32)((1ull << n) - 1ull);
 }
 
+// Field of n (<= 32) bits that starts c (< 64) bits below the top of the top-aligned 64-bit value (hi:lo);
+// n == 0 gives 0.  All six fields of a sequence are cut from one window with independent shifts.
+ZPB_DEVINL u32 zs_field(u32 hi, u32 lo, u32 c, u32 n) {
+#ifdef ZPB_HOST_SIM
+    u64 v = (((u64)hi << 32) | lo) << c;
+    return n ? (u32)(v >> (64 - n)) : 0u;
+#else
+    u32 top = c < 32 ? __funnelshift_l(lo, hi, c) : lo << (c - 32);  // bits [c, c+32) below the top
+    u32 r;
+    asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(top), "r"(32u - n));   // PTX clamps a shift of 32 to "all out"
+    return r;
+#endif
+}
+
 // ------------------------------------------------------------------------------------ copies
 // cooperative forward copy, ranges not overlapping
 ZPB_DEVINL void zs_copy(const ZWarp &w, u8 *dst, const u8 *src, u32 n) {
@@ -189,6 +229,18 @@ ZPB_DEVINL void zs_fill(const ZWarp &w, u8 *dst, u32 v, u64 n) {
     }
 #endif
     for (u64 k = i + w.l; k < n; k += ZWarp::W) dst[k] = (u8)v;
+}
+// One lane copies n bytes, ranges not overlapping.  All loads of a 16-byte piece are issued before its
+// stores, so a piece costs one memory round trip instead of one per byte.
+ZPB_DEVINL void zs_lane_copy(u8 *d, const u8 *s, u32 n) {
+    for (u32 base = 0; base < n; base += 16) {
+        u32 m = n - base;
+        u8 t[16];
+#pragma unroll
+        for (u32 k = 0; k < 16; ++k) if (k < m) t[k] = s[base + k];
+#pragma unroll
+        for (u32 k = 0; k < 16; ++k) if (k < m) d[base + k] = t[k];
+    }
 }
 // match copy (ZSTD_execSequence, zstd_decompress_block.c:804-893): source d - off, may overlap
 ZPB_DEVINL void zs_match(const ZWarp &w, u8 *d, u32 off, u32 ml) {
@@ -277,24 +329,69 @@ ZPB_DEVINL int zs_fse_build(u32 *cell, u16 *next, const NormT *norm, int max_sym
     return 0;
 }
 
+// extra bits / base value of a sequence code (which: 0 LL, 1 OF, 2 ML)
+ZPB_DEVINL void zs_code_info(u32 which, u32 sym, u32 *eb, u32 *bv) {
+    if (which == 0) { *eb = ZS_LL_BITS[sym]; *bv = ZS_LL_BASE[sym]; }
+    else if (which == 1) { *eb = sym; *bv = 1u << sym; }
+    else { *eb = ZS_ML_BITS[sym]; *bv = ZS_ML_BASE[sym]; }
+}
+
+// Sequence decode table from normalized counts, 8-byte cells; serial.  The symbol spread goes to a u32
+// staging area in the upper half of the table's own storage and is converted in place, ascending
+// (cell u is written at words 2u, 2u+1 < size + u', the staging word of any cell u' > u not yet read).
+template <typename NormT>
+ZPB_DEVINL int zs_fse_build_seq(ZsCell *cell, u16 *next, const NormT *norm, int max_sym, int log, u32 which) {
+    int size = 1 << log, high = size - 1;
+    u32 *stage = reinterpret_cast<u32 *>(cell) + size;
+    for (int s = 0; s <= max_sym; ++s) {
+        if (norm[s] == -1) { stage[high--] = (u32)s; next[s] = 1; }
+        else next[s] = (u16)norm[s];
+    }
+    int step = (size >> 1) + (size >> 3) + 3, mask = size - 1, pos = 0;
+    for (int s = 0; s <= max_sym; ++s)
+        for (int i = 0; i < norm[s]; ++i) {
+            stage[pos] = (u32)s;
+            do pos = (pos + step) & mask; while (pos > high);
+        }
+    if (pos != 0) return ZS_ERR;
+    for (int u = 0; u < size; ++u) {
+        u32 s = stage[u];
+        u32 n = next[s]++;
+        u32 nb = (u32)log - (u32)zs_highbit(n);
+        u32 eb, bv;
+        zs_code_info(which, s, &eb, &bv);
+        ZsCell c;
+        c.x = (((n << nb) - (u32)size) & 0xFFFFu) | (nb << 16) | (eb << 24);
+        c.y = bv;
+        cell[u] = c;
+    }
+    return 0;
+}
+
 // one of the three sequence tables (zstd_decompress_block.c:529-575); lane 0. Returns bytes used.
 ZPB_DEVINL int zs_seq_table(ZstdShared &S, u32 base, u32 which, int mode, const u8 *src, u32 len, int max_sym,
                             int max_log, const short *def, int def_n, int def_log) {
     switch (mode) {
     case 0:
-        if (zs_fse_build(S.fse + base, S.next, def, def_n - 1, def_log)) return ZS_ERR;
+        if (zs_fse_build_seq(S.fse + base, S.next, def, def_n - 1, def_log, which)) return ZS_ERR;
         S.log[which] = (u32)def_log;
         return 0;
-    case 1:
+    case 1: {
         if (len == 0 || (int)src[0] > max_sym) return ZS_ERR;
-        S.fse[base] = (u32)src[0] << 16;
+        u32 eb, bv;
+        zs_code_info(which, src[0], &eb, &bv);
+        ZsCell c;
+        c.x = eb << 24;
+        c.y = bv;
+        S.fse[base] = c;
         S.log[which] = 0;
         return 1;
+    }
     case 2: {
         int ms = max_sym, log;
         int hs = zs_read_ncount(src, len, S.norm, &ms, &log);
         if (hs < 0 || log > max_log) return ZS_ERR;
-        if (zs_fse_build(S.fse + base, S.next, S.norm, ms, log)) return ZS_ERR;
+        if (zs_fse_build_seq(S.fse + base, S.next, S.norm, ms, log, which)) return ZS_ERR;
         S.log[which] = (u32)log;
         return hs;
     }
@@ -484,6 +581,50 @@ ZPB_DEVINL int zs_literals(const ZWarp &w, ZstdShared &S, const u8 *src, u32 len
     return (int)(lh + cs);
 }
 
+// ------------------------------------------------------------------------------------ batch scan
+// S.seq_ll/ml/off[0..cnt) -> S.seq_out / S.seq_lit (exclusive prefix sums), bounds checks, and the three
+// execution classes.  `room` = output bytes left, `hist` = bytes of this frame already produced.
+ZPB_DEVINL int zs_scan_batch(const ZWarp &w, ZstdShared &S, u32 cnt, u32 lit_pos, u32 lit_size, u64 room, u64 hist,
+                             u32 *m_long, u32 *m_par, u32 *m_order, u32 *batch_out, u32 *batch_lit) {
+#ifdef ZPB_HOST_SIM
+    u32 out = 0, lp = 0, ml_ = 0, mp_ = 0, mo_ = 0;
+    for (u32 j = 0; j < cnt; ++j) {
+        u32 ll = S.seq_ll[j], ml = S.seq_ml[j], off = S.seq_off[j];
+        if (ll > lit_size - lit_pos - lp) return ZS_ERR;
+        if ((u64)out + ll + ml > room) return ZS_ERR;
+        u32 mpos = out + ll;
+        if ((u64)off > hist + mpos) return ZS_ERR;
+        S.seq_out[j] = out; S.seq_lit[j] = lit_pos + lp;
+        if (ll > ZS_LIT_SHORT) ml_ |= 1u << j;
+        if (ml <= ZS_MATCH_SHORT && off >= mpos + ml) mp_ |= 1u << j; else mo_ |= 1u << j;
+        out = mpos + ml; lp += ll;
+    }
+    *m_long = ml_; *m_par = mp_; *m_order = mo_; *batch_out = out; *batch_lit = lp;
+    return 0;
+#else
+    const bool live = (u32)w.l < cnt;
+    u32 ll = 0, ml = 0, off = 1;
+    if (live) { ll = S.seq_ll[w.l]; ml = S.seq_ml[w.l]; off = S.seq_off[w.l]; }
+    u32 so = ll + ml, sl = ll;  // inclusive scans; 32 x (131071 + 131074) fits easily
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 a = __shfl_up_sync(0xffffffffu, so, d), c = __shfl_up_sync(0xffffffffu, sl, d);
+        if (w.l >= d) { so += a; sl += c; }
+    }
+    const u32 out = so - (ll + ml), lp = sl - ll, mpos = out + ll;
+    bool bad = live && ((u64)lit_pos + sl > lit_size || (u64)so > room || (u64)off > hist + mpos);
+    if (__any_sync(0xffffffffu, bad)) return ZS_ERR;
+    const bool par = ml <= ZS_MATCH_SHORT && off >= mpos + ml;
+    *m_long = __ballot_sync(0xffffffffu, live && ll > ZS_LIT_SHORT);
+    *m_par = __ballot_sync(0xffffffffu, live && par);
+    *m_order = __ballot_sync(0xffffffffu, live && !par);
+    *batch_out = __shfl_sync(0xffffffffu, so, 31);
+    *batch_lit = __shfl_sync(0xffffffffu, sl, 31);
+    if (live) { S.seq_out[w.l] = out; S.seq_lit[w.l] = lit_pos + lp; }
+    return 0;
+#endif
+}
+
 // ------------------------------------------------------------------------------------ block
 // Compressed block (zstd_decompress_block.c:1456-1525, 1090-1210).  Output goes to dst[op..), bounded by
 // cap; matches may reach back to dst[frame_start].  Returns 0 and advances *op_io, or ZS_ERR.
@@ -493,7 +634,9 @@ ZPB_DEVINL int zs_block(const ZWarp &w, ZstdShared &S, const u8 *src, u32 len, u
     if (len >= ZS_BLOCK_MAX) return ZS_ERR;
     const u8 *lit = nullptr;
     u32 lit_size = 0;
+    ZS_TICK(w, 7);
     int used = zs_literals(w, S, src, len, scratch, &lit, &lit_size);
+    ZS_TICK(w, 0);
     if (used < 0) return ZS_ERR;
     src += used;
     len -= (u32)used;
@@ -545,6 +688,7 @@ ZPB_DEVINL int zs_block(const ZWarp &w, ZstdShared &S, const u8 *src, u32 len, u
             } else hdr = ZS_ERR;
         }
         hdr = w.bcast(hdr, 0);
+        ZS_TICK(w, 1);
         if (hdr < 0) return ZS_ERR;
         // ---- batches of sequences: lane 0 decodes + classifies, the warp executes
         u32 done = 0;
@@ -553,18 +697,44 @@ ZPB_DEVINL int zs_block(const ZWarp &w, ZstdShared &S, const u8 *src, u32 len, u
             if (cnt > ZS_BATCH) cnt = ZS_BATCH;
             const u64 batch_op = op;
             int err = 0;
-            u64 op_end = op;
-            u32 lit_end = lit_pos;
             if (w.l == 0) {
-                u32 m_long = 0, m_par = 0, m_order = 0;
                 u32 r0 = S.rep[0], r1 = S.rep[1], r2 = S.rep[2];
                 for (u32 j = 0; j < cnt; ++j) {
-                    u32 cl = S.fse[ZS_LL + sl], co = S.fse[ZS_OF + so], cm = S.fse[ZS_ML + sm];
-                    u32 oc = (co >> 16) & 0xFFu, mc = (cm >> 16) & 0xFFu, lc = (cl >> 16) & 0xFFu;
-                    u32 ofv = oc ? (1u << oc) + zs_rb_read(b, oc) : 1u;
-                    u32 ml = ZS_ML_BASE[mc] + zs_rb_read(b, ZS_ML_BITS[mc]);
-                    u32 ll = ZS_LL_BASE[lc] + zs_rb_read(b, ZS_LL_BITS[lc]);
-                    if (b.left < 0) { err = 1; break; }
+                    const ZsCell cl = S.fse[ZS_LL + sl], co = S.fse[ZS_OF + so], cm = S.fse[ZS_ML + sm];
+                    const bool more = done + j + 1 < nseq;
+                    // read order (zstd_decompress_block.c:937-1039): OF, ML, LL extra bits, then the LL, ML, OF
+                    // state updates (skipped after the last sequence).  All widths are known from the cells,
+                    // so the six fields are cut from one 64-bit window at independent offsets.
+                    const u32 e_of = co.x >> 24, e_ml = cm.x >> 24, e_ll = cl.x >> 24;
+                    const u32 n_ll = more ? (cl.x >> 16) & 0xFFu : 0u, n_ml = more ? (cm.x >> 16) & 0xFFu : 0u,
+                              n_of = more ? (co.x >> 16) & 0xFFu : 0u;
+                    const u32 c1 = e_of, c2 = c1 + e_ml, c3 = c2 + e_ll, c4 = c3 + n_ll, c5 = c4 + n_ml,
+                              total = c5 + n_of;
+                    u32 ofv, ml, ll;
+                    if (total <= 64) {
+                        if (b.left - b.wpos < (int)total) zs_rb_refill(b);
+                        const u32 avail = (u32)(b.left - b.wpos);        // 1..64 unread bits at the top of the window
+                        const u64 v = b.win << (64u - avail);             // top-aligned (avail >= total >= ... > 0 or unused)
+                        const u32 hi = (u32)(v >> 32), lo = (u32)v;
+                        ofv = co.y + zs_field(hi, lo, 0, e_of);
+                        ml = cm.y + zs_field(hi, lo, c1, e_ml);
+                        ll = cl.y + zs_field(hi, lo, c2, e_ll);
+                        if (more) {
+                            sl = (cl.x & 0xFFFFu) + zs_field(hi, lo, c3, n_ll);
+                            sm = (cm.x & 0xFFFFu) + zs_field(hi, lo, c4, n_ml);
+                            so = (co.x & 0xFFFFu) + zs_field(hi, lo, c5, n_of);
+                        }
+                        b.left -= (int)total;
+                    } else {  // > 64 bits in one sequence (huge offset codes): field by field
+                        ofv = co.y + zs_rb_read(b, e_of);
+                        ml = cm.y + zs_rb_read(b, e_ml);
+                        ll = cl.y + zs_rb_read(b, e_ll);
+                        if (more) {
+                            sl = (cl.x & 0xFFFFu) + zs_rb_read(b, n_ll);
+                            sm = (cm.x & 0xFFFFu) + zs_rb_read(b, n_ml);
+                            so = (co.x & 0xFFFFu) + zs_rb_read(b, n_of);
+                        }
+                    }
                     u32 off;
                     if (ofv > 3) { off = ofv - 3; r2 = r1; r1 = r0; r0 = off; }
                     else {  // repeat offsets (zstd_decompress_block.c:971-987)
@@ -578,62 +748,48 @@ ZPB_DEVINL int zs_block(const ZWarp &w, ZstdShared &S, const u8 *src, u32 len, u
                             r0 = off;
                         }
                     }
-                    if (ll > lit_size - lit_end) { err = 1; break; }
-                    if ((u64)ll + ml > cap - op_end) { err = 1; break; }
-                    u64 mpos = op_end + ll;  // where the match starts
-                    if ((u64)off > mpos - frame_start) { err = 1; break; }
                     S.seq_ll[j] = ll; S.seq_ml[j] = ml; S.seq_off[j] = off;
-                    S.seq_out[j] = (u32)(op_end - batch_op);
-                    S.seq_lit[j] = lit_end;
-                    if (ll > ZS_LIT_SHORT) m_long |= 1u << j;
-                    if (ml <= ZS_MATCH_SHORT && mpos - off + ml <= batch_op) m_par |= 1u << j;
-                    else m_order |= 1u << j;
-                    op_end = mpos + ml;
-                    lit_end += ll;
-                    if (done + j + 1 < nseq) {  // state update order: LL, ML, OF
-                        sl = (cl & 0xFFFFu) + zs_rb_read(b, cl >> 24);
-                        sm = (cm & 0xFFFFu) + zs_rb_read(b, cm >> 24);
-                        so = (co & 0xFFFFu) + zs_rb_read(b, co >> 24);
-                        if (b.left < 0) { err = 1; break; }
-                    } else {
+                    if (!more) {
                         // the library updates the states once more, then wants every bit consumed (:1195)
-                        int tail = (int)((cl >> 24) + (cm >> 24) + (co >> 24));
-                        if (b.left > tail) { err = 1; break; }
+                        int tail = (int)(((cl.x >> 16) & 0xFFu) + ((cm.x >> 16) & 0xFFu) + ((co.x >> 16) & 0xFFu));
+                        if (b.left > tail) err = 1;
                     }
                 }
+                if (b.left < 0) err = 1;  // `left` only ever decreases: one check per batch covers every read
                 S.rep[0] = r0; S.rep[1] = r1; S.rep[2] = r2;
-                S.mask_longlit = m_long; S.mask_par = m_par; S.mask_order = m_order;
             }
             err = w.bcast(err, 0);
+            ZS_TICK(w, 2);
             if (err) return ZS_ERR;
-            op_end = w.bcast(op_end, 0);
-            lit_end = w.bcast(lit_end, 0);
+            w.sync();
+            // positions, validation and classification of the whole batch (zstd_decompress_block.c:804-893's
+            // checks; any failing sequence fails the entry, so the order of detection does not matter)
+            u32 m_long, m_par, m_order, batch_out, batch_lit;
+            if (zs_scan_batch(w, S, cnt, lit_pos, lit_size, cap - batch_op, batch_op - frame_start, &m_long, &m_par,
+                              &m_order, &batch_out, &batch_lit))
+                return ZS_ERR;
+            const u64 op_end = batch_op + batch_out;
+            const u32 lit_end = lit_pos + batch_lit;
             w.sync();
             u8 *bd = dst + batch_op;
             // phase 1: literal runs — short ones by the sequence's own lane, long ones by the warp
-            const u32 m_long = S.mask_longlit, m_par = S.mask_par;
-            u32 m_order = S.mask_order;
             for (u32 j = w.l; j < cnt; j += ZWarp::W) {
                 u32 ll = S.seq_ll[j];
-                if (ll <= ZS_LIT_SHORT) {
-                    u8 *d = bd + S.seq_out[j];
-                    const u8 *s = lit + S.seq_lit[j];
-                    for (u32 k = 0; k < ll; ++k) d[k] = s[k];
-                }
+                if (ll <= ZS_LIT_SHORT) zs_lane_copy(bd + S.seq_out[j], lit + S.seq_lit[j], ll);
             }
             for (u32 m = m_long; m; m &= m - 1) {
                 u32 j = (u32)zs_highbit(m & (0u - m));
                 zs_copy(w, bd + S.seq_out[j], lit + S.seq_lit[j], S.seq_ll[j]);
             }
+            ZS_TICK(w, 3);
             // phase 2a: short matches whose source lies wholly before the batch — own lane
             for (u32 j = w.l; j < cnt; j += ZWarp::W) {
                 if ((m_par >> j) & 1u) {
-                    u32 ml = S.seq_ml[j];
                     u8 *d = bd + S.seq_out[j] + S.seq_ll[j];
-                    const u8 *s = d - S.seq_off[j];
-                    for (u32 k = 0; k < ml; ++k) d[k] = s[k];
+                    zs_lane_copy(d, d - S.seq_off[j], S.seq_ml[j]);
                 }
             }
+            ZS_TICK(w, 4);
             // phase 2b: everything else in order, cooperatively
             for (; m_order; m_order &= m_order - 1) {
                 u32 j = (u32)zs_highbit(m_order & (0u - m_order));
@@ -644,7 +800,9 @@ ZPB_DEVINL int zs_block(const ZWarp &w, ZstdShared &S, const u8 *src, u32 len, u
             op = op_end;
             lit_pos = lit_end;
             done += cnt;
+            ZS_TICK(w, 5);
             hs.advance(op, w);
+            ZS_TICK(w, 6);
         }
     }
     u32 rest = lit_size - lit_pos;
@@ -777,7 +935,7 @@ ZPB_DEVINL int zstd_decode_entry(const ZWarp &w, ZstdShared &S, u8 *scratch, con
 // Persistent warps pull zstd entries from a device-side list (built by the scan kernel / the general
 // kernel, which have already applied the guards of zpack_read.c:328-331) and decode + verify them.
 #include "../../include/zpack_b200.h"
-#define ZS_WARPS 4
+#define ZS_WARPS 2
 
 struct ZsHasher {
     Xxh3Stream<32> s;
@@ -803,6 +961,9 @@ zstd_unpack_kernel(const u8 *__restrict__ archive, u8 *__restrict__ out, const z
         u8 *dst = out + e.dst_off;
         ZsHasher hs;
         hs.s.init(dst, e.uncomp_size, w.g);
+#ifdef ZPB_ZS_PROFILE
+        w.t_last = clock64();
+#endif
         u64 produced = 0;
         int rc = zstd_decode_entry(w, S, lit_buf, archive + e.src_off, e.comp_size, dst, e.dst_cap, hs, &produced);
         int st = rc ? ZPB_ST_DECOMPRESS_FAILED : ZPB_ST_OK;  // lib/zpack_read.c:384-388
@@ -815,6 +976,7 @@ zstd_unpack_kernel(const u8 *__restrict__ archive, u8 *__restrict__ out, const z
             status[idx] = st;
             digest[idx] = dg;
         }
+        ZS_TICK(w, 7);
         w.sync();
     }
 }

@@ -13,10 +13,11 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzpack_b200.so")
+LIB_PATH = os.environ.get("ZPB_LIB") or os.path.join(_HERE, "libzpack_b200.so")  # ZPB_LIB: developer builds (profiling)
 
 METHOD_NONE, METHOD_ZSTD, METHOD_LZ4 = 0, 1, 2
 F_NO_VERIFY = 1
+F_DISCARD = 2
 
 # enum zpack_result values the hot path can return (/root/reference/lib/zpack.h:189-218)
 ST_OK = 0
