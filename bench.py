@@ -328,7 +328,7 @@ def run_ours(args):
             line["e2e"] = {"value": world * uncomp_bytes / e2e_s / 1e9, "unit": "GB/s",
                            "h2d_bytes_per_step": comp_bytes + entries.nbytes, "d2h_bytes_per_step": uncomp_bytes + 12 * len(entries),
                            "how": "zpb_unpack_host, pinned host buffers: chunked H2D / kernels / D2H of every decoded byte, "
-                                  "overlapped on 3 streams; PCIe-bound"}
+                                  "overlapped on 6 streams; PCIe-bound (D2H of every decoded byte)"}
             line["e2e_verify_only"] = {"value": world * uncomp_bytes / e2e_verify_s / 1e9, "unit": "GB/s",
                                        "h2d_bytes_per_step": comp_bytes + entries.nbytes, "d2h_bytes_per_step": 12 * len(entries),
                                        "how": "same call with ZPB_F_DISCARD (the `zpack t` integrity test): status + digest come back, "

@@ -71,7 +71,7 @@ struct zpb_ctx {
     DevBuf d_in, d_out;
     // pipelined host path: private sub-contexts (own stream + scratch), one per worker thread
     std::vector<zpb_ctx *> workers;
-    int host_workers = 3;              // ZPB_HOST_WORKERS
+    int host_workers = 6;              // ZPB_HOST_WORKERS (tools/e2e_sweep.py: profiles/r1_e2e_sweep.jsonl)
     u64 host_chunk_bytes = 256u << 20; // decoded bytes per pipeline chunk (ZPB_HOST_CHUNK_MB)
 };
 
