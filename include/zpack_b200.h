@@ -108,6 +108,50 @@ int zpb_unpack_host(zpb_ctx *ctx, const uint8_t *h_archive, uint64_t archive_siz
                     uint8_t *h_out, uint64_t out_size, const zpb_entry *entries, uint64_t n,
                     int32_t *status, uint64_t *digest);
 
+/* one large entry, sharded by blocks ------------------------------------------------------- */
+/* Intra-entry parallelism (BASELINE config C5): an LZ4 entry whose frame has INDEPENDENT 64 KB blocks
+ * (FLG B.Indep = 1 — what zpb_pack_* writes; the reference reader accepts both modes,
+ * /root/reference/externals/lz4/lib/lz4frame.c:1151,1676) is decoded one warp per block, and a contiguous
+ * run of its blocks can be given to each GPU.  Replaces, for such an entry, the LZ4F_decompress loop and the
+ * XXH3_64bits pass of zpack_read_file (/root/reference/lib/zpack_read.c:396-468).  Reference-written
+ * (block-linked) and zstd entries are one dependency chain each and stay on zpb_unpack_*. */
+typedef struct zpb_block {
+    uint64_t src_off;      /* archive offset of the block payload (after its 4-byte header) */
+    uint32_t comp_size;    /* payload bytes                                                */
+    uint32_t flags;        /* ZPB_BLK_STORED: payload is the data itself (header bit 31)    */
+} zpb_block;
+#define ZPB_BLK_STORED 1u
+#define ZPB_INDEX_UNSUPPORTED 1   /* zpb_lz4_frame_index: not a single checksum-free B.Indep frame of 64 KB blocks */
+
+/* Host-side framing walk (no codec work): header checks of LZ4F_decodeHeader (lz4frame.c:1113-1205) and the
+ * block-header chain (lz4frame.c:1503-1531) of the frame at h_frame[0..comp_size).  `archive_off` is added to
+ * every src_off (the entry's offset in the archive).  Writes up to `cap` blocks, always sets *n_blocks.
+ * *content_size = the frame's content-size field or ~0 if absent.  Returns ZPB_OK, ZPB_INDEX_UNSUPPORTED
+ * (use zpb_unpack_* instead), or ZPB_E_ARG. */
+int zpb_lz4_frame_index(const uint8_t *h_frame, uint64_t comp_size, uint64_t archive_off, zpb_block *blocks,
+                        uint64_t cap, uint64_t *n_blocks, uint32_t *block_size, uint64_t *content_size);
+
+/* Decode blocks[0..n) — a contiguous run of one entry's blocks — into d_out + k * block_size.
+ * shard_uncomp_size = decoded bytes of the run: every block but the run's last must decode to exactly
+ * block_size (LZ4F writers fill blocks, lz4frame.c:873-882); only the entry's last shard may end short.
+ * *status: 0, ZPB_ST_OFFSET_INVALID, or ZPB_ST_NOT_AVAILABLE = this path declines the shard (a block is
+ * malformed or has a shape only the general decoder judges) — re-read the entry with zpb_unpack_device for
+ * the reference's verdict.  The shard's per-KiB XXH3 stripe sums stay in the context for zpb_blocks_digest. */
+int zpb_unpack_blocks_device(zpb_ctx *ctx, const uint8_t *d_archive, uint64_t archive_size, uint8_t *d_out,
+                             uint64_t out_size, const zpb_block *blocks, uint64_t n, uint32_t block_size,
+                             uint64_t shard_uncomp_size, int32_t *status, void *stream);
+
+/* XXH3-64 scramble chain (xxhash.h:3527-3534, 3698) over the last decoded shard, which covers entry bytes
+ * [shard_pos, shard_pos + shard_uncomp_size) of total_size.  acc_in: the 8 accumulators the previous shard
+ * ended with (HOST pointer; NULL = first shard, XXH3_INIT_ACC); acc_out (HOST, may be NULL) receives the
+ * state to hand to the next shard — 64 bytes is the only data that ever moves between GPUs.  For the
+ * entry's last shard, d_out (its decoded bytes, device) and digest (HOST) are required: the tail stripes
+ * and the merge (xxhash.h:3701-3747) run there. */
+int zpb_blocks_digest(zpb_ctx *ctx, const uint64_t *acc_in, uint64_t *acc_out, uint64_t shard_pos,
+                      uint64_t total_size, const uint8_t *d_out, uint64_t *digest, void *stream);
+/* device time of xxh3_chain_kernel in the last zpb_blocks_digest (ms) */
+int zpb_last_chain_ms(const zpb_ctx *ctx, float *ms);
+
 /* XXH3-64 (seed 0) of n independent ranges ------------------------------------------------- */
 int zpb_xxh3_device(zpb_ctx *ctx, const uint8_t *d_data, const uint64_t *offsets,
                     const uint64_t *lengths, uint64_t n, uint64_t *digest, void *stream);

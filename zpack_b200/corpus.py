@@ -88,3 +88,15 @@ def generate(n_entries: int, size: int, first: int = 0, seed: int = SEED) -> np.
     for k in range(n_entries):
         out[k] = entry_bytes(first + k, size, seed)
     return out
+
+
+def big_entry_piece(k: int, piece: int, total: int, first: int = 0, seed: int = SEED) -> np.ndarray:
+    """Piece k of the single large entry of BASELINE config C5: the four classes cycling every
+    `piece` bytes (1 MiB in the bench), truncated at `total`."""
+    lo = k * piece
+    return entry_bytes(first + k, max(0, min(piece, total - lo)), seed)
+
+
+def big_entry(total: int, piece: int = 1 << 20, first: int = 0, seed: int = SEED) -> np.ndarray:
+    n = (total + piece - 1) // piece
+    return np.concatenate([big_entry_piece(k, piece, total, first, seed) for k in range(n)]) if n else np.zeros(0, np.uint8)

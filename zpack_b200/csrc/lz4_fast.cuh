@@ -44,6 +44,16 @@
 #define FB_BAD     2u
 #define FB_PARSED  4u
 
+// Internal to the library (never in an archive: comp_method is a u8): one raw LZ4 block of a
+// block-independent frame, decoded as a pseudo-entry by the block-sharded path (zpb_unpack_blocks_device).
+// zpb_entry.reserved = index of the block's first KiB in the per-KiB XXH3 stripe-sum array; such
+// "partial" entries emit stripe sums instead of a digest (the chain is run by xxh3_chain_kernel).
+#define ZPB_M_LZ4_BLOCK   0x102u
+#define ZPB_F_STORED_BLK  0x100u
+#define FE_LINK_NONE    0u
+#define FE_LINK_WINDOW  1u   // blocks of the frame share the 64 KB window (B.Indep = 0)
+#define FE_LINK_PARTIAL 2u   // pseudo-entry of the block-sharded path
+
 struct FastAux {      // host -> device, per entry
     u64 desc_base;    // first descriptor slot of this entry (multiple of 4)
     u32 slot_base;    // first FastBlock slot
@@ -136,6 +146,18 @@ lz4_fast_scan_kernel(const u8 *__restrict__ archive, u64 asz, const zpb_entry *_
         }
     } else if (e.method == ZPB_METHOD_LZ4) {
         f.state = fast_scan_lz4(archive + e.src_off, e.comp_size, e, a, f, fb) ? FE_FAST : FE_GENERAL;
+    } else if (e.method == ZPB_M_LZ4_BLOCK) {                  // one block of an indexed frame (lz4frame.c:1503-1531 done on the host)
+        if (e.comp_size > 65536u || e.uncomp_size > 65536u || a.nslots == 0) st = ST_NOT_AVAILABLE;
+        else {
+            const bool stored = (e.flags & ZPB_F_STORED_BLK) != 0;
+            FastBlock b;
+            b.src = e.src_off; b.desc_off = a.desc_base; b.bsz = (u32)e.comp_size;
+            b.flags = stored ? FB_STORED : 0u; b.nseq = 0; b.out_size = stored ? (u32)e.comp_size : 0u;
+            fb[a.slot_base] = b;
+            f.nblocks = 1;
+            f.linked = FE_LINK_PARTIAL;
+            f.state = FE_FAST;
+        }
     } else if (e.method == ZPB_METHOD_ZSTD) {
         f.state = FE_ZSTD;                                     // guards passed: the zstd kernel decodes it
     } else {
@@ -415,6 +437,7 @@ struct FastExec {
     u32 rbase;      // ring content below this position is stale (direct stored path went around it)
     u32 total, full_blocks;
     u64 acc0, acc1; // XXH3 accumulators of pair j = lane & 3
+    u64 *part;      // block-sharded path: where this pseudo-entry's per-KiB stripe sums go (else nullptr)
     int lane;
 
     ZPB_DEVINL u32 ring_lo(u32 hi) const {
@@ -436,6 +459,12 @@ struct FastExec {
             s1 += __shfl_xor_sync(0xffffffffu, s1, m);
         }
         int j = lane & 3;
+        if (part) {
+            // the 16-stripe sums of KiB (flushed >> 10), words 2j and 2j+1: the scramble chain
+            // (xxhash.h:3527-3534) over the whole entry is xxh3_chain_kernel's job
+            if (lane < 4) *reinterpret_cast<ulonglong2 *>(part + (u64)(flushed >> 10) * 8 + 2 * j) = make_ulonglong2(s0, s1);
+            return;
+        }
         u64 a0 = acc0 + s0, a1 = acc1 + s1;
         a0 ^= a0 >> 47; a0 ^= c_xxh3_key[16 + 2 * j]; a0 *= XXH_P32_1;
         a1 ^= a1 >> 47; a1 ^= c_xxh3_key[16 + 2 * j + 1]; a1 *= XXH_P32_1;
@@ -557,7 +586,7 @@ __global__ void __launch_bounds__(256, 3)
 lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_entry *__restrict__ entries,
                      const u32 *__restrict__ order, u32 n, u32 *counter, const FastEntry *__restrict__ fe,
                      const FastBlock *__restrict__ fb, const u32 *__restrict__ desc, u32 *counters,
-                     u32 *general_list, int *status, u64 *digest) {
+                     u32 *general_list, int *status, u64 *digest, u64 *partials) {
     extern __shared__ uint4 k2_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FastExec x;
@@ -585,21 +614,28 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
                 if (!(B.flags & FB_STORED)) {
                     if (!(B.flags & FB_PARSED) || (B.flags & FB_BAD)) ok = false;
                     u32 reach = (B.flags >> 8) & 0xFFFFu;
-                    if (reach > (f.linked ? before : 0ull)) ok = false;   // lz4.c:2093 with the frame's prefix
+                    if (reach > (f.linked == FE_LINK_WINDOW ? before : 0ull)) ok = false;   // lz4.c:2093 with the frame's prefix
                 }
                 before += B.out_size;
             }
             if (before != e.uncomp_size) ok = false;
         }
+        const bool partial = f.linked == FE_LINK_PARTIAL;
         if (!ok) {
-            if (lane == 0) general_list[atomicAdd(&counters[1], 1u)] = idx;
+            if (lane == 0) {
+                // a block of the sharded path that K1 did not accept: the shard call declines (the caller
+                // re-reads the entry through zpb_unpack_device, whose general decoder has the exact verdict)
+                if (partial) { status[idx] = ST_NOT_AVAILABLE; digest[idx] = 0; }
+                else general_list[atomicAdd(&counters[1], 1u)] = idx;
+            }
             continue;
         }
 
         x.gout = out + e.dst_off;
         x.done = x.flushed = x.rbase = 0;
         x.total = (u32)e.uncomp_size;
-        x.full_blocks = x.total > 240 ? (x.total - 1) >> 10 : 0;
+        x.full_blocks = partial ? x.total >> 10 : x.total > 240 ? (x.total - 1) >> 10 : 0;
+        x.part = partial ? partials + e.reserved * 8 : nullptr;
         x.hash_init();
 
         for (u32 b = 0; b < f.nblocks; ++b) {
@@ -800,7 +836,9 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
             for (u32 p = x.flushed + 16 * lane; p + 16 <= x.total; p += 512) stg128(x.gout + p, lds128(x.ra(p)));
             for (u32 p = x.flushed + (span & ~15u) + lane; p < x.total; p += 32) x.gout[p] = (u8)lds8(x.ra(p));
         }
-        if (x.total <= 240) {
+        if (partial) {
+            dg = e.hash;   // no digest here: every complete KiB has left its stripe sums in `partials`
+        } else if (x.total <= 240) {
             __syncwarp();
             dg = xxh3_small(x.gout, x.total);
         } else {
@@ -838,7 +876,7 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
         __syncwarp();
         if (lane == 0) {
             status[idx] = (!(e.flags & ZPB_F_NO_VERIFY) && dg != e.hash) ? ST_HASH_MISMATCH : ST_OK;
-            digest[idx] = dg;
+            digest[idx] = partial ? 0ull : dg;
         }
     }
 }

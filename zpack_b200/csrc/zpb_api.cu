@@ -15,6 +15,7 @@
 #include "lz4_fast.cuh"
 #include "pack_kernel.cuh"
 #include "zstd_decode.cuh"
+#include "xxh3_chain.cuh"
 
 static thread_local std::string g_last_error = "";
 
@@ -71,6 +72,11 @@ struct zpb_ctx {
     DevBuf d_in, d_out;
     // pipelined host path: private sub-contexts (own stream + scratch), one per worker thread
     std::vector<zpb_ctx *> workers;
+    // block-sharded path (one large block-independent LZ4 entry): per-KiB XXH3 stripe sums of the last shard
+    DevBuf d_partials, d_acc;
+    u64 *cur_partials = nullptr;       // non-null only while zpb_unpack_blocks_device drives the pipeline
+    u64 blk_uncomp = 0;                // decoded bytes of the last shard (0 = none / declined)
+    float chain_ms = 0.f;
     int host_workers = 6;              // ZPB_HOST_WORKERS (tools/e2e_sweep.py: profiles/r1_e2e_sweep.jsonl)
     u64 host_chunk_bytes = 256u << 20; // decoded bytes per pipeline chunk (ZPB_HOST_CHUNK_MB)
 };
@@ -161,6 +167,7 @@ extern "C" void zpb_destroy(zpb_ctx *ctx) {
     ctx->d_in.release(); ctx->d_out.release(); ctx->h_stage.release();
     ctx->d_aux.release(); ctx->d_fe.release(); ctx->d_fb.release(); ctx->d_plist.release();
     ctx->d_glist.release(); ctx->d_fdesc.release(); ctx->d_zlist.release(); ctx->d_zlit.release();
+    ctx->d_partials.release(); ctx->d_acc.release();
     for (auto &ev : ctx->evs) if (ev) cudaEventDestroy(ev);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -310,6 +317,9 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
     zpb_entry *h_desc = (zpb_entry *)hs;
     u32 *h_order = (u32 *)(hs + desc_b);
     memcpy(h_desc, entries, desc_b);
+    if (!ctx->cur_partials)   // method codes above a byte are internal (comp_method is a u8, lib/zpack.h:79): never from callers
+        for (u64 i = 0; i < n; ++i)
+            if (h_desc[i].method > 0xFFu) h_desc[i].method = 0xFFu;
     build_order(entries, n, h_order);
     u64 *d_digest = (u64 *)ctx->d_res.p;
     int *d_status = (int *)((u8 *)ctx->d_res.p + n * sizeof(u64));
@@ -327,7 +337,10 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
             u32 ns = 0; u64 nd = 0;
             if (e.uncomp_size < 0x7fffffffull && e.comp_size) {
                 if (e.method == ZPB_METHOD_NONE) ns = 1;
-                else if (e.method == ZPB_METHOD_LZ4) {
+                else if (e.method == ZPB_M_LZ4_BLOCK) {
+                    ns = 1;
+                    nd = ((e.comp_size / 3 + 20) + 3) & ~3ull;
+                } else if (e.method == ZPB_METHOD_LZ4) {
                     ns = (u32)(e.uncomp_size >> 16) + 2;
                     nd = ((e.comp_size / 3 + 12ull * ns + 8) + 3) & ~3ull;
                 }
@@ -360,7 +373,7 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
         lz4_fast_exec_kernel<<<ctx->sm_count * 3, 256, 8 * FAST_WARP_SMEM, s>>>(
             d_archive, archive_size, d_out, d_e, d_ord, (u32)n, cnt + 3, (const FastEntry *)ctx->d_fe.p,
             (const FastBlock *)ctx->d_fb.p, (const u32 *)ctx->d_fdesc.p, cnt, (u32 *)ctx->d_glist.p, d_status,
-            d_digest);
+            d_digest, ctx->cur_partials);
         CK(ctx, cudaGetLastError());
         CK(ctx, cudaEventRecord(ctx->evs[3], s));
         cudaError_t ge;
@@ -557,6 +570,9 @@ extern "C" int zpb_unpack_host(zpb_ctx *ctx, const uint8_t *h_archive, uint64_t 
         if (rcs[t] != ZPB_OK) return fail(ctx, rcs[t], errs[t].c_str());
     return ZPB_OK;
 }
+
+// ------------------------------------------------------------------------------------ block-sharded entry
+#include "blocks_api.inl"
 
 // ------------------------------------------------------------------------------------ xxh3
 extern "C" int zpb_xxh3_device(zpb_ctx *ctx, const uint8_t *d_data, const uint64_t *offsets,

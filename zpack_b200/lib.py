@@ -41,13 +41,18 @@ File = np.dtype(
     [("src_off", "<u8"), ("size", "<u8"), ("dst_off", "<u8"), ("dst_cap", "<u8"),
      ("method", "<u4"), ("level", "<i4"), ("reserved", "<u8", (3,))]
 )
-assert Entry.itemsize == 64 and File.itemsize == 64
+#: numpy dtype of `struct zpb_block` (16 bytes)
+Block = np.dtype([("src_off", "<u8"), ("comp_size", "<u4"), ("flags", "<u4")])
+BLK_STORED = 1
+INDEX_UNSUPPORTED = 1
+assert Entry.itemsize == 64 and File.itemsize == 64 and Block.itemsize == 16
 
 EXPORTS = [
     "zpb_abi_version", "zpb_create", "zpb_destroy", "zpb_last_error", "zpb_device_info",
     "zpb_launch_count", "zpb_unpack_device", "zpb_unpack_host", "zpb_xxh3_device", "zpb_xxh3_host",
     "zpb_pack_bound", "zpb_pack_device", "zpb_pack_host", "zpb_last_kernel_ms", "zpb_set_tuning",
     "zpb_last_stage_ms", "zpb_set_fast_path", "zpb_last_zstd_ms",
+    "zpb_lz4_frame_index", "zpb_unpack_blocks_device", "zpb_blocks_digest", "zpb_last_chain_ms",
 ]
 
 
@@ -89,6 +94,10 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.zpb_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.zpb_set_fast_path.argtypes = [vp, C.c_int]
     lib.zpb_last_zstd_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.zpb_lz4_frame_index.argtypes = [vp, u64, u64, vp, u64, u64p, C.POINTER(C.c_uint32), u64p]
+    lib.zpb_unpack_blocks_device.argtypes = [vp, vp, u64, vp, u64, vp, u64, C.c_uint32, u64, i32p, vp]
+    lib.zpb_blocks_digest.argtypes = [vp, vp, vp, u64, u64, vp, u64p, vp]
+    lib.zpb_last_chain_ms.argtypes = [vp, C.POINTER(C.c_float)]
     _lib = lib
     return lib
 
@@ -104,6 +113,24 @@ def _ptr(a) -> int:
     if hasattr(a, "data_ptr"):
         return a.data_ptr()
     raise TypeError(type(a))
+
+
+def lz4_frame_index(frame: np.ndarray, archive_off: int = 0):
+    """Host-side framing walk of one block-independent LZ4 frame (no GPU needed, no codec work):
+    returns (blocks: Block[n], block_size, content_size or None), or None when the frame is not a single
+    checksum-free B.Indep frame of 64 KB blocks (zpb_lz4_frame_index -> ZPB_INDEX_UNSUPPORTED)."""
+    lib = load_library()
+    frame = np.ascontiguousarray(frame, np.uint8)
+    n, bs, cs = C.c_uint64(), C.c_uint32(), C.c_uint64()
+    cap = len(frame) // 5 + 2   # every block costs at least 4 header bytes + 1 payload byte
+    blocks = np.zeros(cap, Block)
+    rc = lib.zpb_lz4_frame_index(frame.ctypes.data, len(frame), archive_off, blocks.ctypes.data, cap,
+                                 C.byref(n), C.byref(bs), C.byref(cs))
+    if rc == INDEX_UNSUPPORTED:
+        return None
+    if rc != 0:
+        raise ZpbError(f"zpb_lz4_frame_index: {rc}")
+    return blocks[:n.value].copy(), bs.value, (None if cs.value == 2**64 - 1 else cs.value)
 
 
 class Context:
@@ -176,6 +203,36 @@ class Context:
         self._check(self.lib.zpb_unpack_host(self.h, _ptr(h_archive), archive_size, _ptr(h_out), out_size,
                                              _ptr(entries), n, _ptr(status), _ptr(digest)))
         return status, digest
+
+    # ---- one large entry, sharded by blocks (C5) ------------------------------------------------
+    def unpack_blocks_device(self, d_archive, archive_size: int, d_out, out_size: int, blocks: np.ndarray,
+                             block_size: int, shard_uncomp_size: int, stream: int = 0) -> int:
+        """Decode a contiguous run of one entry's independent blocks; returns the shard status."""
+        assert blocks.dtype == Block and blocks.flags.c_contiguous
+        st = C.c_int32(-1)
+        self._check(self.lib.zpb_unpack_blocks_device(self.h, _ptr(d_archive), archive_size, _ptr(d_out), out_size,
+                                                      _ptr(blocks), len(blocks), block_size, shard_uncomp_size,
+                                                      C.byref(st), stream))
+        self._blk_uncomp = shard_uncomp_size if st.value == 0 else None
+        return st.value
+
+    def blocks_digest(self, acc_in: Optional[np.ndarray], shard_pos: int, total_size: int, d_out=None,
+                      stream: int = 0):
+        """XXH3 chain over the last decoded shard.  Returns (acc_out: uint64[8], digest or None)."""
+        acc_out = np.empty(8, np.uint64)
+        dg = C.c_uint64(0)
+        if acc_in is not None:
+            acc_in = np.ascontiguousarray(acc_in, np.uint64)
+            assert acc_in.shape == (8,)
+        self._check(self.lib.zpb_blocks_digest(self.h, _ptr(acc_in), _ptr(acc_out), shard_pos, total_size,
+                                               _ptr(d_out), C.byref(dg), stream))
+        final = shard_pos + (getattr(self, "_blk_uncomp", None) or 0) == total_size
+        return acc_out, (dg.value if final else None)
+
+    def last_chain_ms(self) -> float:
+        a = C.c_float()
+        self.lib.zpb_last_chain_ms(self.h, C.byref(a))
+        return a.value
 
     # ---- digest ------------------------------------------------------------------------------
     def xxh3_host(self, data) -> int:
