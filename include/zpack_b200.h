@@ -149,6 +149,14 @@ int zpb_unpack_blocks_device(zpb_ctx *ctx, const uint8_t *d_archive, uint64_t ar
  * and the merge (xxhash.h:3701-3747) run there. */
 int zpb_blocks_digest(zpb_ctx *ctx, const uint64_t *acc_in, uint64_t *acc_out, uint64_t shard_pos,
                       uint64_t total_size, const uint8_t *d_out, uint64_t *digest, void *stream);
+/* zpack_read_file for ONE large block-independent LZ4 entry with host buffers: frame index, then chunks of
+ * blocks pipelined over the context's worker streams (H2D / decode / chain / D2H overlap), the XXH3 state
+ * relayed chunk to chunk.  Returns ZPB_OK with *status = the entry's zpack_result, or ZPB_INDEX_UNSUPPORTED
+ * when the entry is not eligible (linked blocks, checksums, sizes that do not add up, a block the fast
+ * kernels decline) — the caller then uses zpb_unpack_host, which decodes anything.  flags: ZPB_F_*. */
+int zpb_unpack_entry_blocks_host(zpb_ctx *ctx, const uint8_t *h_entry, uint64_t comp_size, uint8_t *h_out,
+                                 uint64_t out_cap, uint64_t uncomp_size, uint64_t expect_hash, uint32_t flags,
+                                 int32_t *status, uint64_t *digest);
 /* device time of xxh3_chain_kernel in the last zpb_blocks_digest (ms) */
 int zpb_last_chain_ms(const zpb_ctx *ctx, float *ms);
 

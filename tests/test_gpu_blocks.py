@@ -73,11 +73,16 @@ def test_declines_a_malformed_block_and_the_entry_path_gives_the_reference_verdi
     blocks, bs, _ = zlib.lz4_frame_index(frame)
     bad = frame.copy()
     b0 = int(blocks["src_off"][0])
-    tok = int(bad[b0])
-    lit = tok >> 4
-    assert lit < 15
-    bad[b0 + 1 + lit] = 0
-    bad[b0 + 2 + lit] = 0                                           # first match offset := 0 (lz4.c:2093 rejects)
+    p = b0 + 1
+    lit = int(bad[b0]) >> 4
+    if lit == 15:
+        while True:
+            lit += int(bad[p])
+            p += 1
+            if bad[p - 1] != 255:
+                break
+    bad[p + lit] = 0
+    bad[p + lit + 1] = 0                                            # first match offset := 0 (lz4.c:2093 rejects)
     d_arch = torch.from_numpy(bad).cuda()
     d_out = torch.zeros(total, dtype=torch.uint8, device="cuda")
     assert gpu_ctx.unpack_blocks_device(d_arch, len(bad), d_out, total, blocks, bs, total) == zlib.ST_NOT_AVAILABLE
@@ -137,3 +142,32 @@ def test_large_entry_properties(gpu_ctx, oracle):
         assert np.array_equal(out, data)
     d = torch.from_numpy(data).cuda()
     assert int(gpu_ctx.xxh3_device(d, [0], [total])[0]) == want
+
+
+@pytest.mark.parametrize("total", [5 << 20, (9 << 20) + 777])
+def test_entry_blocks_host_pipeline(gpu_ctx, oracle, total):
+    """zpb_unpack_entry_blocks_host: host buffers, chunks pipelined over the worker streams with the XXH3 state
+    relayed chunk to chunk (1 MiB chunks here so that several chunks and several workers are exercised)."""
+    import os
+    data = corpus.big_entry(total, piece=1 << 20, first=1)
+    frame = oracle.lz4f_encode_port(data, 0, independent=True)
+    want = oracle.xxh3_port(data)
+    os.environ["ZPB_HOST_CHUNK_MB"] = "1"
+    import zpack_b200
+    ctx = zpack_b200.Context(0)
+    del os.environ["ZPB_HOST_CHUNK_MB"]
+    try:
+        out = np.zeros(total + 5, np.uint8)
+        assert ctx.unpack_entry_blocks_host(frame, len(frame), out, total + 5, total, want) == (0, want)
+        assert np.array_equal(out[:total], data) and not out[total:].any()
+        assert ctx.unpack_entry_blocks_host(frame, len(frame), out, total, total, want ^ 1) == (zlib.ST_HASH_MISMATCH, want)
+        assert ctx.unpack_entry_blocks_host(frame, len(frame), out, total - 1, total, want)[0] == zlib.ST_BUFFER_TOO_SMALL
+        out[:] = 0
+        assert ctx.unpack_entry_blocks_host(frame, len(frame), out, total, total, want, flags=zlib.F_DISCARD) == (0, want)
+        assert not out.any()                                        # verdict only: nothing copied back
+        # not eligible -> None (the caller goes through zpb_unpack_host): linked frame, wrong declared size
+        linked = oracle.lz4f_encode_port(data, 0, independent=False)
+        assert ctx.unpack_entry_blocks_host(linked, len(linked), out, total, total, want) is None
+        assert ctx.unpack_entry_blocks_host(frame, len(frame), out, total, total - 70000, want) is None
+    finally:
+        ctx.close()

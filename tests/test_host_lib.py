@@ -325,3 +325,44 @@ def test_batched_read_extension_and_stream_with_tiny_buffers(golden_dir, oracle)
     assert s.total_in == e.comp_size and s.total_out == size and bytes(got) == bufs[3].tobytes()
     lib.zpack_close_stream(C.byref(s))
     lib.zpack_close_reader(C.byref(r))
+
+
+@pytest.mark.gpu
+def test_large_entry_takes_the_block_parallel_path_and_round_trips(oracle):
+    """One 12 MiB file written by zpack_write_archive (GPU writer: independent 64 KB blocks) and read back by
+    zpack_read_file — comp_size >= 4 MiB, so the read goes through zpb_unpack_entry_blocks_host (frame index,
+    warp per block, XXH3 chain) — and by the unmodified reference reader."""
+    lib = _lib()
+    from zpack_b200 import corpus
+    from zpack_b200 import lib as zlib
+    total = 12 << 20
+    data = corpus.big_entry(total, piece=1 << 20)
+    opt = Options(2, 0)
+    w = Writer()
+    assert lib.zpack_init_writer_heap(C.byref(w), C.c_size_t(0)) == 0
+    files = (ZFile * 1)()
+    files[0].filename, files[0].buffer, files[0].size, files[0].options = b"big.bin", data.ctypes.data, total, C.pointer(opt)
+    assert lib.zpack_write_archive(C.byref(w), files, C.c_uint64(1)) == 0
+    arch = np.ctypeslib.as_array(C.cast(w.buffer, C.POINTER(C.c_uint8)), shape=(w.file_size,)).copy()
+    lib.zpack_close_writer(C.byref(w))
+    r = Reader()
+    assert lib.zpack_init_reader_memory_shared(C.byref(r), arch.ctypes.data_as(C.c_void_p), C.c_size_t(len(arch))) == 0
+    e = r.file_entries[0]
+    assert e.comp_size >= (4 << 20) and e.hash == oracle.xxh3_port(data)
+    frame = arch[e.offset:e.offset + e.comp_size]
+    assert zlib.lz4_frame_index(frame) is not None                  # eligible: this read is block-parallel
+    out = np.zeros(total, np.uint8)
+    assert lib.zpack_read_file(C.byref(r), C.byref(e), out.ctypes.data_as(C.c_void_p), C.c_size_t(total), None) == 0
+    assert np.array_equal(out, data)
+    # a flipped payload byte inside a stored (random) block: decode succeeds, digest does not (lib/zpack_read.c:466-468)
+    blocks, _, _ = zlib.lz4_frame_index(frame)
+    k = int(np.flatnonzero(blocks["flags"] == zlib.BLK_STORED)[0])
+    arch[e.offset + int(blocks["src_off"][k]) + 5] ^= 0x40
+    assert lib.zpack_read_file(C.byref(r), C.byref(e), out.ctypes.data_as(C.c_void_p), C.c_size_t(total), None) == 15
+    arch[e.offset + int(blocks["src_off"][k]) + 5] ^= 0x40
+    lib.zpack_close_reader(C.byref(r))
+    if oracle.have_ref():
+        rd = oracle.RefReader(arch)
+        rc, ref_out = rd.read(0)
+        assert rc == 0 and np.array_equal(ref_out[:total], data)
+        rd.close()

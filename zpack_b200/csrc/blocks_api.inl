@@ -171,3 +171,112 @@ extern "C" int zpb_last_chain_ms(const zpb_ctx *ctx, float *ms) {
     *ms = ctx->chain_ms;
     return ZPB_OK;
 }
+
+// ---- host buffers in, host buffers out: what zpack_read_file does for one large block-independent entry.
+// The entry is cut into chunks of ~host_chunk_bytes decoded bytes; chunk c goes to worker c % W (a private
+// sub-context: own stream and scratch), so that chunk c+1's H2D, chunk c's kernels and chunk c-1's D2H overlap.
+// The workers are this call's "ranks": each decodes its run of blocks, waits for the previous chunk's 64-byte
+// accumulator state, runs its part of the XXH3 chain and publishes the state — the same relay N GPUs do.
+#include <condition_variable>
+#include <mutex>
+
+extern "C" int zpb_unpack_entry_blocks_host(zpb_ctx *ctx, const uint8_t *h_entry, uint64_t comp_size, uint8_t *h_out,
+                                            uint64_t out_cap, uint64_t uncomp_size, uint64_t expect_hash,
+                                            uint32_t flags, int32_t *status, uint64_t *digest) {
+    if (!ctx || !h_entry || (!h_out && out_cap) || !status) return fail(ctx, ZPB_E_ARG, "null argument");
+    u64 nb = 0, content = 0;
+    u32 bs = 0;
+    int rc = zpb_lz4_frame_index(h_entry, comp_size, 0, nullptr, 0, &nb, &bs, &content);
+    if (rc != ZPB_OK) return rc;
+    if (nb == 0 || uncomp_size > nb * (u64)bs || uncomp_size <= (nb - 1) * (u64)bs ||
+        (content != ~0ull && content != uncomp_size))
+        return ZPB_INDEX_UNSUPPORTED;                                  // sizes that do not add up: the general path decides
+    if (out_cap < uncomp_size) { *status = ZPB_ST_BUFFER_TOO_SMALL; if (digest) *digest = 0; return ZPB_OK; }   // zpack_read.c:329
+    std::vector<zpb_block> blocks(nb);
+    rc = zpb_lz4_frame_index(h_entry, comp_size, 0, blocks.data(), nb, &nb, &bs, nullptr);
+    if (rc != ZPB_OK) return rc;
+
+    const u64 per_chunk = std::max<u64>(2, ctx->host_chunk_bytes / bs);
+    std::vector<u64> cuts;
+    for (u64 b = 0; b < nb; b += per_chunk) cuts.push_back(b);
+    // the last chunk holds the XXH3 tail: never let it be a lone short block
+    if (cuts.size() > 1 && nb - cuts.back() < 2) cuts.pop_back();
+    cuts.push_back(nb);
+    const size_t nchunks = cuts.size() - 1;
+    const int W = (int)std::min<size_t>((size_t)std::max(1, ctx->host_workers), nchunks);
+    while ((int)ctx->workers.size() < W) {
+        zpb_ctx *w = zpb_create(ctx->device);
+        if (!w) return fail(ctx, ZPB_E_CUDA, "pipeline sub-context creation failed");
+        ctx->workers.push_back(w);
+    }
+    std::mutex mu;
+    std::condition_variable cv;
+    size_t chained = 0;             // chunks [0, chained) have been folded into `acc`
+    u64 acc[8];
+    bool have_acc = false, abort_all = false;
+    int32_t verdict = ZPB_ST_OK;
+    u64 dg = 0;
+    std::vector<int> rcs(W, ZPB_OK);
+    std::vector<std::string> errs(W);
+
+    auto body = [&](int t) {
+        zpb_ctx *w = ctx->workers[t];
+        auto bail = [&](int code, int32_t st) {
+            std::lock_guard<std::mutex> lk(mu);
+            if (code != ZPB_OK) { rcs[t] = code; errs[t] = w->err; }
+            if (st != ZPB_ST_OK && verdict == ZPB_ST_OK) verdict = st;
+            abort_all = true;
+            cv.notify_all();
+        };
+        if (cudaSetDevice(w->device) != cudaSuccess) { w->err = "cudaSetDevice failed"; bail(ZPB_E_CUDA, 0); return; }
+        cudaStream_t s = w->stream;
+        for (size_t c = t; c < nchunks; c += W) {
+            { std::lock_guard<std::mutex> lk(mu); if (abort_all) return; }
+            const u64 b0 = cuts[c], b1 = cuts[c + 1];
+            const u64 pos = b0 * bs, size = std::min<u64>(uncomp_size, b1 * (u64)bs) - pos;
+            const u64 lo = blocks[b0].src_off & ~15ull, hi = blocks[b1 - 1].src_off + blocks[b1 - 1].comp_size;
+            if (!w->d_in.ensure(hi - lo + 64) || !w->d_out.ensure(size + 64)) { w->err = "device staging allocation failed"; bail(ZPB_E_NOMEM, 0); return; }
+            if (cudaMemcpyAsync(w->d_in.p, h_entry + lo, hi - lo, cudaMemcpyHostToDevice, s) != cudaSuccess) { w->err = "H2D failed"; bail(ZPB_E_CUDA, 0); return; }
+            std::vector<zpb_block> rel(blocks.begin() + b0, blocks.begin() + b1);
+            for (auto &b : rel) b.src_off -= lo;
+            int32_t st = 0;
+            int r = zpb_unpack_blocks_device(w, (const u8 *)w->d_in.p, hi - lo, (u8 *)w->d_out.p, size, rel.data(), b1 - b0, bs, size, &st, s);
+            if (r != ZPB_OK || st != ZPB_ST_OK) { bail(r, st); return; }
+            if (!(flags & ZPB_F_DISCARD) &&
+                cudaMemcpyAsync(h_out + pos, w->d_out.p, size, cudaMemcpyDeviceToHost, s) != cudaSuccess) { w->err = "D2H failed"; bail(ZPB_E_CUDA, 0); return; }
+            u64 in[8], out[8], d = 0;
+            bool first;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return chained == c || abort_all; });
+                if (abort_all) return;
+                first = !have_acc;
+                memcpy(in, acc, sizeof in);
+            }
+            r = zpb_blocks_digest(w, first ? nullptr : in, out, pos, uncomp_size, (const u8 *)w->d_out.p, &d, s);   // syncs s: D2H done too
+            if (r != ZPB_OK) { bail(r, 0); return; }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                memcpy(acc, out, sizeof acc);
+                have_acc = true;
+                chained = c + 1;
+                if (c + 1 == nchunks) dg = d;
+                cv.notify_all();
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < W; ++t) th.emplace_back(body, t);
+    body(0);
+    for (auto &x : th) x.join();
+    u64 launches = 0;
+    for (int t = 0; t < W; ++t) { launches += ctx->workers[t]->launches; ctx->workers[t]->launches = 0; }
+    ctx->launches += launches;
+    for (int t = 0; t < W; ++t)
+        if (rcs[t] != ZPB_OK) return fail(ctx, rcs[t], errs[t].c_str());
+    if (verdict == ZPB_ST_NOT_AVAILABLE) return ZPB_INDEX_UNSUPPORTED;      // a block the fast kernels declined: general path
+    if (verdict == ZPB_ST_OK && !(flags & ZPB_F_NO_VERIFY) && dg != expect_hash) verdict = ZPB_ST_HASH_MISMATCH;   // zpack_read.c:466-468
+    *status = verdict;
+    if (digest) *digest = verdict == ZPB_ST_OK || verdict == ZPB_ST_HASH_MISMATCH ? dg : 0;
+    return ZPB_OK;
+}

@@ -116,6 +116,16 @@ int gpu_unpack_one(const zpack_u8 *comp, zpack_u64 comp_size, zpack_u8 *dst, siz
     d.uncomp_size = e->uncomp_size; d.hash = e->hash; d.method = e->comp_method;
     int32_t st = 0;
     uint64_t dg = 0;
+    // a large LZ4 entry written with independent blocks (what this library's writer emits) is decoded block-parallel,
+    // chunks pipelined over PCIe; anything else — and anything that path declines — is one dependency chain
+    if (e->comp_method == ZPACK_COMPRESSION_LZ4 && comp_size >= (4u << 20)) {
+        int rc = zpb_unpack_entry_blocks_host(g, comp, comp_size, dst, max_size, e->uncomp_size, e->hash, 0, &st, &dg);
+        if (rc == ZPB_OK) {
+            if (last_return) *last_return = (size_t)st;
+            return st;
+        }
+        if (rc != ZPB_INDEX_UNSUPPORTED) return ZPACK_ERROR_DECOMPRESS_FAILED;
+    }
     if (zpb_unpack_host(g, comp, comp_size, dst, max_size, &d, 1, &st, &dg) != ZPB_OK) return ZPACK_ERROR_DECOMPRESS_FAILED;
     if (last_return) *last_return = (size_t)st;
     return st;

@@ -53,6 +53,7 @@ EXPORTS = [
     "zpb_pack_bound", "zpb_pack_device", "zpb_pack_host", "zpb_last_kernel_ms", "zpb_set_tuning",
     "zpb_last_stage_ms", "zpb_set_fast_path", "zpb_last_zstd_ms",
     "zpb_lz4_frame_index", "zpb_unpack_blocks_device", "zpb_blocks_digest", "zpb_last_chain_ms",
+    "zpb_unpack_entry_blocks_host",
 ]
 
 
@@ -98,6 +99,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.zpb_unpack_blocks_device.argtypes = [vp, vp, u64, vp, u64, vp, u64, C.c_uint32, u64, i32p, vp]
     lib.zpb_blocks_digest.argtypes = [vp, vp, vp, u64, u64, vp, u64p, vp]
     lib.zpb_last_chain_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.zpb_unpack_entry_blocks_host.argtypes = [vp, vp, u64, vp, u64, u64, u64, C.c_uint32, i32p, u64p]
     _lib = lib
     return lib
 
@@ -228,6 +230,18 @@ class Context:
                                                _ptr(d_out), C.byref(dg), stream))
         final = shard_pos + (getattr(self, "_blk_uncomp", None) or 0) == total_size
         return acc_out, (dg.value if final else None)
+
+    def unpack_entry_blocks_host(self, h_entry, comp_size: int, h_out, out_cap: int, uncomp_size: int,
+                                 expect_hash: int, flags: int = 0):
+        """One large block-independent LZ4 entry, host buffers (pipelined chunks + XXH3 relay).
+        Returns (status, digest), or None when the entry is not eligible for the block path."""
+        st, dg = C.c_int32(-1), C.c_uint64(0)
+        rc = self.lib.zpb_unpack_entry_blocks_host(self.h, _ptr(h_entry), comp_size, _ptr(h_out), out_cap,
+                                                   uncomp_size, expect_hash, flags, C.byref(st), C.byref(dg))
+        if rc == INDEX_UNSUPPORTED:
+            return None
+        self._check(rc)
+        return st.value, dg.value
 
     def last_chain_ms(self) -> float:
         a = C.c_float()
