@@ -5,8 +5,8 @@
 // where S_n depends on the data only (pure adds) and scramble is the non-linear per-lane step
 // (xxhash.h:3527-3534).  The block-sharded decode (lz4_fast_exec_kernel in partial mode) leaves
 // S_n for every complete KiB in HBM (64 bytes each); this kernel runs the chain.  Nothing about
-// it is parallel beyond the 8 independent accumulator lanes: one warp, lanes 0-3
-// each carrying accumulator pair (2j, 2j+1), the other lanes only help to stage S_n.
+// it is parallel beyond the 8 independent accumulator lanes: one warp, lanes 0-7
+// each carrying one accumulator, the other lanes only help to stage S_n.
 //
 // Multi-GPU (BASELINE config C5): shard k's chain starts from the 64-byte accumulator state shard
 // k-1 ended with (acc_in / acc_out); the last shard also folds the tail (xxhash.h:3701-3711) from
@@ -15,7 +15,8 @@
 #include "common.cuh"
 #include "xxh3.cuh"
 
-#define XC_BATCH 64u   // KiB steps staged per round: 64 x 64 B = 4 KiB of shared memory, double buffered
+#define XC_BATCH  64u   // KiB steps per batch: 64 x 64 B = 4 KiB of shared memory
+#define XC_STAGES 8u    // batches in flight (cp.async ring, 32 KiB)
 
 // acc[8] in xxHash order.  nscr = how many leading S_n are followed by a scramble (all of the shard's
 // complete KiBs, except that the entry's very last KiB is never scrambled: it belongs to the tail).
@@ -24,64 +25,80 @@
 __global__ void __launch_bounds__(32)
 xxh3_chain_kernel(const u64 *__restrict__ partials, u64 nscr, const u64 *__restrict__ acc_in, u64 *acc_out,
                   int final, const u8 *tail_ptr, u64 tail_pos, u64 total, u64 *digest_out) {
-    __shared__ ulonglong2 stage[2][XC_BATCH * 4];
+    __shared__ ulonglong2 stage[XC_STAGES][XC_BATCH * 4];
     const int lane = threadIdx.x;
     const int j = lane & 3;
-    u64 a0, a1;
-    if (acc_in) { a0 = acc_in[2 * j]; a1 = acc_in[2 * j + 1]; }
+    const int i8 = lane & 7;      // the chain runs one accumulator per lane on lanes 0-7: every instruction of a
+                                  // step then serves all 8 chains (a warp instruction costs the same for 1 or 32 lanes)
+    u64 a;
+    if (acc_in) a = acc_in[i8];
     else {
-        a0 = j == 0 ? (u64)XXH_P32_3 : j == 1 ? XXH_P64_2 : j == 2 ? XXH_P64_4 : XXH_P64_5;
-        a1 = j == 0 ? XXH_P64_1 : j == 1 ? XXH_P64_3 : j == 2 ? (u64)XXH_P32_2 : (u64)XXH_P32_1;
+        const u64 init[8] = {XXH_P32_3, XXH_P64_1, XXH_P64_2, XXH_P64_3, XXH_P64_4, XXH_P32_2, XXH_P64_5, XXH_P32_1};
+        a = init[i8];
     }
-    const u64 k0 = c_xxh3_key[16 + 2 * j], k1 = c_xxh3_key[16 + 2 * j + 1];
+    // One chain step is acc' = ((x ^ (x >> 47)) ^ key) * PRIME32_1 with x = acc + S_n.  Carrying x instead of
+    // acc (x' = acc' + S_{n+1}) puts the next add INSIDE the multiply-add: with y = (x ^ (x >> 47)) ^ key,
+    //     x' = y_lo * P + { S'_lo , y_hi * P + S'_hi }        (one mad.wide.u32 with a 64-bit addend)
+    // so the loop-carried path is shift -> xor3 -> mad.wide (3 dependent instructions) instead of
+    // add.cc -> addc -> shift -> xor3 -> mad.wide -> mad.  The stream consumed is S shifted by one with a
+    // trailing zero, so after the last step x is the accumulator itself.
+    const u64 kk = c_xxh3_key[16 + i8];
+    const u32 kl = (u32)kk, kh = (u32)(kk >> 32);
     const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(partials);   // 4 x 16 B per KiB
-    const u64 nbatch = (nscr + XC_BATCH - 1) / XC_BATCH;
-    // software pipeline: batch b+1 travels HBM -> registers while lanes 0-3 walk batch b in shared memory
-    ulonglong2 r[8];
-    auto fetch = [&](u64 b) {
-        const u64 lo = b * XC_BATCH * 4, hi = nscr * 4;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            u64 i = lo + (u64)k * 32 + lane;
-            r[k] = i < hi ? src[i] : make_ulonglong2(0, 0);
-        }
+    if (nscr) a += partials[i8];
+    auto step = [&](u64 x, u64 vnext) -> u64 {
+        const u32 xl = (u32)x, xh = (u32)(x >> 32);
+        const u32 yl = xl ^ (xh >> 15) ^ kl;
+        const u32 ch = (xh ^ kh) * XXH_P32_1 + (u32)(vnext >> 32);
+        u64 r;
+        asm("{\n\t.reg .b64 c;\n\tmov.b64 c, {%3, %4};\n\tmad.wide.u32 %0, %1, %2, c;\n\t}"
+            : "=l"(r) : "r"(yl), "r"(XXH_P32_1), "r"((u32)vnext), "r"(ch));
+        return r;
     };
-    if (nbatch) fetch(0);
-    for (u64 b = 0; b < nbatch; ++b) {
-        ulonglong2 *st = stage[b & 1];
+    const u64 nbatch = (nscr + XC_BATCH - 1) / XC_BATCH;
+    // XC_STAGES-deep cp.async ring: a batch is 64 chain steps (~0.7 us of dependent arithmetic), an HBM round trip
+    // is about as long, so several batches must be in flight for the walk never to wait on memory
+    const u32 stage_s = (u32)__cvta_generic_to_shared(&stage[0][0]);
+    auto issue = [&](u64 b) {
+        if (b < nbatch) {
+            const u64 lo = b * XC_BATCH * 4 + 4, hi = nscr * 4;   // + 4: the stream is S shifted by one KiB
+            const u32 dst = stage_s + (u32)(b % XC_STAGES) * (XC_BATCH * 64u);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) st[k * 32 + lane] = r[k];
+            for (int k = 0; k < 8; ++k) {
+                const u64 i = lo + (u64)k * 32 + lane;
+                const bool in = i < hi;                           // beyond the shard: zero-filled (src-size 0)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (u32)(k * 32 + lane) * 16u),
+                             "l"(src + (in ? i : 0)), "r"(in ? 16u : 0u) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (u64 b = 0; b + 1 < XC_STAGES; ++b) issue(b);
+    for (u64 b = 0; b < nbatch; ++b) {
+        issue(b + XC_STAGES - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(XC_STAGES - 1) : "memory");
         __syncwarp();
-        if (b + 1 < nbatch) fetch(b + 1);
-        if (lane < 4) {
+        const u64 *st = reinterpret_cast<const u64 *>(stage[b % XC_STAGES]);
+        if (lane < 8) {
             const u32 steps = (u32)(nscr - b * XC_BATCH < XC_BATCH ? nscr - b * XC_BATCH : XC_BATCH);
             u32 s = 0;
-            for (; s + 8 <= steps; s += 8) {
-                ulonglong2 v[8];
+            for (; s + 16 <= steps; s += 16) {
+                u64 v[16];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = st[(s + k) * 4 + j];
+                for (int k = 0; k < 16; ++k) v[k] = st[(s + k) * 8 + i8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    a0 += v[k].x; a1 += v[k].y;
-                    a0 ^= a0 >> 47; a0 ^= k0; a0 *= XXH_P32_1;
-                    a1 ^= a1 >> 47; a1 ^= k1; a1 *= XXH_P32_1;
-                }
+                for (int k = 0; k < 16; ++k) a = step(a, v[k]);
             }
-            for (; s < steps; ++s) {
-                ulonglong2 v = st[s * 4 + j];
-                a0 += v.x; a1 += v.y;
-                a0 ^= a0 >> 47; a0 ^= k0; a0 *= XXH_P32_1;
-                a1 ^= a1 >> 47; a1 ^= k1; a1 *= XXH_P32_1;
-            }
+            for (; s < steps; ++s) a = step(a, st[s * 8 + i8]);
         }
         __syncwarp();
     }
-    if (acc_out && lane < 4) { acc_out[2 * j] = a0; acc_out[2 * j + 1] = a1; }
+    if (acc_out && lane < 8) acc_out[i8] = a;
     if (!final) return;
 
-    // ---- tail (xxhash.h:3701-3711) + merge (:3714-3747); every lane needs its pair's accumulators
-    a0 = __shfl_sync(0xffffffffu, a0, j);
-    a1 = __shfl_sync(0xffffffffu, a1, j);
+    // ---- tail (xxhash.h:3701-3711) + merge (:3714-3747): pairwise layout again (lane l works for pair l & 3)
+    const u64 a0 = __shfl_sync(0xffffffffu, a, 2 * j);
+    const u64 a1 = __shfl_sync(0xffffffffu, a, 2 * j + 1);
     u64 dg;
     if (total <= 240) {
         dg = xxh3_small(tail_ptr, (u32)total);   // tail_pos == 0
