@@ -32,8 +32,12 @@
 #define FAST_RING      4096u
 #define FAST_RMASK     4095u
 #define FAST_LONG      32u     // lit or match >= this: executed cooperatively by the whole warp
-#define FAST_SCR       48u     // per-lane staging for a far match: 3 x 16 B covers 15 + 31 bytes
-#define FAST_WARP_SMEM (FAST_RING + 32u * FAST_SCR)
+#define FAST_SCR       80u     // per-lane staging for a far match: 5 x 16 B cover 15 + 64 bytes
+#define FAST_ST        64u     // far matches up to this length are staged (cp.async from L2)
+#define CR_SIZE        2048u   // per-warp staging ring for the compressed stream
+#define CR_MASK        2047u
+#define CR_ROW         512u    // one fill: 16 bytes per lane
+#define FAST_WARP_SMEM (FAST_RING + 32u * FAST_SCR + CR_SIZE)
 
 #define FE_DONE    0u   // status already final (guards, unsupported method)
 #define FE_FAST    1u   // block table filled, goes through K1/K2
@@ -428,6 +432,10 @@ ZPB_DEVINL u32 ldg8_coherent(const u8 *p) {
 #define FAST_LT 16u   // literal runs up to this go one-lane-per-sequence; longer ones warp-wide
 #define FAST_MT 16u   // same for matches
 
+#define DS_FINAL 0u   // source bytes are final (possibly after redirection by `shift`)
+#define DS_CHILD 1u   // source wholly inside lane `parent`'s match: being resolved
+#define DS_HARD  2u   // source straddles pending matches: executed in lane order
+
 struct FastExec {
     u32 rb;         // this warp's output ring (shared-window address): position p lives at rb + (p & FAST_RMASK)
     u32 scr_s;      // this lane's far-match staging (shared-window address)
@@ -563,6 +571,96 @@ struct FastExec {
     }
 };
 
+ZPB_DEVINL void cp_async16_cg(u32 smem_addr, const void *gptr) {   // L2 only: coherent with this kernel's own stores
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+
+// The compressed bytes of the block a warp is executing, staged through a per-warp shared-memory ring:
+// rows of CR_ROW bytes (16 per lane, cp.async), requested one row ahead of the step that reads them, so
+// the per-lane token / length / offset / literal reads of K2 are shared-memory reads.  Positions are
+// "ring coordinates" c = block position + skew, with the global address of coordinate 0 16-byte aligned.
+struct CompStage {
+    const u8 *gbase;     // global address of ring coordinate 0
+    const u8 *glo, *ghi; // readable range (the archive)
+    u32 rb;              // the ring (shared-window address)
+    u32 skew;
+    u32 fill;            // rows below this coordinate have been requested (multiple of CR_ROW)
+    u32 pending;         // cp.async groups committed since the last full wait (warp-uniform)
+    int lane;
+
+    ZPB_DEVINL void open(const u8 *src) {
+        cp_async_wait_all();         // a look-ahead row of the previous block may still be in flight
+        __syncwarp();
+        skew = (u32)((uintptr_t)src & 15u);
+        gbase = src - skew;
+        fill = 0;
+        pending = 0;
+    }
+    ZPB_DEVINL void request_row() {
+        const u32 c = fill + 16u * lane;
+        const u8 *g = gbase + c;
+        const u32 sdst = rb + (c & CR_MASK);
+        if (g >= glo && g + 16 <= ghi) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(g) : "memory");
+        } else if (g + 16 > glo && g < ghi) {   // straddles an end of the archive: byte by byte
+            for (u32 k = 0; k < 16; ++k)
+                if (g + k >= glo && g + k < ghi) sts8(sdst + k, g[k]);
+        }
+        cp_async_commit();
+        fill += CR_ROW;
+        ++pending;
+    }
+    // Makes block positions [s_lo, s_hi) readable through the ring; false when the span does not fit
+    // (the caller then reads global memory for this step).  Warp-uniform arguments and result.
+    ZPB_DEVINL bool prepare(u32 s_lo, u32 s_hi, u32 bsz) {
+        const u32 rlo = (s_lo + skew) & ~(CR_ROW - 1u);
+        const u32 rhi = (s_hi + skew + CR_ROW - 1u) & ~(CR_ROW - 1u);
+        if (rhi - rlo > CR_SIZE) return false;
+        if (fill < rlo) {            // rows nobody needs (after a step that went around the ring)
+            cp_async_wait_all();
+            pending = 0;
+            __syncwarp();
+            fill = rlo;
+        }
+        while (fill < rhi) request_row();
+        u32 ahead = 0;
+        if (fill + CR_ROW - rlo <= CR_SIZE && fill < bsz + skew) { request_row(); ahead = 1; }   // one row of look-ahead
+        else if (fill > rhi) ahead = 1;                                                          // requested by the previous step
+        if (pending > ahead) {
+            if (ahead) cp_async_wait_1(); else cp_async_wait_all();
+            pending = ahead;
+        }
+        __syncwarp();
+        return true;
+    }
+};
+struct CompRing {     // byte reader over the staging ring
+    u32 rb, skew;
+    ZPB_DEVINL u32 operator()(u32 p) const { return lds8(rb + ((p + skew) & CR_MASK)); }
+};
+struct CompGlobal {   // byte reader over global memory (steps whose span does not fit the ring)
+    const u8 *__restrict__ s;
+    ZPB_DEVINL u32 operator()(u32 p) const { return s[p]; }
+};
+// One sequence's control bytes (lz4.c:1797-1822, 1845-1860; K1 has validated them): literal length and
+// start, match offset and length (0 for the block's last sequence).
+template <class R>
+ZPB_DEVINL void fast_decode_seq(const R rd, u32 tok, u32 bsz, u32 &lit, u32 &lsrc, u32 &off, u32 &ml) {
+    const u32 t = rd(tok);
+    u32 p = tok + 1;
+    lit = t >> 4;
+    if (lit == 15) { u32 bb; do { bb = rd(p++); lit += bb; } while (bb == 255); }
+    lsrc = p;
+    p += lit;
+    if (p < bsz) {
+        off = rd(p) | (rd(p + 1) << 8);
+        p += 2;
+        ml = t & 15;
+        if (ml == 15) { u32 bb; do { bb = rd(p++); ml += bb; } while (bb == 255); }
+        ml += 4;
+    }
+}
+
 // unaligned 16-byte global load assembled from 4-byte-aligned words
 ZPB_DEVINL uint4 ldg128_unaligned(const u8 *p) {
     const u32 *s = reinterpret_cast<const u32 *>((uintptr_t)p & ~(uintptr_t)3);
@@ -594,6 +692,13 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
     x.rb = (u32)__cvta_generic_to_shared(k2_smem) + warp * FAST_WARP_SMEM;
     x.scr_s = x.rb + FAST_RING + lane * FAST_SCR;
     const u8 *arch_end = archive + asz;
+    CompStage cs;
+    cs.lane = lane;
+    cs.rb = x.rb + FAST_RING + 32u * FAST_SCR;
+    cs.glo = archive;
+    cs.ghi = arch_end;
+    cs.fill = cs.pending = cs.skew = 0;
+    cs.gbase = archive;
 
     for (;;) {
         u32 wslot = 0;
@@ -672,44 +777,42 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
             const u32 obase = x.done;
             const u32 bsz = B.bsz;
             const u32 nseq = B.nseq;
-            // two steps of descriptors and one step of token bytes are kept in flight
+            cs.open(src);
+            // two steps of descriptors are kept in flight; the compressed bytes come through the staging ring
             u32 d0 = (u32)lane < nseq ? dp[lane] : 0u;
             u32 d1 = 32u + lane < nseq ? dp[32 + lane] : 0u;
-            u32 t0 = (u32)lane < nseq ? (u32)src[d0 & 0xFFFFu] : 0u;
             for (u32 s0i = 0; s0i < nseq; s0i += 32) {
                 const bool have = s0i + lane < nseq;
-                const u32 d = d0, t = t0;
+                const u32 d = d0;
                 d0 = d1;
                 d1 = s0i + 64 + lane < nseq ? dp[s0i + 64 + lane] : 0u;
-                t0 = s0i + 32 + lane < nseq ? (u32)src[d0 & 0xFFFFu] : 0u;
+                // compressed bytes this step reads: from its first token to the next step's first token
+                const u32 s_lo = __shfl_sync(0xffffffffu, d & 0xFFFFu, 0);
+                const u32 s_nx = __shfl_sync(0xffffffffu, d0 & 0xFFFFu, 0);
+                const bool in_ring = cs.prepare(s_lo, s0i + 32 < nseq ? s_nx : bsz, bsz);   // warp-uniform
                 u32 lit = 0, lsrc = 0, off = 0, ml = 0, o = 0;
                 if (have) {
-                    u32 tok = d & 0xFFFFu;
                     o = obase + (d >> 16);
-                    u32 p = tok + 1;
-                    lit = t >> 4;
-                    if (lit == 15) { u32 bb; do { bb = src[p++]; lit += bb; } while (bb == 255); }
-                    lsrc = p;
-                    p += lit;
-                    if (p < bsz) {
-                        off = (u32)src[p] | ((u32)src[p + 1] << 8);
-                        p += 2;
-                        ml = t & 15;
-                        if (ml == 15) { u32 bb; do { bb = src[p++]; ml += bb; } while (bb == 255); }
-                        ml += 4;
-                    }
+                    if (in_ring) fast_decode_seq(CompRing{cs.rb, cs.skew}, d & 0xFFFFu, bsz, lit, lsrc, off, ml);
+                    else fast_decode_seq(CompGlobal{src}, d & 0xFFFFu, bsz, lit, lsrc, off, ml);
                 }
                 const u32 sz = lit + ml;
                 const u32 mo = o + lit, msrc = mo - off;
                 const u8 *__restrict__ sp = src + lsrc;
-                // short matches whose whole source is already in HBM: fetch it now (2 x 16 B cover any
-                // alignment of <= 16 bytes), park it in this lane's scratch after the literal phase
+                // matches whose whole source is already in HBM: fetch it now, asynchronously, into this lane's
+                // scratch (16-byte pieces straight from L2; up to 5 cover any alignment of <= 64 bytes)
                 const u32 abase = msrc & ~15u;
-                const bool staged = have && ml > 0 && ml <= FAST_MT && msrc + ml <= x.flushed;
-                uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+                const bool staged = have && ml > 0 && ml <= FAST_ST && msrc + ml <= x.flushed;
                 if (staged) {
-                    q0 = ldg128_coherent(x.gout + abase);
-                    if ((msrc - abase) + ml > 16) q1 = ldg128_coherent(x.gout + abase + 16);
+                    const u32 np = ((msrc - abase) + ml + 15u) >> 4;
+                    const u8 *g = x.gout + abase;
+                    cp_async16_cg(x.scr_s, g);
+                    if (np > 1) cp_async16_cg(x.scr_s + 16, g + 16);
+                    if (np > 2) {
+                        cp_async16_cg(x.scr_s + 32, g + 32);
+                        if (np > 3) cp_async16_cg(x.scr_s + 48, g + 48);
+                        if (np > 4) cp_async16_cg(x.scr_s + 64, g + 64);
+                    }
                 }
                 else if (have && ml > 0 && msrc < x.flushed) {
                     // longer match reaching back into flushed output: pull its lines towards L1 now, the
@@ -718,6 +821,47 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
                     if (pe > msrc + 512) pe = msrc + 512;
                     for (u32 a = msrc & ~127u; a < pe; a += 128)
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(x.gout + a));
+                }
+                cp_async_commit();
+                // ---- same-step dependencies.  A match whose source lies inside the output of an earlier
+                // match of this step would have to wait for it; instead, when the source range is wholly inside
+                // that match (the usual case: repeated words, records), it is redirected through the parent's
+                // offset (out[x] = out[x - off_k] holds for every x of the parent's match), parents' shifts are
+                // composed by pointer jumping, and the match reads bytes that are already final.
+                u32 shift = 0, dstate = DS_FINAL;
+                {
+                    const u32 o_first = __shfl_sync(0xffffffffu, o, 0);
+                    const bool has_mm = have && ml > 0;
+                    const u32 send_ = msrc + ml < mo ? msrc + ml : mo;
+                    const bool inside = has_mm && send_ > o_first && msrc < o;
+                    if (__any_sync(0xffffffffu, inside)) {
+                        const u32 okey = have ? o : 0xFFFFFFFFu;
+                        u32 k = 0;   // largest lane whose sequence starts at or below msrc
+#pragma unroll
+                        for (u32 st = 16; st; st >>= 1) {
+                            const u32 ot = __shfl_sync(0xffffffffu, okey, k + st);
+                            if (ot <= msrc) k += st;
+                        }
+                        const u32 mo_k = __shfl_sync(0xffffffffu, mo, k), e_k = __shfl_sync(0xffffffffu, o + sz, k),
+                                  off_k = __shfl_sync(0xffffffffu, off, k);
+                        u32 parent = 0;
+                        if (inside) {
+                            if (msrc < o_first) dstate = DS_HARD;                 // straddles the step start
+                            else if (send_ <= mo_k) dstate = DS_FINAL;           // inside lane k's literals
+                            else if (msrc >= mo_k && send_ <= e_k && off_k >= e_k - mo_k && off >= ml) {
+                                dstate = DS_CHILD; parent = k; shift = off_k;
+                            } else dstate = DS_HARD;
+                        }
+                        while (__any_sync(0xffffffffu, dstate == DS_CHILD)) {
+                            const u32 pst = __shfl_sync(0xffffffffu, dstate, parent),
+                                      psh = __shfl_sync(0xffffffffu, shift, parent),
+                                      pp = __shfl_sync(0xffffffffu, parent, parent);
+                            if (dstate == DS_CHILD) {
+                                if (pst == DS_HARD) { dstate = DS_HARD; shift = 0; }
+                                else { shift += psh; parent = pp; if (pst == DS_FINAL) dstate = DS_FINAL; }
+                            }
+                        }
+                    }
                 }
                 bool parked = false;
                 u32 todo = __ballot_sync(0xffffffffu, have);
@@ -741,17 +885,29 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
                     const u32 lo = x.ring_lo(seg_end);
                     {
                         const u32 da = x.ra(o);
-                        const bool lane_lit = in && lit <= FAST_LT && (o & FAST_RMASK) + lit <= FAST_RING;
+                        const u32 cq = (lsrc + cs.skew) & CR_MASK;    // literal source in the staging ring
+                        const bool lane_lit = in && lit <= FAST_LT && (o & FAST_RMASK) + lit <= FAST_RING &&
+                                              (!in_ring || cq + lit <= CR_SIZE);
                         const u32 mylit = lane_lit ? lit : 0u;
                         const u32 maxlit = __reduce_max_sync(0xffffffffu, mylit);
-#define LDL(u) ldg8nc<u>(spi)
 #define STL(u, v) sts8o<u>(dai, v)
-                        for (u32 i = 0; i < maxlit; i += 4) {
-                            const u8 *spi = sp + i;
-                            const u32 dai = da + i;
-                            FAST_BYTE4(LDL, STL, mylit, i)
-                        }
+                        if (in_ring) {
+                            const u32 ca = cs.rb + cq;
+#define LDL(u) lds8o<u>(cai)
+                            for (u32 i = 0; i < maxlit; i += 4) {
+                                const u32 cai = ca + i, dai = da + i;
+                                FAST_BYTE4(LDL, STL, mylit, i)
+                            }
 #undef LDL
+                        } else {
+#define LDL(u) ldg8nc<u>(spi)
+                            for (u32 i = 0; i < maxlit; i += 4) {
+                                const u8 *spi = sp + i;
+                                const u32 dai = da + i;
+                                FAST_BYTE4(LDL, STL, mylit, i)
+                            }
+#undef LDL
+                        }
 #undef STL
                         u32 cm = __ballot_sync(0xffffffffu, in && lit > 0 && !lane_lit);
                         while (cm) {
@@ -759,33 +915,38 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
                             cm &= cm - 1;
                             u32 O = __shfl_sync(0xffffffffu, o, r), S = __shfl_sync(0xffffffffu, lsrc, r),
                                 L = __shfl_sync(0xffffffffu, lit, r);
-                            x.coop_lit(O, src + S, L);
+                            if (in_ring) {
+                                for (u32 i = lane; i < L; i += 32) sts8(x.ra(O + i), lds8(cs.rb + ((S + cs.skew + i) & CR_MASK)));
+                            } else {
+                                x.coop_lit(O, src + S, L);
+                            }
                         }
                     }
-                    if (!parked) {
-                        if (staged) { sts128(x.scr_s, q0); sts128(x.scr_s + 16, q1); }
+                    if (!parked) {   // far-match sources requested at decode time have landed in the scratch
+                        cp_async_wait_all();
+                        cs.pending = 0;
                         parked = true;
                     }
-                    // ... then matches: one parallel round for everything whose source is final already
-                    // (one lane per match, linear shared-memory addresses), the rest warp-wide in order
+                    // ... then matches.  Everything whose source bytes are final (before this step, in literal
+                    // regions, or redirected there by the dependency pass above) goes first: one lane per short
+                    // match, warp-wide for the longer ones, in any order.  What is left (DS_HARD: a source that
+                    // straddles pending matches) runs warp-wide in lane order.
                     const bool has_m = in && ml > 0;
-                    const bool near_lin = msrc >= lo && (msrc & FAST_RMASK) + ml <= FAST_RING;
-                    const bool lane_ok = has_m && ml <= FAST_MT && (mo & FAST_RMASK) + ml <= FAST_RING &&
-                                         (staged || near_lin);
-                    const u32 sa = staged ? x.scr_s + (msrc - abase) : x.ra(msrc);
+                    const u32 esrc = msrc - shift;
+                    const bool near_lin = esrc >= lo && (esrc & FAST_RMASK) + ml <= FAST_RING;
+                    const bool from_scr = staged && shift == 0;
+                    const bool lane_ok = has_m && dstate == DS_FINAL && ml <= FAST_MT &&
+                                         (mo & FAST_RMASK) + ml <= FAST_RING && (from_scr || near_lin);
+                    const u32 sa = from_scr ? x.scr_s + (msrc - abase) : x.ra(esrc);
                     const u32 dm = x.ra(mo);
-                    const u32 send = msrc + ml < mo ? msrc + ml : mo;   // own overlap is handled in lane order
                     __syncwarp();
                     const u32 pend = __ballot_sync(0xffffffffu, has_m);
                     if (pend) {
-                        const int fl = __ffs(pend) - 1;
-                        const u32 front = __shfl_sync(0xffffffffu, mo, fl);
-                        const bool el = lane_ok && (lane == fl || send <= front);
-                        const u32 elmask = __ballot_sync(0xffffffffu, el);
+                        const u32 elmask = __ballot_sync(0xffffffffu, lane_ok);
                         if (elmask) {
-                            const u32 myml = el ? ml : 0u;
+                            const u32 myml = lane_ok ? ml : 0u;
                             const u32 maxml = __reduce_max_sync(0xffffffffu, myml);
-                            if (!__any_sync(0xffffffffu, el && off < 4)) {
+                            if (!__any_sync(0xffffffffu, lane_ok && off < 4)) {
 #define LDM(u) lds8o<u>(sai)
 #define STM(u, v) sts8o<u>(dmi, v)
                                 for (u32 i = 0; i < maxml; i += 4) {
@@ -798,17 +959,27 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
                                 for (u32 i = 0; i < maxml; ++i)
                                     if (i < myml) sts8(dm + i, lds8(sa + i));
                             }
-                            __syncwarp();
                         }
                         u32 rest = pend & ~elmask;
-                        const u32 pk = off | (ml << 16);
+                        const u32 hardmask = __ballot_sync(0xffffffffu, has_m && dstate == DS_HARD);
+                        const u32 offe = off + shift;
+                        const u32 scr_src = from_scr ? sa : 0u;   // linear copy of the source in the scratch
                         while (rest) {
                             int r = __ffs(rest) - 1;
                             rest &= rest - 1;
-                            const u32 MO = __shfl_sync(0xffffffffu, mo, r), PK = __shfl_sync(0xffffffffu, pk, r);
-                            const u32 OF = PK & 0xFFFFu, ML = PK >> 16;
-                            if (ML <= 64 && OF >= ML && MO - OF >= lo) {
-                                // the common dependent case: short, source still in the ring, no self-overlap
+                            if ((hardmask >> r) & 1u) __syncwarp();   // needs what earlier lanes have just written
+                            const u32 MO = __shfl_sync(0xffffffffu, mo, r), OF = __shfl_sync(0xffffffffu, offe, r),
+                                      ML = __shfl_sync(0xffffffffu, ml, r), SS = __shfl_sync(0xffffffffu, scr_src, r);
+                            if (SS && OF >= ML) {
+                                // far source, fetched at decode time (ML <= FAST_ST = 64)
+                                const u32 dd = MO + lane;
+                                u32 v0 = 0, v1 = 0;
+                                if ((u32)lane < ML) v0 = lds8(SS + lane);
+                                if ((u32)lane + 32 < ML) v1 = lds8(SS + lane + 32);
+                                if ((u32)lane < ML) sts8(x.ra(dd), v0);
+                                if ((u32)lane + 32 < ML) sts8(x.ra(dd + 32), v1);
+                            } else if (ML <= 64 && OF >= ML && MO - OF >= lo) {
+                                // the common case: short, source still in the ring, no self-overlap
                                 const u32 a = MO - OF + lane, dd = MO + lane;
                                 u32 v0 = 0, v1 = 0;
                                 if ((u32)lane < ML) v0 = lds8(x.ra(a));
@@ -818,7 +989,6 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
                             } else {
                                 x.coop_match(MO, OF, ML, lo);
                             }
-                            __syncwarp();
                         }
                     }
                     x.done = seg_end;
