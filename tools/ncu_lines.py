@@ -53,6 +53,7 @@ def main():
     ap.add_argument("--so", default="zpack_b200/libzpack_b200.so")
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--sass", action="store_true", help="also list the hottest SASS instructions")
+    ap.add_argument("--dump", default=None, help="write the whole kernel, in address order, with per-instruction counts")
     a = ap.parse_args()
     lines = sass_lines(a.so, a.kernel)
     raw = subprocess.run(["ncu", "-i", a.report, "--page", "source", "--csv", "--kernel-name", "regex:" + a.kernel],
@@ -94,6 +95,11 @@ def main():
     for ln, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:a.top]:
         name = f"{ln[0]}:{ln[1]}" if ln else "?"
         print(f"{name:>24} {100 * v[0] / tot_i:7.2f} {100 * v[1] / tot_s:7.2f} {v[0]:12.3e} {v[3] / max(v[0], 1):8.1f} {v[2]:12.3e}")
+    if a.dump:
+        with open(a.dump, "w") as f:
+            for inst, smp, off, ln, txt in sorted(hot, key=lambda t: t[2]):
+                name = f"{ln[0]}:{ln[1]}" if ln else "?"
+                f.write(f"{off:06x} {name:>20} {inst:11.4e} {100 * smp / tot_s:5.2f}%  {txt}\n")
     if a.sass:
         print("\nhottest SASS (by samples):")
         for inst, smp, off, ln, txt in sorted(hot, key=lambda t: -t[1])[:a.top]:

@@ -32,11 +32,13 @@
 #define FAST_RING      4096u
 #define FAST_RMASK     4095u
 #define FAST_LONG      32u     // lit or match >= this: executed cooperatively by the whole warp
+#ifndef FAST_SCR
 #define FAST_SCR       80u     // per-lane staging for a far match: 5 x 16 B cover 15 + 64 bytes
 #define FAST_ST        64u     // far matches up to this length are staged (cp.async from L2)
 #define CR_SIZE        2048u   // per-warp staging ring for the compressed stream
-#define CR_MASK        2047u
 #define CR_ROW         512u    // one fill: 16 bytes per lane
+#endif
+#define CR_MASK        (CR_SIZE - 1u)
 #define FAST_WARP_SMEM (FAST_RING + 32u * FAST_SCR + CR_SIZE)
 
 #define FE_DONE    0u   // status already final (guards, unsupported method)
@@ -202,6 +204,51 @@ ZPB_DEVINL uint4 lds128(u32 a) {
 }
 ZPB_DEVINL void sts128(u32 a, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+ZPB_DEVINL u32 lds32(u32 a) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+ZPB_DEVINL void sts32(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// Warp-lockstep copy inside shared memory: every lane moves its own n bytes (0 = idle) from s to d, any
+// alignment, ranges not overlapping.  Head bytes up to the destination's word boundary, then whole words
+// assembled from two aligned source words with a funnel shift, then tail bytes: 4 instructions per word
+// instead of 12 per 4 bytes of a byte loop.  The source words may straddle bytes outside [s, s+n) (and the
+// last one may be the word just after it): they are read, never stored.
+ZPB_DEVINL void lane_copy(u32 s, u32 d, u32 n) {
+    u32 h = (0u - d) & 3u;
+    h = h < n ? h : n;
+    {
+        u32 v0 = 0, v1 = 0, v2 = 0;
+        if (h > 0) v0 = lds8o<0>(s);
+        if (h > 1) v1 = lds8o<1>(s);
+        if (h > 2) v2 = lds8o<2>(s);
+        if (h > 0) sts8o<0>(d, v0);
+        if (h > 1) sts8o<1>(d, v1);
+        if (h > 2) sts8o<2>(d, v2);
+    }
+    s += h; d += h; n -= h;
+    const u32 nw = n >> 2, t = n & 3u;
+    const u32 maxnw = __reduce_max_sync(0xffffffffu, nw);
+    const u32 sw = s & ~3u, sh = (s & 3u) << 3;
+    u32 w0 = nw ? lds32(sw) : 0u;
+#pragma unroll 4
+    for (u32 k = 0; k < maxnw; ++k) {
+        if (k < nw) {
+            const u32 w1 = lds32(sw + 4 * k + 4);
+            sts32(d + 4 * k, __funnelshift_r(w0, w1, sh));
+            w0 = w1;
+        }
+    }
+    {
+        const u32 ts = s + 4 * nw, td = d + 4 * nw;
+        u32 v0 = 0, v1 = 0, v2 = 0;
+        if (t > 0) v0 = lds8o<0>(ts);
+        if (t > 1) v1 = lds8o<1>(ts);
+        if (t > 2) v2 = lds8o<2>(ts);
+        if (t > 0) sts8o<0>(td, v0);
+        if (t > 1) sts8o<1>(td, v1);
+        if (t > 2) sts8o<2>(td, v2);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ K1
@@ -429,8 +476,9 @@ ZPB_DEVINL u32 ldg8_coherent(const u8 *p) {
     return r;
 }
 
-#define FAST_LT 16u   // literal runs up to this go one-lane-per-sequence; longer ones warp-wide
-#define FAST_MT 16u   // same for matches
+#define FAST_LT  16u   // literal runs up to this go one-lane-per-sequence (from global memory); longer ones warp-wide
+#define FAST_LTR 32u   // the same when the source is the staging ring (word copies)
+#define FAST_MT  64u   // matches up to this go one-lane-per-sequence (non-overlapping, linear in shared memory)
 
 #define DS_FINAL 0u   // source bytes are final (possibly after redirection by `shift`)
 #define DS_CHILD 1u   // source wholly inside lane `parent`'s match: being resolved
@@ -600,7 +648,8 @@ struct CompStage {
         const u32 c = fill + 16u * lane;
         const u8 *g = gbase + c;
         const u32 sdst = rb + (c & CR_MASK);
-        if (g >= glo && g + 16 <= ghi) {
+        if (16u * lane >= CR_ROW) {
+        } else if (g >= glo && g + 16 <= ghi) {
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(g) : "memory");
         } else if (g + 16 > glo && g < ghi) {   // straddles an end of the archive: byte by byte
             for (u32 k = 0; k < 16; ++k)
@@ -680,7 +729,12 @@ ZPB_DEVINL uint4 ldg128_unaligned(const u8 *p) {
         if (p0_) ST(0, v0_); if (p1_) ST(1, v1_); if (p2_) ST(2, v2_); if (p3_) ST(3, v3_);           \
     }
 
-__global__ void __launch_bounds__(256, 3)
+#ifndef FAST_EXEC_CTAS
+#define FAST_EXEC_CTAS 3
+#endif
+// resident CTAs per SM the kernel is compiled for (registers) and launched with
+
+__global__ void __launch_bounds__(256, FAST_EXEC_CTAS)
 lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_entry *__restrict__ entries,
                      const u32 *__restrict__ order, u32 n, u32 *counter, const FastEntry *__restrict__ fe,
                      const FastBlock *__restrict__ fb, const u32 *__restrict__ desc, u32 *counters,
@@ -886,20 +940,14 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
                     {
                         const u32 da = x.ra(o);
                         const u32 cq = (lsrc + cs.skew) & CR_MASK;    // literal source in the staging ring
-                        const bool lane_lit = in && lit <= FAST_LT && (o & FAST_RMASK) + lit <= FAST_RING &&
-                                              (!in_ring || cq + lit <= CR_SIZE);
+                        const bool lane_lit = in && (o & FAST_RMASK) + lit <= FAST_RING &&
+                                              (in_ring ? lit <= FAST_LTR && cq + lit <= CR_SIZE : lit <= FAST_LT);
                         const u32 mylit = lane_lit ? lit : 0u;
-                        const u32 maxlit = __reduce_max_sync(0xffffffffu, mylit);
-#define STL(u, v) sts8o<u>(dai, v)
                         if (in_ring) {
-                            const u32 ca = cs.rb + cq;
-#define LDL(u) lds8o<u>(cai)
-                            for (u32 i = 0; i < maxlit; i += 4) {
-                                const u32 cai = ca + i, dai = da + i;
-                                FAST_BYTE4(LDL, STL, mylit, i)
-                            }
-#undef LDL
+                            lane_copy(cs.rb + cq, da, mylit);
                         } else {
+                            const u32 maxlit = __reduce_max_sync(0xffffffffu, mylit);
+#define STL(u, v) sts8o<u>(dai, v)
 #define LDL(u) ldg8nc<u>(spi)
                             for (u32 i = 0; i < maxlit; i += 4) {
                                 const u8 *spi = sp + i;
@@ -907,8 +955,8 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
                                 FAST_BYTE4(LDL, STL, mylit, i)
                             }
 #undef LDL
-                        }
 #undef STL
+                        }
                         u32 cm = __ballot_sync(0xffffffffu, in && lit > 0 && !lane_lit);
                         while (cm) {
                             int r = __ffs(cm) - 1;
@@ -935,7 +983,8 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
                     const u32 esrc = msrc - shift;
                     const bool near_lin = esrc >= lo && (esrc & FAST_RMASK) + ml <= FAST_RING;
                     const bool from_scr = staged && shift == 0;
-                    const bool lane_ok = has_m && dstate == DS_FINAL && ml <= FAST_MT &&
+                    const u32 offe = off + shift;
+                    const bool lane_ok = has_m && dstate == DS_FINAL && ml <= FAST_MT && offe >= ml &&
                                          (mo & FAST_RMASK) + ml <= FAST_RING && (from_scr || near_lin);
                     const u32 sa = from_scr ? x.scr_s + (msrc - abase) : x.ra(esrc);
                     const u32 dm = x.ra(mo);
@@ -943,26 +992,9 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
                     const u32 pend = __ballot_sync(0xffffffffu, has_m);
                     if (pend) {
                         const u32 elmask = __ballot_sync(0xffffffffu, lane_ok);
-                        if (elmask) {
-                            const u32 myml = lane_ok ? ml : 0u;
-                            const u32 maxml = __reduce_max_sync(0xffffffffu, myml);
-                            if (!__any_sync(0xffffffffu, lane_ok && off < 4)) {
-#define LDM(u) lds8o<u>(sai)
-#define STM(u, v) sts8o<u>(dmi, v)
-                                for (u32 i = 0; i < maxml; i += 4) {
-                                    const u32 sai = sa + i, dmi = dm + i;
-                                    FAST_BYTE4(LDM, STM, myml, i)
-                                }
-#undef LDM
-#undef STM
-                            } else {
-                                for (u32 i = 0; i < maxml; ++i)
-                                    if (i < myml) sts8(dm + i, lds8(sa + i));
-                            }
-                        }
+                        if (elmask) lane_copy(sa, dm, lane_ok ? ml : 0u);
                         u32 rest = pend & ~elmask;
                         const u32 hardmask = __ballot_sync(0xffffffffu, has_m && dstate == DS_HARD);
-                        const u32 offe = off + shift;
                         const u32 scr_src = from_scr ? sa : 0u;   // linear copy of the source in the scratch
                         while (rest) {
                             int r = __ffs(rest) - 1;
