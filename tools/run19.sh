@@ -1,2 +1,1 @@
-python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/s8c_bench_c2.json 2>gpurun_out/s8c_bench_c2.err; tail -3 gpurun_out/s8c_bench_c2.err; cat gpurun_out/s8c_bench_c2.json
-for c in 1 2 3; do ZPB_EXEC_CTAS=$c python bench.py --steps 3 --warmup 2 --no-cpu --no-e2e --entries 32768 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('ctas',$c, d['value'], d['roofline']['stages_ms'])"; done
+python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['roofline']['frac'], d['roofline']['stages_ms'])"

@@ -40,6 +40,7 @@
 #endif
 #define CR_MASK        (CR_SIZE - 1u)
 #define FAST_WARP_SMEM (FAST_RING + 32u * FAST_SCR + CR_SIZE)
+#define FAST_EXEC_SMEM (8u * FAST_WARP_SMEM + 48u)   // per CTA of 8 warps, plus slack at both ends
 
 #define FE_DONE    0u   // status already final (guards, unsupported method)
 #define FE_FAST    1u   // block table filled, goes through K1/K2
@@ -213,41 +214,68 @@ ZPB_DEVINL void sts32(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"
 // alignment, ranges not overlapping.  Head bytes up to the destination's word boundary, then whole words
 // assembled from two aligned source words with a funnel shift, then tail bytes: 4 instructions per word
 // instead of 12 per 4 bytes of a byte loop.  The source words may straddle bytes outside [s, s+n) (and the
-// last one may be the word just after it): they are read, never stored.
-ZPB_DEVINL void lane_copy(u32 s, u32 d, u32 n) {
+// last round may read up to four words past it): they are read, never stored.
+ZPB_DEVINL void lane_copy(u32 s, u32 d, u32 n) {   // idle lanes: n = 0 (s, d are not dereferenced)
     u32 h = (0u - d) & 3u;
     h = h < n ? h : n;
-    {
-        u32 v0 = 0, v1 = 0, v2 = 0;
-        if (h > 0) v0 = lds8o<0>(s);
-        if (h > 1) v1 = lds8o<1>(s);
-        if (h > 2) v2 = lds8o<2>(s);
-        if (h > 0) sts8o<0>(d, v0);
-        if (h > 1) sts8o<1>(d, v1);
-        if (h > 2) sts8o<2>(d, v2);
-    }
-    s += h; d += h; n -= h;
-    const u32 nw = n >> 2, t = n & 3u;
+    const u32 n2 = n - h;
+    const u32 nw = n2 >> 2, t = n2 & 3u;
+    const u32 s2 = s + h, d2 = d + h;            // d2 is word aligned whenever nw > 0
+    const u32 ts = s2 + 4 * nw, td = d2 + 4 * nw;
+    // edge bytes (<= 3 before the first whole word, <= 3 after the last): predicated, no branches
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p0, p1, p2, q0, q1, q2;\n\t"
+        ".reg .b32 a0, a1, a2, b0, b1, b2;\n\t"
+        "setp.gt.u32 p0, %0, 0;\n\t"
+        "setp.gt.u32 p1, %0, 1;\n\t"
+        "setp.gt.u32 p2, %0, 2;\n\t"
+        "setp.gt.u32 q0, %1, 0;\n\t"
+        "setp.gt.u32 q1, %1, 1;\n\t"
+        "setp.gt.u32 q2, %1, 2;\n\t"
+        "@p0 ld.shared.u8 a0, [%2];\n\t"
+        "@p1 ld.shared.u8 a1, [%2+1];\n\t"
+        "@p2 ld.shared.u8 a2, [%2+2];\n\t"
+        "@q0 ld.shared.u8 b0, [%4];\n\t"
+        "@q1 ld.shared.u8 b1, [%4+1];\n\t"
+        "@q2 ld.shared.u8 b2, [%4+2];\n\t"
+        "@p0 st.shared.u8 [%3], a0;\n\t"
+        "@p1 st.shared.u8 [%3+1], a1;\n\t"
+        "@p2 st.shared.u8 [%3+2], a2;\n\t"
+        "@q0 st.shared.u8 [%5], b0;\n\t"
+        "@q1 st.shared.u8 [%5+1], b1;\n\t"
+        "@q2 st.shared.u8 [%5+2], b2;\n\t"
+        "}" ::"r"(h), "r"(t), "r"(s), "r"(d), "r"(ts), "r"(td) : "memory");
     const u32 maxnw = __reduce_max_sync(0xffffffffu, nw);
-    const u32 sw = s & ~3u, sh = (s & 3u) << 3;
-    u32 w0 = nw ? lds32(sw) : 0u;
-#pragma unroll 4
-    for (u32 k = 0; k < maxnw; ++k) {
-        if (k < nw) {
-            const u32 w1 = lds32(sw + 4 * k + 4);
-            sts32(d + 4 * k, __funnelshift_r(w0, w1, sh));
-            w0 = w1;
-        }
-    }
-    {
-        const u32 ts = s + 4 * nw, td = d + 4 * nw;
-        u32 v0 = 0, v1 = 0, v2 = 0;
-        if (t > 0) v0 = lds8o<0>(ts);
-        if (t > 1) v1 = lds8o<1>(ts);
-        if (t > 2) v2 = lds8o<2>(ts);
-        if (t > 0) sts8o<0>(td, v0);
-        if (t > 1) sts8o<1>(td, v1);
-        if (t > 2) sts8o<2>(td, v2);
+    const u32 sw = s2 & ~3u, sh = (s2 & 3u) << 3;
+    for (u32 kb = 0; kb < maxnw; kb += 4) {      // four whole words per round
+        const u32 rem = nw > kb ? nw - kb : 0u;
+        const u32 sa = sw + 4 * kb, da = d2 + 4 * kb;
+        u32 a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.gt.u32 p, %5, 0;\n\t"
+            "@p ld.shared.u32 %0, [%6];\n\t"
+            "@p ld.shared.u32 %1, [%6+4];\n\t"
+            "@p ld.shared.u32 %2, [%6+8];\n\t"
+            "@p ld.shared.u32 %3, [%6+12];\n\t"
+            "@p ld.shared.u32 %4, [%6+16];\n\t"
+            "}" : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4) : "r"(rem), "r"(sa) : "memory");
+        const u32 w0 = __funnelshift_r(a0, a1, sh), w1 = __funnelshift_r(a1, a2, sh),
+                  w2 = __funnelshift_r(a2, a3, sh), w3 = __funnelshift_r(a3, a4, sh);
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p0, p1, p2, p3;\n\t"
+            "setp.gt.u32 p0, %0, 0;\n\t"
+            "setp.gt.u32 p1, %0, 1;\n\t"
+            "setp.gt.u32 p2, %0, 2;\n\t"
+            "setp.gt.u32 p3, %0, 3;\n\t"
+            "@p0 st.shared.u32 [%1], %2;\n\t"
+            "@p1 st.shared.u32 [%1+4], %3;\n\t"
+            "@p2 st.shared.u32 [%1+8], %4;\n\t"
+            "@p3 st.shared.u32 [%1+12], %5;\n\t"
+            "}" ::"r"(rem), "r"(da), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
     }
 }
 
@@ -743,7 +771,7 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FastExec x;
     x.lane = lane;
-    x.rb = (u32)__cvta_generic_to_shared(k2_smem) + warp * FAST_WARP_SMEM;
+    x.rb = (u32)__cvta_generic_to_shared(k2_smem) + 16u + warp * FAST_WARP_SMEM;   // 16 B of slack in front, 32 behind (lane_copy reads whole words)
     x.scr_s = x.rb + FAST_RING + lane * FAST_SCR;
     const u8 *arch_end = archive + asz;
     CompStage cs;
