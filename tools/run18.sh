@@ -1,1 +1,1 @@
-ncu --set full --clock-control none --import-source on -k regex:lz4_fast_exec -s 2 -c 1 -o gpurun_out/s8f_exec_text python tools/class_bench.py --entries 7104 --groups 8 --classes 1 --reps 1 > gpurun_out/s8f_ncu1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:lz4_fast_parse -s 2 -c 1 -o gpurun_out/s8h_parse python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/s8h_ncu.log 2>&1

@@ -583,17 +583,53 @@ struct FastExec {
         for (u32 i = lane; i < L; i += 32) sts8(ra(O + i), sp[i]);
     }
     // warp-wide match: out[MO + i] = out[MO + i - OF], i < ML, everything below MO final
+    // 16 source bytes starting at output position p (any alignment), from the ring or from HBM
+    ZPB_DEVINL uint4 load16_ring(u32 p) const {
+        const u32 b = p & ~3u, sh = (p & 3u) << 3;
+        const u32 w0 = lds32(ra(b)), w1 = lds32(ra(b + 4)), w2 = lds32(ra(b + 8)), w3 = lds32(ra(b + 12)), w4 = lds32(ra(b + 16));
+        return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                          __funnelshift_r(w3, w4, sh));
+    }
+    ZPB_DEVINL uint4 load16_hbm(u32 p) const {   // plain ld.global: the buffer is written by this kernel
+        const u8 *g = gout + (p & ~3u);
+        const u32 sh = (p & 3u) << 3;
+        u32 w0, w1, w2, w3, w4;
+        asm volatile("ld.global.u32 %0, [%5];\n\tld.global.u32 %1, [%5+4];\n\tld.global.u32 %2, [%5+8];\n\t"
+                     "ld.global.u32 %3, [%5+12];\n\tld.global.u32 %4, [%5+16];"
+                     : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3), "=r"(w4) : "l"(g) : "memory");
+        return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                          __funnelshift_r(w3, w4, sh));
+    }
+    // warp-wide match: out[MO + i] = out[MO + i - OF], i < ML, everything below MO final
     ZPB_DEVINL void coop_match(u32 MO, u32 OF, u32 ML, u32 lo) const {
-        if (OF == 1 && ML >= 64 && (MO & FAST_RMASK) + ML <= FAST_RING) {
-            // run of one byte (lz4.c:1917-1921 pattern case): aligned 16-byte fills
-            u32 v = rd(MO - 1, lo) * 0x01010101u;
-            u32 a = ra(MO), head = (0u - a) & 15u;
-            if ((u32)lane < head) sts8(a + lane, v);
-            a += head;
-            u32 n16 = (ML - head) >> 4;
-            for (u32 c = lane; c < n16; c += 32) sts128(a + 16 * c, make_uint4(v, v, v, v));
-            u32 donev = head + (n16 << 4);
-            if ((u32)lane < ML - donev) sts8(ra(MO) + donev + lane, v);
+        if (ML >= 32 && (OF == 1 || OF == 2 || OF == 4)) {
+            // short period dividing 4 (runs; lz4.c:1917-1921 pattern case): one 32-bit pattern word, 16-byte fills.
+            // Byte j of W is the byte that belongs at any output position congruent to j mod 4.
+            u32 W = 0;
+#pragma unroll
+            for (u32 j = 0; j < 4; ++j) W |= rd(MO - OF + ((j - MO) & (OF - 1u)), lo) << (8 * j);
+            const u32 head = (0u - MO) & 15u;                    // ML >= 32 > head
+            if ((u32)lane < head) sts8(ra(MO + lane), W >> (8 * ((MO + lane) & 3u)));
+            const u32 body = MO + head, n16 = (ML - head) >> 4;  // 16-aligned ring positions never straddle the ring end
+            for (u32 c = lane; c < n16; c += 32) sts128(ra(body + 16 * c), make_uint4(W, W, W, W));
+            const u32 tpos = body + (n16 << 4), tail = MO + ML - tpos;
+            if ((u32)lane < tail) sts8(ra(tpos + lane), W >> (8 * (lane & 3u)));
+            return;
+        }
+        if (ML >= 32 && OF >= ML && (MO - OF >= lo || MO - OF + ML + 4 <= lo)) {   // +4: whole-word reads stay below lo
+            // long, not self-overlapping, source wholly in the ring or wholly in HBM: 16-byte destination chunks
+            // (aligned stores), each lane assembling its 16 source bytes from aligned words
+            const bool hbm = MO - OF < lo;
+            const u32 head = (0u - MO) & 15u;
+            if ((u32)lane < head) sts8(ra(MO + lane), rd(MO - OF + lane, lo));
+            const u32 body = MO + head, n16 = (ML - head) >> 4;
+            for (u32 c = lane; c < n16; c += 32) {
+                const u32 dpos = body + 16 * c;
+                const uint4 v = hbm ? load16_hbm(dpos - OF) : load16_ring(dpos - OF);
+                sts128(ra(dpos), v);
+            }
+            const u32 tpos = body + (n16 << 4), tail = MO + ML - tpos;
+            if ((u32)lane < tail) sts8(ra(tpos + lane), rd(tpos - OF + lane, lo));
             return;
         }
         if (MO - OF >= lo) {
