@@ -558,7 +558,10 @@ def run_ours(args):
                                         else "scan -> zstd_unpack_kernel (warp per entry), 5 launches per step"),
                            "archive_prep_s": round(prep_s, 1)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "frac": achieved / peak,
+                             "traffic": (algo_bytes * NCU_TRAFFIC_RATIO[args.workload][0] if args.workload in NCU_TRAFFIC_RATIO else None),
+                             "traffic_source": (NCU_TRAFFIC_RATIO[args.workload][1] if args.workload in NCU_TRAFFIC_RATIO else None),
+                             "peak_source": peak_src,
                              "kernel": wl["kernel"], "kernel_ms": kern_ms,
                              "algorithmic_bytes_per_launch": algo_bytes,
                              "all_kernels_ms": all_kern_ms, "all_kernels_frac": algo_bytes / (all_kern_ms * 1e-3) / 1e9 / peak,
@@ -584,6 +587,13 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
     ctx.close()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from one `ncu --set full` capture, as a ratio
+# to the algorithmic bytes of the captured launch (the capture runs fewer entries than the bench; the ratio carries over)
+NCU_TRAFFIC_RATIO = {
+    "c2": (7.0757 / (12297207239 * 28416 / 65536 / 1e9), "profiles/r1_ncu_full_exec_v3_mixed28416.csv: 3.363 + 3.713 GB for 28 416 entries"),
+}
 
 
 def main():
