@@ -67,6 +67,7 @@ struct zpb_ctx {
     cudaEvent_t evs[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // descriptor / result scratch
     DevBuf d_desc, d_order, d_res, d_counter;
+    std::vector<uint16_t> h_keys;   // cost key per entry of the batch being prepared
     PinBuf h_stage;
     // staging arenas for the *_host entry points
     DevBuf d_in, d_out;
@@ -273,54 +274,66 @@ static cudaError_t launch_zstd(zpb_ctx *ctx, cudaStream_t s, const u8 *arch, u8 
     return cudaGetLastError();
 }
 
-// Expensive entries first: compressed LZ4/zstd bytes are a good proxy for sequence count;
-// stored-ish entries (ratio ~1) and raw copies are cheap per byte, so they go last.
-static void build_order(const zpb_entry *e, u64 n, u32 *order) {
-    // counting sort on a coarse cost key (descending): O(n), stable, no comparisons
-    auto key = [&](u64 i) -> u32 {
-        const zpb_entry &x = e[i];
-        u64 c = (x.method == ZPB_METHOD_NONE || x.comp_size >= x.uncomp_size) ? x.comp_size / 16 : x.comp_size;
-        c >>= 9;  // 512-byte cost buckets
-        return c > 1023 ? 0u : 1023u - (u32)c;
-    };
-    std::vector<u32> head(1025, 0);
-    for (u64 i = 0; i < n; ++i) ++head[key(i) + 1];
-    for (u32 k = 0; k < 1024; ++k) head[k + 1] += head[k];
-    for (u64 i = 0; i < n; ++i) order[head[key(i)]++] = (u32)i;
-}
-
 static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_size, u8 *d_out,
                               u64 out_size, const zpb_entry *entries, u64 n, int32_t *status,
                               u64 *digest, cudaStream_t s) {
     if (n == 0) return ZPB_OK;
     if (n > 0x7fffffffull) return fail(ctx, ZPB_E_ARG, "too many entries in one batch");
-    for (u64 i = 0; i < n; ++i) {
-        const zpb_entry &e = entries[i];
-        if (e.comp_size == 0) continue;
-        if (e.dst_off > out_size || e.dst_cap > out_size - e.dst_off)
-            return fail(ctx, ZPB_E_ARG, "entry output slot exceeds the output buffer");
-    }
     size_t desc_b = n * sizeof(zpb_entry), ord_b = n * sizeof(u32);
     size_t res_b = n * (sizeof(int) + sizeof(u64));
     if (!ctx->d_desc.ensure(desc_b) || !ctx->d_order.ensure(ord_b) || !ctx->d_res.ensure(res_b + 64) ||
         !ctx->d_counter.ensure(256) || !ctx->h_stage.ensure(desc_b + ord_b + res_b + 64 + n * sizeof(FastAux)))
         return fail(ctx, ZPB_E_NOMEM, "scratch allocation failed");
 
+    // ---- one pass over the descriptors (the GPU idles while the host prepares a batch, so this is kept to a single
+    // read of the 64-byte records): bounds check, copy into pinned staging, coarse cost key for the work order
+    // (expensive entries first: compressed bytes are a good proxy for sequence count; stored-ish entries and raw
+    // copies are cheap per byte), and the fast path's scratch layout (block slots + descriptor slots per entry).
+    u8 *hs = (u8 *)ctx->h_stage.p;
+    zpb_entry *h_desc = (zpb_entry *)hs;
+    u32 *h_order = (u32 *)(hs + desc_b);
+    FastAux *h_aux = (FastAux *)(hs + desc_b + ord_b + res_b + 64);
+    ctx->h_keys.resize(n);
+    u16 *keys = ctx->h_keys.data();
+    u32 head[1025];
+    memset(head, 0, sizeof(head));
     bool any_zstd = false;
-    for (u64 i = 0; i < n && !any_zstd; ++i) any_zstd = entries[i].method == ZPB_METHOD_ZSTD;
+    const bool internal = ctx->cur_partials != nullptr;   // method codes above a byte are internal (comp_method is a u8, lib/zpack.h:79)
+    u64 slots = 0, ndesc = 0;
+    for (u64 i = 0; i < n; ++i) {
+        zpb_entry e = entries[i];
+        if (e.comp_size != 0 && (e.dst_off > out_size || e.dst_cap > out_size - e.dst_off))
+            return fail(ctx, ZPB_E_ARG, "entry output slot exceeds the output buffer");
+        any_zstd |= e.method == ZPB_METHOD_ZSTD;
+        u64 c = (e.method == ZPB_METHOD_NONE || e.comp_size >= e.uncomp_size) ? e.comp_size / 16 : e.comp_size;
+        c >>= 9;  // 512-byte cost buckets, descending
+        const u32 key = c > 1023 ? 0u : 1023u - (u32)c;
+        keys[i] = (u16)key;
+        ++head[key + 1];
+        u32 ns = 0; u64 nd = 0;
+        if (e.uncomp_size < 0x7fffffffull && e.comp_size) {
+            if (e.method == ZPB_METHOD_NONE) ns = 1;
+            else if (e.method == ZPB_M_LZ4_BLOCK) {
+                ns = 1;
+                nd = ((e.comp_size / 3 + 20) + 3) & ~3ull;
+            } else if (e.method == ZPB_METHOD_LZ4) {
+                ns = (u32)(e.uncomp_size >> 16) + 2;
+                nd = ((e.comp_size / 3 + 12ull * ns + 8) + 3) & ~3ull;
+            }
+        }
+        h_aux[i].desc_base = ndesc; h_aux[i].slot_base = (u32)slots; h_aux[i].nslots = ns;
+        slots += ns; ndesc += nd;
+        if (!internal && e.method > 0xFFu) e.method = 0xFFu;
+        h_desc[i] = e;
+    }
+    if (slots > 0x7fffffffull) return fail(ctx, ZPB_E_ARG, "too many blocks in one batch");
+    for (u32 k = 0; k < 1024; ++k) head[k + 1] += head[k];
+    for (u64 i = 0; i < n; ++i) h_order[head[keys[i]]++] = (u32)i;   // counting sort: O(n), stable
+
     if (any_zstd && (!ctx->d_zlist.ensure(n * 4) ||
                      !ctx->d_zlit.ensure((size_t)ctx->zs_grid * ZS_WARPS * ZS_LIT_SCRATCH)))
         return fail(ctx, ZPB_E_NOMEM, "zstd scratch allocation failed");
     ctx->zstd_ms = 0.f;
-
-    u8 *hs = (u8 *)ctx->h_stage.p;
-    zpb_entry *h_desc = (zpb_entry *)hs;
-    u32 *h_order = (u32 *)(hs + desc_b);
-    memcpy(h_desc, entries, desc_b);
-    if (!ctx->cur_partials)   // method codes above a byte are internal (comp_method is a u8, lib/zpack.h:79): never from callers
-        for (u64 i = 0; i < n; ++i)
-            if (h_desc[i].method > 0xFFu) h_desc[i].method = 0xFFu;
-    build_order(entries, n, h_order);
     u64 *d_digest = (u64 *)ctx->d_res.p;
     int *d_status = (int *)((u8 *)ctx->d_res.p + n * sizeof(u64));
 
@@ -330,25 +343,6 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
     if (ctx->fast) {
         // ---- scan -> parse -> exec (lz4_fast.cuh), then the general kernel over whatever they declined
         size_t aux_b = n * sizeof(FastAux);
-        FastAux *h_aux = (FastAux *)(hs + desc_b + ord_b + res_b + 64);
-        u64 slots = 0, ndesc = 0;
-        for (u64 i = 0; i < n; ++i) {
-            const zpb_entry &e = entries[i];
-            u32 ns = 0; u64 nd = 0;
-            if (e.uncomp_size < 0x7fffffffull && e.comp_size) {
-                if (e.method == ZPB_METHOD_NONE) ns = 1;
-                else if (e.method == ZPB_M_LZ4_BLOCK) {
-                    ns = 1;
-                    nd = ((e.comp_size / 3 + 20) + 3) & ~3ull;
-                } else if (e.method == ZPB_METHOD_LZ4) {
-                    ns = (u32)(e.uncomp_size >> 16) + 2;
-                    nd = ((e.comp_size / 3 + 12ull * ns + 8) + 3) & ~3ull;
-                }
-            }
-            h_aux[i].desc_base = ndesc; h_aux[i].slot_base = (u32)slots; h_aux[i].nslots = ns;
-            slots += ns; ndesc += nd;
-        }
-        if (slots > 0x7fffffffull) return fail(ctx, ZPB_E_ARG, "too many blocks in one batch");
         if (!ctx->d_aux.ensure(aux_b) || !ctx->d_fe.ensure(n * sizeof(FastEntry)) ||
             !ctx->d_fb.ensure((slots + 1) * sizeof(FastBlock)) || !ctx->d_plist.ensure((slots + 1) * 4) ||
             !ctx->d_glist.ensure(n * 4) || !ctx->d_fdesc.ensure((ndesc + 4) * 4))
