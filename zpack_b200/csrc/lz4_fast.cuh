@@ -39,7 +39,7 @@
 #define CR_ROW         512u    // one fill: 16 bytes per lane
 #endif
 #define CR_MASK        (CR_SIZE - 1u)
-#define FAST_WARP_SMEM (FAST_RING + 32u * FAST_SCR + CR_SIZE)
+#define FAST_WARP_SMEM (FAST_RING + 32u * FAST_SCR + CR_SIZE + 32u)   // + 32: lane_copy's whole-word over-reads past the staging ring stay inside the warp's own region
 #define FAST_EXEC_SMEM (8u * FAST_WARP_SMEM + 48u)   // per CTA of 8 warps, plus slack at both ends
 
 #define FE_DONE    0u   // status already final (guards, unsupported method)
