@@ -40,7 +40,10 @@
 #endif
 #define CR_MASK        (CR_SIZE - 1u)
 #define FAST_WARP_SMEM (FAST_RING + 32u * FAST_SCR + CR_SIZE + 32u)   // + 32: lane_copy's whole-word over-reads past the staging ring stay inside the warp's own region
-#define FAST_EXEC_SMEM (8u * FAST_WARP_SMEM + 48u)   // per CTA of 8 warps, plus slack at both ends
+#ifndef FAST_EXEC_WARPS
+#define FAST_EXEC_WARPS 8u
+#endif
+#define FAST_EXEC_SMEM (FAST_EXEC_WARPS * FAST_WARP_SMEM + 48u)   // per CTA, plus slack at both ends
 
 #define FE_DONE    0u   // status already final (guards, unsupported method)
 #define FE_FAST    1u   // block table filled, goes through K1/K2
@@ -798,7 +801,7 @@ ZPB_DEVINL uint4 ldg128_unaligned(const u8 *p) {
 #endif
 // resident CTAs per SM the kernel is compiled for (registers) and launched with
 
-__global__ void __launch_bounds__(256, FAST_EXEC_CTAS)
+__global__ void __launch_bounds__(32 * FAST_EXEC_WARPS, FAST_EXEC_CTAS)
 lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_entry *__restrict__ entries,
                      const u32 *__restrict__ order, u32 n, u32 *counter, const FastEntry *__restrict__ fe,
                      const FastBlock *__restrict__ fb, const u32 *__restrict__ desc, u32 *counters,

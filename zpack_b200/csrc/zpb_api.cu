@@ -365,7 +365,7 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
         CK(ctx, cudaGetLastError());
         CK(ctx, cudaEventRecord(ctx->evs[2], s));
         static const int k2_ctas = [] { const char *e = getenv("ZPB_EXEC_CTAS"); int v = e ? atoi(e) : 0; return v > 0 && v <= 8 ? v : FAST_EXEC_CTAS; }();
-        lz4_fast_exec_kernel<<<ctx->sm_count * k2_ctas, 256, FAST_EXEC_SMEM, s>>>(
+        lz4_fast_exec_kernel<<<ctx->sm_count * k2_ctas, 32 * FAST_EXEC_WARPS, FAST_EXEC_SMEM, s>>>(
             d_archive, archive_size, d_out, d_e, d_ord, (u32)n, cnt + 3, (const FastEntry *)ctx->d_fe.p,
             (const FastBlock *)ctx->d_fb.p, (const u32 *)ctx->d_fdesc.p, cnt, (u32 *)ctx->d_glist.p, d_status,
             d_digest, ctx->cur_partials);
