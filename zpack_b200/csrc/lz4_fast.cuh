@@ -299,6 +299,7 @@ ZPB_DEVINL void cp_async64(u32 s, const void *g) {  // one whole 64-byte chunk, 
 ZPB_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 ZPB_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 ZPB_DEVINL void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+ZPB_DEVINL void cp_async_wait_2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
 
 // Per-lane view of one block's compressed bytes through a 256-byte staging ring.  Positions are
 // "ring coordinates" q = block position + skew, so that q & 255 is both the ring slot and the low
@@ -335,17 +336,38 @@ struct LaneStage {
             }
         }
     }
-    // afterwards ring coordinates [q & ~63, (q & ~63) + 192) are readable
+    // Afterwards ring coordinates [q & ~63, (q & ~63) + 128) are readable: chunks c and c+1 are complete, c+2 and c+3
+    // may still be in flight.  cp.async groups retire per WARP in commit order, whatever lanes took part, so the wait
+    // is kept as loose as correctness allows: chunk c+1 is older than this lane's own two newest commits (c+2, c+3),
+    // hence `wait_group 2` always covers it, and it does not wait for the chunk a neighbouring lane asked for one
+    // iteration ago.  The usual case — exactly one new chunk, wholly inside the archive — is predicated, not branched:
+    // the 32 lanes cross their 64-byte boundaries in different iterations, so a divergent refill would run in nearly
+    // every iteration of the warp.  (Measured on one warp per SM, 5 700-sequence text blocks: 2.75 -> 2.25 ms.)
     ZPB_DEVINL void ensure(u32 q) {
-        u32 c = q >> 6;
-        if (c + 4 > nreq) refill(c);
+        const u32 c = q >> 6;
+        const bool one = nreq == c + 3 && nreq >= klo && nreq < khi;
+        if (c + 4 > nreq && !one) { refill(c); return; }
+        const u8 *g = gbase + ((u64)nreq << 6);
+        const u32 sdst = row_s + ((nreq << 6) & 255u);
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.u32 p, %0, 0;\n\t"
+            "@p cp.async.ca.shared.global [%1], [%2], 16;\n\t"
+            "@p cp.async.ca.shared.global [%1+16], [%2+16], 16;\n\t"
+            "@p cp.async.ca.shared.global [%1+32], [%2+32], 16;\n\t"
+            "@p cp.async.ca.shared.global [%1+48], [%2+48], 16;\n\t"
+            "@p cp.async.commit_group;\n\t"
+            "cp.async.wait_group 2;\n\t"
+            "}" ::"r"((u32)one), "r"(sdst), "l"(g) : "memory");
+        nreq += one ? 1u : 0u;
     }
     ZPB_DEVINL void refill(u32 c) {
         u32 lo = nreq > c ? nreq : c;
         for (u32 k = lo; k < c + 4; ++k) request(k);
         cp_async_commit();
         nreq = c + 4;
-        if (c + 4 - lo > 1) cp_async_wait_all(); else cp_async_wait_1();
+        if (c + 4 - lo > 1) cp_async_wait_all(); else cp_async_wait_2();
     }
     ZPB_DEVINL u32 rd(u32 q) const { return lds8(row_s + (q & 255u)); }
 };
@@ -395,7 +417,7 @@ lz4_fast_parse_kernel(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, co
         bool bad = false, fin = false;
         sg.ensure(q);
         const u32 token = sg.rd(q);
-        const u32 lim = (q & ~63u) + 192u;   // readable without another ensure
+        const u32 lim = (q & ~63u) + 128u;   // readable without another ensure
         // Common shape first, branch-free: at most one length-extension byte each, offset inside the
         // staged window, not the block's last sequences.  Everything else takes the general walk below.
         bool fast = false;
