@@ -27,6 +27,9 @@ WORKLOADS = {
     "c4": {"method": 1, "metric": "zstd_unpack_xxh3_verify_uncompressed_GBps", "entries": 32768,
            "kernel": "zstd_unpack_kernel", "stage": "zstd_ms",
            "what": "C4: zstd level-3 unpack + XXH3-64 verify (frames written by the reference's ZSTD_compress)"},
+    # LZ4 pack of the C2 corpus (run_c3 below); `entries` = files per GPU
+    "c3": {"method": 2, "metric": "lz4_pack_xxh3_uncompressed_GBps", "entries": 65536, "kernel": "lz4_pack_kernel",
+           "stage": "pack_ms", "what": "C3: LZ4 pack (independent 64 KB blocks) + XXH3-64 of the input"},
     # one entry of gpus x 2 GiB, independent 64 KB blocks, sharded by blocks (run_c5 below); `entries` = blocks per GPU
     "c5": {"method": 2, "metric": "lz4_single_entry_unpack_xxh3_verify_uncompressed_GBps", "entries": 32768,
            "kernel": "lz4_fast_exec_kernel", "stage": "exec_ms",
@@ -177,6 +180,23 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     n_sample = args.ref_entries
     wl = WORKLOADS[args.workload]
+    if args.workload == "c3":
+        data, _, _ = build_corpus(n_sample, ENTRY_SIZE, 0, cores)
+        for _ in range(args.warmup):
+            cpu_pack_throughput(data, ENTRY_SIZE, min(n_sample, 512), cores)
+        vals = [cpu_pack_throughput(data, ENTRY_SIZE, n_sample, cores) for _ in range(args.steps)]
+        value, kind = float(np.mean([v[0] for v in vals])), vals[0][2]
+        line = {"metric": wl["metric"], "value": value, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * n_sample * ENTRY_SIZE / (value * 1e9),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "impl": "reference",
+                "config": {"workload": f"{wl['what']}, sample of {n_sample} x 128 KiB files (zpk-synth-v1), reference "
+                                       "zpack_write_archive (level 0) on host cores", "ratio": vals[0][3]},
+                "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": kind,
+                                 "sample": f"{n_sample} files x 128 KiB per step, {cores} independent writers"},
+                "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
     arch = build_archive(n_sample, ENTRY_SIZE, independent=False, method=wl["method"])
     d = container.parse(arch)
     for _ in range(args.warmup):
@@ -589,6 +609,205 @@ def run_ours(args):
     ctx.close()
 
 
+# ------------------------------------------------------------------ C3: pack
+_C3_SHARED = None
+
+
+def _gen_shard(args):
+    """Worker (fork): fills its slice of the shared corpus buffer, returns the XXH3-64 of every entry and the size
+    the CPU checker's reference-format writer gives for every 17th entry (ratio reference, untimed)."""
+    lo, hi, first, size = args
+    from zpack_b200 import corpus
+    from oracle import oracle as O
+    buf = np.frombuffer(_C3_SHARED, np.uint8)
+    hashes, ref = np.empty(hi - lo, np.uint64), 0
+    for k, i in enumerate(range(lo, hi)):
+        b = corpus.entry_bytes(first + i, size)
+        buf[i * size:(i + 1) * size] = b
+        hashes[k] = O.xxh3_port(b)
+        if i % 17 == 0:   # 17: coprime with the 4-class cycle of the corpus
+            ref += len(O.lz4f_encode_port(b, 0, False))
+    return lo, hashes, ref
+
+
+def build_corpus(n, size, first, workers):
+    """(n x size) bytes of zpk-synth-v1 in one anonymous shared mapping, filled by `workers` forked processes."""
+    import mmap
+    import multiprocessing as mp
+    global _C3_SHARED
+    _C3_SHARED = mmap.mmap(-1, n * size)
+    step = max(1, min(256, n // (workers * 4) or 1))
+    jobs = [(a, min(a + step, n), first, size) for a in range(0, n, step)]
+    hashes, ref = np.empty(n, np.uint64), 0
+    with mp.get_context("fork").Pool(workers) as pool:
+        for lo, hs, r in pool.imap_unordered(_gen_shard, jobs, chunksize=1):
+            hashes[lo:lo + len(hs)] = hs
+            ref += r
+    return np.frombuffer(_C3_SHARED, np.uint8), hashes, ref * 17
+
+
+def cpu_pack_throughput(data, size, n_sample, threads):
+    """The reference's own writer (zpack_write_archive into a heap writer, oracle/_ref) over `n_sample` files split
+    across `threads` independent writers (the reference writer is single-threaded by contract, lib/zpack.h:476-485:
+    this is the T-way sharded variant of SURVEY section 8(d)); the port's frame writer when _ref is absent."""
+    from oracle import oracle as O
+    n_sample = min(n_sample, len(data) // size)
+    threads = max(1, min(threads, n_sample))
+    use_ref = O.have_ref()
+    comp = [0] * threads
+
+    def work(t):
+        idx = range(t, n_sample, threads)
+        bufs = [data[i * size:(i + 1) * size] for i in idx]
+        if use_ref:
+            comp[t] = len(O.write_archive_ref([f"f{i}" for i in idx], bufs, 2, 0))
+        else:
+            comp[t] = sum(len(O.lz4f_encode_port(b, 0, False)) for b in bufs)
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    dt = time.perf_counter() - t0
+    return n_sample * size / dt / 1e9, dt, ("reference" if use_ref else "port"), n_sample * size / max(1, sum(comp))
+
+
+def run_c3(args):
+    """BASELINE config C3: LZ4 pack of the C2 corpus, files sharded across ranks, no collective; the compressed-size
+    offset table is assembled on the host from comp_size[].  Gates before timing: every status 0, every digest equal
+    to the XXH3-64 of the input, every GPU-written frame decodes back to its digest (GPU reader, all files) and a
+    sample opens bit-exactly in the CPU checker / the unmodified reference reader."""
+    import torch
+    import torch.distributed as dist
+    import zpack_b200
+    from zpack_b200 import lib as zlib
+    from oracle import oracle as O
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl = WORKLOADS["c3"]
+    n = args.entries or wl["entries"]
+    size = ENTRY_SIZE
+    t_prep = time.time()
+    data, hashes, ref_comp = build_corpus(n, size, rank * n, max(1, (os.cpu_count() or 1) // world))
+    prep_s = time.time() - t_prep
+    ctx = zpack_b200.Context(local)
+    cap = ctx.pack_bound(2, size)
+    slot = (cap + 15) & ~15
+    f = np.zeros(n, zlib.File)
+    f["src_off"] = np.arange(n, dtype=np.uint64) * size
+    f["size"] = size
+    f["dst_off"] = np.arange(n, dtype=np.uint64) * slot
+    f["dst_cap"] = cap
+    f["method"] = 2
+    in_size, out_size = n * size, n * slot
+    h_in = torch.from_numpy(data).pin_memory()
+    d_in = h_in.cuda()
+    d_out = torch.empty(out_size, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        comp, dg, st = ctx.pack_device(d_in, in_size, d_out, out_size, f, stream)
+    assert (st == 0).all() and np.array_equal(dg, hashes), "pack parity gate failed: status / XXH3-64 of the input"
+    # validity gates: (1) every frame decodes back to its digest on the GPU reader, (2) a sample through the CPU checker
+    e = np.zeros(n, zlib.Entry)
+    e["src_off"], e["comp_size"], e["uncomp_size"] = f["dst_off"], comp, size
+    e["dst_off"] = np.arange(n, dtype=np.uint64) * size
+    e["dst_cap"], e["hash"], e["method"] = size, hashes, 2
+    d_back = torch.empty(in_size, dtype=torch.uint8, device="cuda")
+    st2, dg2 = ctx.unpack_device(d_out, out_size, d_back, in_size, e, stream)
+    assert (st2 == 0).all() and np.array_equal(dg2, hashes), "GPU-written frames do not read back"
+    assert torch.equal(d_back[:64 * size], d_in[:64 * size])
+    del d_back
+    for i in range(0, n, max(1, n // 32)):
+        fr = d_out[int(f["dst_off"][i]):int(f["dst_off"][i]) + int(comp[i])].cpu().numpy()
+        rc, got, _ = O.read_entry_port(2, fr, size, size, int(hashes[i]))
+        assert rc == 0 and np.array_equal(got, data[i * size:(i + 1) * size]), "CPU checker rejects a GPU-written frame"
+    comp_bytes = int(comp.sum())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    kernel_ms = []
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        comp, dg, st = ctx.pack_device(d_in, in_size, d_out, out_size, f, stream)
+        kernel_ms.append(ctx.last_kernel_ms()["pack_ms"])
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0
+    assert (st == 0).all() and np.array_equal(dg, hashes)
+
+    e2e_s = 0.0
+    if args.e2e:
+        h_out = torch.empty(out_size, dtype=torch.uint8).pin_memory()
+        h_in_np, h_out_np = h_in.numpy(), h_out.numpy()
+        ctx.pack_host(h_in_np, in_size, h_out_np, out_size, f)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            comp3, dg3, st3 = ctx.pack_host(h_in_np, in_size, h_out_np, out_size, f)
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+        assert (st3 == 0).all() and np.array_equal(dg3, hashes) and np.array_equal(comp3, comp)
+        for i in (0, n // 2, n - 1):   # the host copy really holds the frames
+            o, c = int(f["dst_off"][i]), int(comp[i])
+            assert np.array_equal(h_out_np[o:o + c], d_out[o:o + c].cpu().numpy()), "e2e output mismatch"
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total, float(np.mean(kernel_ms)), e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, kern_ms, e2e_s = [float(x) for x in t.cpu()]
+    if rank == 0:
+        peak, peak_src = peaks()
+        ms_step = ms_total / args.steps
+        value = world * in_size / (ms_step * 1e-3) / 1e9
+        algo_bytes = in_size + comp_bytes
+        achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+        line = {"metric": wl["metric"], "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": f"{wl['what']}, {n} files x 128 KiB per GPU ({in_size / 2**30:.2f} GiB), zpk-synth-v1",
+                           "files_per_gpu": n, "file_bytes": size, "sharding": f"files x{world}, no collective; offsets assembled on the host",
+                           "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)",
+                           "pipeline": "lz4_pack_kernel (warp per file), 1 launch per step",
+                           "ratio_gpu": in_size / comp_bytes, "ratio_reference_level0_sampled": in_size / ref_comp,
+                           "validity": "all frames read back on the GPU reader; 32 sampled frames decode bit-exactly in the CPU checker",
+                           "corpus_prep_s": round(prep_s, 1)},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src, "kernel": wl["kernel"], "kernel_ms": kern_ms,
+                             "algorithmic_bytes_per_launch": algo_bytes},
+                "gpu_launches": int(launches), "clocks": clocks}
+        if args.e2e:
+            line["e2e"] = {"value": world * in_size / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": in_size + f.nbytes,
+                           "d2h_bytes_per_step": comp_bytes + 20 * n,
+                           "how": "zpb_pack_host, pinned host buffers: chunked H2D of every input byte / kernel / gather + D2H of every frame, "
+                                  "overlapped on worker streams"}
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            v, dt, kind, ratio = cpu_pack_throughput(data, size, min(n, args.ref_entries), cores)
+            v1, _, _, _ = cpu_pack_throughput(data, size, min(n, 1024), 1)
+            line["cpu_baseline"] = {"value": v, "unit": "GB/s", "cores": cores, "kind": kind, "ratio": ratio,
+                                    "sample": f"first {min(n, args.ref_entries)} files, {cores} independent writers "
+                                              f"(zpack_write_archive, level 0); single writer: {v1:.3f} GB/s"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from one `ncu --set full` capture, as a ratio
 # to the algorithmic bytes of the captured launch (the capture runs fewer entries than the bench; the ratio carries over)
 NCU_TRAFFIC_RATIO = {
@@ -603,7 +822,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS),
-                    help="c2 (default): the config BASELINE.json's metric is quoted on; c4: zstd level-3 unpack; "
+                    help="c2 (default): the config BASELINE.json's metric is quoted on; c3: LZ4 pack of the same corpus; c4: zstd level-3 unpack; "
                          "c5: one entry of gpus x 2 GiB sharded by independent blocks")
     ap.add_argument("--entries", type=int, default=0, help="entries per GPU (default: C2 65536 / C4 32768, x 128 KiB)")
     ap.add_argument("--independent", action="store_true", help="archive with B.Indep=1 frames (what the GPU packer writes)")
@@ -618,6 +837,8 @@ def main():
         run_reference(args)
     elif args.workload == "c5":
         run_c5(args)
+    elif args.workload == "c3":
+        run_c3(args)
     else:
         run_ours(args)
 

@@ -70,27 +70,150 @@ extern "C" int zpb_pack_device(zpb_ctx *ctx, const uint8_t *d_in, uint64_t in_si
     return pack_device_impl(ctx, d_in, in_size, d_out, out_size, files, n, comp_size, digest, status, s);
 }
 
+// Gathers every file's frame from its bounded slot into one contiguous staging buffer (16-byte aligned starts):
+// a single D2H then carries exactly the compressed bytes instead of one small copy per file.
+__global__ void __launch_bounds__(256)
+pack_gather_kernel(const u8 *__restrict__ slots, u8 *__restrict__ compact, const zpb_file *__restrict__ files,
+                   const u64 *__restrict__ comp, const u64 *__restrict__ off, u32 n) {
+    const u32 w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const u8 *src = slots + files[w].dst_off;
+    u8 *dst = compact + off[w];
+    const u64 len = comp[w];
+    if ((((uintptr_t)src) & 15u) == 0) {
+        const u64 n16 = len >> 4;
+        for (u64 i = lane; i < n16; i += 32) reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+        for (u64 i = (n16 << 4) + lane; i < len; i += 32) dst[i] = src[i];
+    } else {
+        for (u64 i = lane; i < len; i += 32) dst[i] = src[i];
+    }
+}
+
+// One chunk on one (sub-)context: H2D of the chunk's input range -> pack kernel -> gather -> one D2H into a pinned
+// bounce buffer -> host scatter into the caller's slots.
+static int pack_host_chunk(zpb_ctx *ctx, const uint8_t *h_in, uint64_t in_size, uint8_t *h_out, uint64_t out_size,
+                           const zpb_file *files, uint64_t n, uint64_t *comp_size, uint64_t *digest, int32_t *status) {
+    if (n == 0) return ZPB_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    u64 lo = ~0ull, hi = 0, olo = ~0ull, ohi = 0;
+    for (u64 i = 0; i < n; ++i) {
+        const zpb_file &f = files[i];
+        if (f.src_off > in_size || f.size > in_size - f.src_off || f.dst_off > out_size || f.dst_cap > out_size - f.dst_off)
+            continue;                                             // flagged by the kernel's own bounds check
+        if (f.size) { lo = std::min(lo, f.src_off); hi = std::max(hi, f.src_off + f.size); }
+        olo = std::min(olo, f.dst_off); ohi = std::max(ohi, f.dst_off + f.dst_cap);
+    }
+    if (hi <= lo) lo = hi = 0;
+    if (ohi <= olo) olo = ohi = 0;
+    lo &= ~15ull; olo &= ~15ull;                                  // device layout congruent to the host layout mod 16
+    std::vector<zpb_file> rel(files, files + n);
+    for (auto &f : rel) {
+        if (f.src_off > in_size || f.size > in_size - f.src_off || f.dst_off > out_size || f.dst_cap > out_size - f.dst_off) {
+            f.src_off = ~0ull;                                    // stays invalid after rebasing
+            continue;
+        }
+        f.src_off -= f.size ? lo : f.src_off;
+        f.dst_off -= olo;
+    }
+    if (!ctx->d_in.ensure(hi - lo + 64) || !ctx->d_out.ensure(ohi - olo + 64))
+        return fail(ctx, ZPB_E_NOMEM, "device staging allocation failed");
+    if (hi > lo) CK(ctx, cudaMemcpyAsync(ctx->d_in.p, h_in + lo, hi - lo, cudaMemcpyHostToDevice, s));
+    std::vector<int32_t> st_local;
+    if (!status) { st_local.resize(n); status = st_local.data(); }
+    int rc = pack_device_impl(ctx, (const u8 *)ctx->d_in.p, hi - lo, (u8 *)ctx->d_out.p, ohi - olo, rel.data(), n,
+                              comp_size, digest, status, s);
+    if (rc != ZPB_OK) return rc;
+    // compact layout of what each file actually produced
+    std::vector<u64> off(n);
+    u64 total = 0;
+    for (u64 i = 0; i < n; ++i) {
+        const bool ok = status[i] == ZPB_ST_OK && comp_size[i] && rel[i].src_off != ~0ull && comp_size[i] <= files[i].dst_cap;
+        off[i] = total;
+        if (!ok) { off[i] = ~0ull; continue; }
+        total += (comp_size[i] + 15) & ~15ull;
+    }
+    if (total == 0) return ZPB_OK;
+    if (!ctx->d_gather.ensure(total + 64) || !ctx->d_goff.ensure(2 * n * sizeof(u64)) || !ctx->h_bounce.ensure(total + 64))
+        return fail(ctx, ZPB_E_NOMEM, "gather staging allocation failed");
+    std::vector<u64> up(2 * n);
+    for (u64 i = 0; i < n; ++i) { up[i] = off[i] == ~0ull ? 0 : comp_size[i]; up[n + i] = off[i] == ~0ull ? 0 : off[i]; }
+    CK(ctx, cudaMemcpyAsync(ctx->d_goff.p, up.data(), 2 * n * sizeof(u64), cudaMemcpyHostToDevice, s));
+    pack_gather_kernel<<<(u32)((n * 32 + 255) / 256), 256, 0, s>>>((const u8 *)ctx->d_out.p, (u8 *)ctx->d_gather.p,
+                                                                  (const zpb_file *)ctx->d_desc.p, (const u64 *)ctx->d_goff.p,
+                                                                  (const u64 *)ctx->d_goff.p + n, (u32)n);
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    CK(ctx, cudaMemcpyAsync(ctx->h_bounce.p, ctx->d_gather.p, total, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaStreamSynchronize(s));
+    const u8 *b = (const u8 *)ctx->h_bounce.p;
+    for (u64 i = 0; i < n; ++i)
+        if (off[i] != ~0ull) memcpy(h_out + files[i].dst_off, b + off[i], comp_size[i]);
+    return ZPB_OK;
+}
+
+// Host buffers in, host buffers out.  Large batches are cut into chunks of ~host_chunk_bytes of input (files in
+// source order, so a chunk's input is one contiguous H2D) and dealt to `host_workers` threads, each driving a private
+// sub-context: while one chunk is being packed, the next one's input is on its way in and the previous one's frames
+// on their way out.
 extern "C" int zpb_pack_host(zpb_ctx *ctx, const uint8_t *h_in, uint64_t in_size, uint8_t *h_out,
                              uint64_t out_size, const zpb_file *files, uint64_t n, uint64_t *comp_size,
                              uint64_t *digest, int32_t *status) {
     if (!ctx || (!files && n) || (!h_in && in_size) || (!h_out && out_size) || !comp_size)
         return fail(ctx, ZPB_E_ARG, "null argument");
     if (n == 0) return ZPB_OK;
-    CK(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
-    if (!ctx->d_in.ensure(in_size + 64) || !ctx->d_out.ensure(out_size + 64))
-        return fail(ctx, ZPB_E_NOMEM, "device staging allocation failed");
-    if (in_size) CK(ctx, cudaMemcpyAsync(ctx->d_in.p, h_in, in_size, cudaMemcpyHostToDevice, s));
-    int rc = pack_device_impl(ctx, (const u8 *)ctx->d_in.p, in_size, (u8 *)ctx->d_out.p, out_size, files, n,
-                              comp_size, digest, status, s);
-    if (rc != ZPB_OK) return rc;
-    // only the bytes each file actually produced travel back
-    for (u64 i = 0; i < n; ++i) {
-        if (!comp_size[i] || (status && status[i] != ZPB_ST_OK)) continue;
-        if (files[i].dst_off > out_size || comp_size[i] > out_size - files[i].dst_off) continue;
-        CK(ctx, cudaMemcpyAsync(h_out + files[i].dst_off, (u8 *)ctx->d_out.p + files[i].dst_off, comp_size[i],
-                                cudaMemcpyDeviceToHost, s));
+    u64 total = 0;
+    for (u64 i = 0; i < n; ++i) total += files[i].size;
+    const int W = ctx->host_workers;
+    if (W <= 1 || total < 2 * ctx->host_chunk_bytes)
+        return pack_host_chunk(ctx, h_in, in_size, h_out, out_size, files, n, comp_size, digest, status);
+
+    std::vector<u32> by_src(n);
+    std::iota(by_src.begin(), by_src.end(), 0u);
+    std::sort(by_src.begin(), by_src.end(), [&](u32 a, u32 b) { return files[a].src_off < files[b].src_off; });
+    std::vector<u64> cuts{0};
+    u64 acc = 0;
+    for (u64 k = 0; k < n; ++k) {
+        acc += files[by_src[k]].size;
+        if (acc >= ctx->host_chunk_bytes && k + 1 < n) { cuts.push_back(k + 1); acc = 0; }
     }
-    CK(ctx, cudaStreamSynchronize(s));
+    cuts.push_back(n);
+    const size_t nchunks = cuts.size() - 1;
+    while ((int)ctx->workers.size() < W) {
+        zpb_ctx *w = zpb_create(ctx->device);
+        if (!w) return fail(ctx, ZPB_E_CUDA, "pipeline sub-context creation failed");
+        ctx->workers.push_back(w);
+    }
+    std::vector<int> rcs(W, ZPB_OK);
+    std::vector<std::string> errs(W);
+    auto body = [&](int t) {
+        zpb_ctx *w = ctx->workers[t];
+        std::vector<zpb_file> sub;
+        std::vector<int32_t> st;
+        std::vector<u64> cs, dg;
+        for (size_t c = t; c < nchunks; c += W) {
+            const u64 a = cuts[c], b = cuts[c + 1], m = b - a;
+            sub.resize(m); st.resize(m); cs.resize(m); dg.resize(m);
+            for (u64 k = 0; k < m; ++k) sub[k] = files[by_src[a + k]];
+            int rc = pack_host_chunk(w, h_in, in_size, h_out, out_size, sub.data(), m, cs.data(), dg.data(), st.data());
+            if (rc != ZPB_OK) { rcs[t] = rc; errs[t] = w->err; return; }
+            for (u64 k = 0; k < m; ++k) {
+                comp_size[by_src[a + k]] = cs[k];
+                if (digest) digest[by_src[a + k]] = dg[k];
+                if (status) status[by_src[a + k]] = st[k];
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < W; ++t) th.emplace_back(body, t);
+    body(0);
+    for (auto &x : th) x.join();
+    u64 launches = 0;
+    float ms = 0.f;
+    for (zpb_ctx *w : ctx->workers) { launches += w->launches; w->launches = 0; ms += w->pack_ms; }
+    ctx->launches += launches;
+    ctx->pack_ms = ms;
+    for (int t = 0; t < W; ++t)
+        if (rcs[t] != ZPB_OK) return fail(ctx, rcs[t], errs[t].c_str());
     return ZPB_OK;
 }

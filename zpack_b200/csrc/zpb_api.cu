@@ -71,6 +71,8 @@ struct zpb_ctx {
     PinBuf h_stage;
     // staging arenas for the *_host entry points
     DevBuf d_in, d_out;
+    DevBuf d_gather, d_goff;   // pack: compacted frames + their sizes / offsets
+    PinBuf h_bounce;           // pack: landing zone of the one D2H per chunk
     // pipelined host path: private sub-contexts (own stream + scratch), one per worker thread
     std::vector<zpb_ctx *> workers;
     // block-sharded path (one large block-independent LZ4 entry): per-KiB XXH3 stripe sums of the last shard
@@ -168,6 +170,7 @@ extern "C" void zpb_destroy(zpb_ctx *ctx) {
     ctx->d_in.release(); ctx->d_out.release(); ctx->h_stage.release();
     ctx->d_aux.release(); ctx->d_fe.release(); ctx->d_fb.release(); ctx->d_plist.release();
     ctx->d_glist.release(); ctx->d_fdesc.release(); ctx->d_zlist.release(); ctx->d_zlit.release();
+    ctx->d_gather.release(); ctx->d_goff.release(); ctx->h_bounce.release();
     ctx->d_partials.release(); ctx->d_acc.release();
     for (auto &ev : ctx->evs) if (ev) cudaEventDestroy(ev);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
