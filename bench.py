@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """bench.py — LZ4 unpack + XXH3-64 verify throughput (BASELINE.json metric) on N B200s.
 
-A "step" is one pass of the hot path (zpb_unpack_device: descriptor upload, one kernel, status /
+A "step" is one pass of the hot path (zpb_unpack_device: descriptor upload, scan / parse / exec kernels, status /
 digest download) over one synthetic archive.  See DESIGN.md §Measurement for the definitions of
-value / e2e / roofline / cpu_baseline.
+value / e2e / roofline / cpu_baseline.  `--workload` selects the other BASELINE.json configurations in the same
+contract format: c3 (LZ4 pack of the corpus), c4 (zstd level-3 unpack), c5 (one huge entry sharded by blocks);
+`--impl reference` times the unmodified reference (oracle/_ref) on the host cores for the same workload.
 """
 import argparse
 import json

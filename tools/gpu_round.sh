@@ -11,6 +11,7 @@ python bench.py --steps 5 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/be
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_c2_ref.json 2> gpurun_out/bench_c2_ref.err; cat gpurun_out/bench_c2_ref.json
 python bench.py --workload c4 --steps 5 --warmup 3 > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; cat gpurun_out/bench_c4.json
 python bench.py --workload c5 --steps 5 --warmup 3 > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err; cat gpurun_out/bench_c5.json
+python bench.py --workload c3 --steps 5 --warmup 3 > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; cat gpurun_out/bench_c3.json
 python tools/class_bench.py --entries 14208 --groups 8 --classes 0,1,2,3,-1 --reps 3 > gpurun_out/class.jsonl 2> gpurun_out/class.err
 python tools/pack_bench.py > gpurun_out/pack.jsonl 2> gpurun_out/pack.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
