@@ -123,3 +123,52 @@ def test_none_method_and_error_statuses(gpu_ctx, oracle):
     f["dst_cap"][0] = 100                                            # slot smaller than the bound
     comp, digest, status = gpu_ctx.pack_host(h_in, len(h_in), np.zeros(out_size, np.uint8), out_size, f)
     assert list(status) == [14]
+
+
+def test_pipelined_pack_host_matches_the_device_path(oracle, monkeypatch):
+    """zpb_pack_host cuts big batches into chunks over worker sub-contexts and brings each chunk's frames back with
+    one gathered D2H.  Tiny chunks force that path on a test-sized batch; caller order != source order, slots at
+    odd (not 16-byte aligned) offsets, zero-length and mixed-method files included.  Frames, sizes and digests must
+    equal what the single-launch device path produces, and slack between slots must stay untouched."""
+    import torch
+    import zpack_b200
+    monkeypatch.setenv("ZPB_HOST_CHUNK_MB", "1")
+    monkeypatch.setenv("ZPB_HOST_WORKERS", "3")
+    ctx = zpack_b200.Context(0)
+    try:
+        n = 80
+        sizes = [0 if i == 11 else (131072 if i % 3 else 50001 + i) for i in range(n)]
+        bufs = [corpus.entry_bytes(i, s) for i, s in enumerate(sizes)]
+        f = np.zeros(n, zlib.File)
+        in_off, out_off = 0, 3
+        for i, b in enumerate(bufs):
+            m = 0 if i % 7 == 5 else 2
+            f["src_off"][i], f["size"][i] = in_off, len(b)
+            cap = ctx.pack_bound(m, len(b))
+            f["dst_off"][i], f["dst_cap"][i] = out_off, cap
+            f["method"][i] = m
+            in_off += (len(b) + 15) & ~15
+            out_off += cap + 5                       # odd slot starts
+        h_in = np.zeros(in_off + 16, np.uint8)
+        for i, b in enumerate(bufs):
+            h_in[int(f["src_off"][i]):int(f["src_off"][i]) + len(b)] = b
+        perm = np.random.default_rng(5).permutation(n)
+        fp = np.ascontiguousarray(f[perm])
+        out_size = out_off + 16
+        h_out = np.full(out_size, 0xA5, np.uint8)
+        comp, digest, status = ctx.pack_host(h_in, len(h_in), h_out, out_size, fp)
+        d_in = torch.from_numpy(h_in).cuda()
+        d_out = torch.zeros(out_size, dtype=torch.uint8, device="cuda")
+        comp_d, digest_d, status_d = ctx.pack_device(d_in, len(h_in), d_out, out_size, fp)
+        ref = d_out.cpu().numpy()
+        assert (status == 0).all() and np.array_equal(status, status_d)
+        assert np.array_equal(comp, comp_d) and np.array_equal(digest, digest_d)
+        touched = np.zeros(out_size, bool)
+        for k in range(n):
+            o, c = int(fp["dst_off"][k]), int(comp[k])
+            assert np.array_equal(h_out[o:o + c], ref[o:o + c]), k
+            assert digest[k] == oracle.xxh3_port(bufs[perm[k]])
+            touched[o:o + c] = True
+        assert (h_out[~touched] == 0xA5).all()       # nothing outside the frames was written on the host side
+    finally:
+        ctx.close()
