@@ -530,8 +530,12 @@ ZPB_DEVINL u32 ldg8_coherent(const u8 *p) {
 }
 
 #define FAST_LT  16u   // literal runs up to this go one-lane-per-sequence (from global memory); longer ones warp-wide
+#ifndef FAST_LTR
 #define FAST_LTR 32u   // the same when the source is the staging ring (word copies)
+#endif
+#ifndef FAST_MT
 #define FAST_MT  64u   // matches up to this go one-lane-per-sequence (non-overlapping, linear in shared memory)
+#endif
 
 #define DS_FINAL 0u   // source bytes are final (possibly after redirection by `shift`)
 #define DS_CHILD 1u   // source wholly inside lane `parent`'s match: being resolved
