@@ -189,6 +189,10 @@ int zpb_last_zstd_ms(const zpb_ctx *ctx, float *ms);
 /* 1 (default): LZ4 / stored entries go through the scan -> parse -> exec pipeline and only what it
  * declines reaches the general decoder; 0: general decoder for everything (A/B and test use). */
 int zpb_set_fast_path(zpb_ctx *ctx, int enabled);
+/* 1 (default; env ZPB_OVERLAP): the execute kernel starts as soon as the scan has finished and overlaps the tail of the
+ * parse kernel (separate streams, entries whose blocks are not parsed yet are put aside for a last pass);
+ * 0: scan, parse, execute back to back on one stream — what per-kernel timings (zpb_last_stage_ms) are meaningful for. */
+int zpb_set_overlap(zpb_ctx *ctx, int enabled);
 
 /* tuning knobs: lanes per dependency chain (4, 8, 16, 32; 0 = keep) and resident CTAs per SM
  * (0 = occupancy API, -1 = keep).  Defaults can also come from ZPB_GROUP / ZPB_CTAS_PER_SM. */

@@ -50,6 +50,9 @@
 #define FE_GENERAL 2u   // handed to the general kernel
 #define FE_ZSTD    3u   // handed to the zstd kernel (zstd_decode.cuh)
 
+#define K1_HEAVY   (24u << 10)   // compressed block bytes: heavy / medium / light parse work lists
+#define K1_MEDIUM  (6u << 10)
+
 #define FB_STORED  1u
 #define FB_BAD     2u
 #define FB_PARSED  4u
@@ -127,7 +130,7 @@ __device__ __noinline__ bool fast_scan_lz4(const u8 *src, u64 n, const zpb_entry
 __global__ void __launch_bounds__(256)
 lz4_fast_scan_kernel(const u8 *__restrict__ archive, u64 asz, const zpb_entry *__restrict__ entries,
                      const u32 *__restrict__ order, u32 n, const FastAux *__restrict__ aux, FastEntry *fe,
-                     FastBlock *fb, u32 *parse_list, u32 *counters, u32 *general_list, u32 *zstd_list,
+                     FastBlock *fb, u32 *parse_list, u32 plist_cap, u32 *counters, u32 *general_list, u32 *zstd_list,
                      int *status, u64 *digest) {
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
@@ -183,7 +186,19 @@ lz4_fast_scan_kernel(const u8 *__restrict__ archive, u64 asz, const zpb_entry *_
     } else {
         for (u32 b = 0; b < f.nblocks; ++b)
             if (!(fb[a.slot_base + b].flags & FB_STORED))
-                parse_list[atomicAdd(&counters[0], 1u)] = a.slot_base + b;
+            {
+                // three work lists by weight (compressed bytes ~ sequences to walk): the parse kernel hands the heavy
+                // list to its first CTAs, so that the CTAs holding light blocks retire early and make room for K2
+                const u32 bz = fb[a.slot_base + b].bsz;
+                const u32 cls = bz >= K1_HEAVY ? 0u : bz >= K1_MEDIUM ? 1u : 2u;
+                // one atomic per class and warp, not per block
+                const u32 peers = __match_any_sync(__activemask(), cls);
+                const int leader = __ffs(peers) - 1;
+                u32 base = 0;
+                if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&counters[8 + cls], (u32)__popc(peers));
+                base = __shfl_sync(peers, base, leader);
+                parse_list[(u64)cls * plist_cap + base + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u))] = a.slot_base + b;
+            }
     }
     fe[idx] = f;
 }
@@ -374,12 +389,13 @@ struct LaneStage {
 
 __global__ void __launch_bounds__(K1_THREADS)
 lz4_fast_parse_kernel(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, const u32 *__restrict__ parse_list,
-                      const u32 *__restrict__ counters, u32 *work_counter, u32 *desc) {
+                      u32 plist_cap, const u32 *__restrict__ counters, u32 *work_counter, u32 *desc) {
     extern __shared__ uint4 k1_smem[];
     const int lane = threadIdx.x & 31;
     const u32 row_s = (u32)__cvta_generic_to_shared(k1_smem) + threadIdx.x * K1_ROW;
-    const u32 nitems = counters[0];
-    bool active = false, exhausted = false;
+    const u32 n_heavy = counters[8], n_medium = counters[9], nitems = n_heavy + n_medium + counters[10];
+    const u32 nlanes = gridDim.x * blockDim.x;
+    bool active = false, exhausted = false, first = true;
     LaneStage sg;
     // all positions below are ring coordinates (block position + skew)
     u32 slot = 0, skew = 0, qend = 0, q = 0, op = 0, nseq = 0, reach = 0, last_ms = 0;
@@ -391,15 +407,25 @@ lz4_fast_parse_kernel(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, co
         u32 idle = __ballot_sync(0xffffffffu, !active);
         if (idle) {
             if (!exhausted) {
-                u32 base = 0;
-                int leader = __ffs(idle) - 1;
-                if (lane == leader) base = atomicAdd(work_counter, (u32)__popc(idle));
-                base = __shfl_sync(0xffffffffu, base, leader);
+                // first item: by position in the grid (CTA c walks items [256c, 256c + 256): the heavy list lands on
+                // the first CTAs); afterwards from the shared counter, which starts behind the statically dealt items
+                u32 base;
+                if (first) {
+                    base = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u));
+                    first = false;
+                } else {
+                    base = 0;
+                    int leader = __ffs(idle) - 1;
+                    if (lane == leader) base = atomicAdd(work_counter, (u32)__popc(idle));
+                    base = __shfl_sync(0xffffffffu, base, leader) + nlanes;
+                }
                 if (base + __popc(idle) > nitems) exhausted = true;
                 if (!active) {
                     u32 w = base + __popc(idle & ((1u << lane) - 1u));
                     if (w < nitems) {
-                        slot = parse_list[w];
+                        slot = w < n_heavy ? parse_list[w]
+                             : w < n_heavy + n_medium ? parse_list[(u64)plist_cap + (w - n_heavy)]
+                                                      : parse_list[2ull * plist_cap + (w - n_heavy - n_medium)];
                         FastBlock B = fb[slot];
                         dout = desc + B.desc_off;
                         skew = sg.open(archive, asz, B.src, row_s);
@@ -510,7 +536,8 @@ lz4_fast_parse_kernel(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, co
             }
             fb[slot].nseq = nseq;
             fb[slot].out_size = op;
-            fb[slot].flags = (bad ? FB_BAD : FB_PARSED) | (reach << 8);
+            __threadfence();   // K2 may already be running (it polls `flags`): descriptors and sizes first, verdict last
+            *reinterpret_cast<volatile u32 *>(&fb[slot].flags) = (bad ? FB_BAD : FB_PARSED) | (reach << 8);
             cp_async_wait_all();
             active = false;
         }
@@ -528,6 +555,10 @@ ZPB_DEVINL u32 ldg8_coherent(const u8 *p) {
     asm volatile("ld.global.u8 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
     return r;
 }
+
+// K2 starts while K1 is still walking the heaviest blocks (separate streams): everything K1 produces is read through
+// L2 (ld.global.cg / volatile), never through the non-coherent or L1 paths, whose lines could predate K1's stores.
+ZPB_DEVINL u32 ldcg32(const u32 *p) { return __ldcg(p); }
 
 #define FAST_LT  16u   // literal runs up to this go one-lane-per-sequence (from global memory); longer ones warp-wide
 #ifndef FAST_LTR
@@ -831,8 +862,10 @@ __global__ void __launch_bounds__(32 * FAST_EXEC_WARPS, FAST_EXEC_CTAS)
 lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_entry *__restrict__ entries,
                      const u32 *__restrict__ order, u32 n, u32 *counter, const FastEntry *__restrict__ fe,
                      const FastBlock *__restrict__ fb, const u32 *__restrict__ desc, u32 *counters,
-                     u32 *general_list, int *status, u64 *digest, u64 *partials) {
+                     u32 *general_list, int *status, u64 *digest, u64 *partials, u32 *defer_list, u32 *defer_cnt,
+                     const u32 *n_ptr) {
     extern __shared__ uint4 k2_smem[];
+    if (n_ptr) n = *n_ptr;   // the late pass over the deferred list: its length was only known on the device
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FastExec x;
     x.lane = lane;
@@ -852,25 +885,43 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
         if (lane == 0) wslot = atomicAdd(counter, 1u);
         wslot = __shfl_sync(0xffffffffu, wslot, 0);
         if (wslot >= n) break;
-        const u32 idx = order ? order[wslot] : wslot;
+        const u32 idx = order ? __ldcg(order + wslot) : wslot;
         const FastEntry f = fe[idx];
         if (f.state != FE_FAST) continue;
         const zpb_entry e = entries[idx];
 
         // ---- K1 verdicts: every block parsed clean, window reach legal, sizes add up exactly
-        bool ok = true;
+        bool ok = true, deferred = false;
         {
             u64 before = 0;
             for (u32 b = 0; b < f.nblocks; ++b) {
-                const FastBlock B = fb[f.first_slot + b];
-                if (!(B.flags & FB_STORED)) {
-                    if (!(B.flags & FB_PARSED) || (B.flags & FB_BAD)) ok = false;
-                    u32 reach = (B.flags >> 8) & 0xFFFFu;
+                const FastBlock *pb = fb + f.first_slot + b;
+                // This grid may run while K1 is still walking the heavy blocks.  It never waits for a verdict (a
+                // resident CTA that waits could keep K1's own CTAs off the SMs): an entry with a block still in
+                // flight goes to the deferred list, which a last launch works off after K1 has finished.
+                u32 ready = 1;
+                if (lane == 0) {
+                    ready = (*reinterpret_cast<const volatile u32 *>(&pb->flags) & (FB_STORED | FB_PARSED | FB_BAD)) != 0;
+                    if (ready) __threadfence();
+                }
+                ready = __shfl_sync(0xffffffffu, ready, 0);
+                if (!ready) { deferred = true; break; }
+                const u32 bflags = __ldcg(&pb->flags);
+                if (!(bflags & FB_STORED)) {
+                    if (!(bflags & FB_PARSED) || (bflags & FB_BAD)) ok = false;
+                    u32 reach = (bflags >> 8) & 0xFFFFu;
                     if (reach > (f.linked == FE_LINK_WINDOW ? before : 0ull)) ok = false;   // lz4.c:2093 with the frame's prefix
                 }
-                before += B.out_size;
+                before += __ldcg(&pb->out_size);
             }
             if (before != e.uncomp_size) ok = false;
+        }
+        if (deferred) {
+            if (defer_list) {
+                if (lane == 0) defer_list[atomicAdd(defer_cnt, 1u)] = idx;
+                continue;
+            }
+            ok = false;   // launches without a list run after K1, where every verdict is in: never skip an entry silently
         }
         const bool partial = f.linked == FE_LINK_PARTIAL;
         if (!ok) {
@@ -891,11 +942,11 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
         x.hash_init();
 
         for (u32 b = 0; b < f.nblocks; ++b) {
-            const FastBlock B = fb[f.first_slot + b];
-            const u8 *__restrict__ src = archive + B.src;
-            if (B.flags & FB_STORED) {
+            const FastBlock *pb = fb + f.first_slot + b;   // fields are read where they are needed, through L2
+            const u8 *__restrict__ src = archive + __ldcg(&pb->src);
+            if (__ldcg(&pb->flags) & FB_STORED) {
                 // ---- stored block / NONE entry (lz4frame.c:1534-1572, zpack_read.c:352-368)
-                u32 len = B.bsz;
+                u32 len = __ldcg(&pb->bsz);
                 if (x.done == x.flushed && (x.done & 1023u) == 0) {
                     // direct: HBM -> registers -> XXH3 + HBM, no ring
                     while (len >= 1024 && (x.flushed >> 10) < x.full_blocks && src + 1024 + 16 <= arch_end) {
@@ -920,19 +971,19 @@ lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb
             }
 
             // ---- compressed block: 32 sequences per step, one per lane
-            const u32 *__restrict__ dp = desc + B.desc_off;
+            const u32 *dp = desc + __ldcg(&pb->desc_off);
             const u32 obase = x.done;
-            const u32 bsz = B.bsz;
-            const u32 nseq = B.nseq;
+            const u32 bsz = __ldcg(&pb->bsz);
+            const u32 nseq = __ldcg(&pb->nseq);
             cs.open(src);
             // two steps of descriptors are kept in flight; the compressed bytes come through the staging ring
-            u32 d0 = (u32)lane < nseq ? dp[lane] : 0u;
-            u32 d1 = 32u + lane < nseq ? dp[32 + lane] : 0u;
+            u32 d0 = (u32)lane < nseq ? ldcg32(dp + lane) : 0u;
+            u32 d1 = 32u + lane < nseq ? ldcg32(dp + 32 + lane) : 0u;
             for (u32 s0i = 0; s0i < nseq; s0i += 32) {
                 const bool have = s0i + lane < nseq;
                 const u32 d = d0;
                 d0 = d1;
-                d1 = s0i + 64 + lane < nseq ? dp[s0i + 64 + lane] : 0u;
+                d1 = s0i + 64 + lane < nseq ? ldcg32(dp + s0i + 64 + lane) : 0u;
                 // compressed bytes this step reads: from its first token to the next step's first token
                 const u32 s_lo = __shfl_sync(0xffffffffu, d & 0xFFFFu, 0);
                 const u32 s_nx = __shfl_sync(0xffffffffu, d0 & 0xFFFFu, 0);

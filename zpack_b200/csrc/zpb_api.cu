@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -65,6 +66,11 @@ struct zpb_ctx {
     int zs_grid = 0;         // persistent grid of zstd_unpack_kernel (CTAs)
     float zstd_ms = 0.f;
     cudaEvent_t evs[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // the execute kernel runs on its own stream so that it overlaps the tail of the parse kernel
+    cudaStream_t stream_p = nullptr, stream_b = nullptr;   // parse (high priority), the late third of the execute grid
+    cudaEvent_t ev_scan = nullptr, ev_x0 = nullptr, ev_x1 = nullptr, ev_p0 = nullptr, ev_p1 = nullptr, ev_xb = nullptr;
+    DevBuf d_order2, d_defer;
+    int overlap = 1;         // ZPB_OVERLAP=0: parse, then execute, on one stream
     // descriptor / result scratch
     DevBuf d_desc, d_order, d_res, d_counter;
     std::vector<uint16_t> h_keys;   // cost key per entry of the batch being prepared
@@ -140,6 +146,17 @@ extern "C" zpb_ctx *zpb_create(int device) {
     if (const char *s = getenv("ZPB_HOST_CHUNK_MB")) ctx->host_chunk_bytes = (u64)std::max(1, atoi(s)) << 20;
     for (auto &ev : ctx->evs)
         if (cudaEventCreate(&ev) != cudaSuccess) { g_last_error = "event setup failed"; delete ctx; return nullptr; }
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&ctx->stream_p, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->stream_b, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_scan, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_xb, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_p0) != cudaSuccess || cudaEventCreate(&ctx->ev_p1) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_x0) != cudaSuccess || cudaEventCreate(&ctx->ev_x1) != cudaSuccess) {
+        g_last_error = "second stream setup failed"; delete ctx; return nullptr;
+    }
+    if (const char *e = getenv("ZPB_OVERLAP")) ctx->overlap = atoi(e);
     if (cudaFuncSetAttribute(lz4_fast_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(K1_THREADS * K1_ROW)) != cudaSuccess ||
         cudaFuncSetAttribute(lz4_fast_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -175,6 +192,15 @@ extern "C" void zpb_destroy(zpb_ctx *ctx) {
     for (auto &ev : ctx->evs) if (ev) cudaEventDestroy(ev);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_scan) cudaEventDestroy(ctx->ev_scan);
+    if (ctx->ev_x0) cudaEventDestroy(ctx->ev_x0);
+    if (ctx->ev_x1) cudaEventDestroy(ctx->ev_x1);
+    if (ctx->ev_p0) cudaEventDestroy(ctx->ev_p0);
+    if (ctx->ev_p1) cudaEventDestroy(ctx->ev_p1);
+    if (ctx->ev_xb) cudaEventDestroy(ctx->ev_xb);
+    if (ctx->stream_p) cudaStreamDestroy(ctx->stream_p);
+    if (ctx->stream_b) cudaStreamDestroy(ctx->stream_b);
+    ctx->d_order2.release(); ctx->d_defer.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -220,6 +246,12 @@ extern "C" int zpb_debug_zstd_profile(unsigned long long *out8) {
     return cudaMemcpyToSymbol(g_zs_prof, z, sizeof z) == cudaSuccess ? ZPB_OK : ZPB_E_CUDA;
 }
 #endif
+
+extern "C" int zpb_set_overlap(zpb_ctx *ctx, int enabled) {
+    if (!ctx) return ZPB_E_ARG;
+    ctx->overlap = enabled ? 1 : 0;
+    return ZPB_OK;
+}
 
 extern "C" int zpb_set_fast_path(zpb_ctx *ctx, int enabled) {
     if (!ctx) return ZPB_E_ARG;
@@ -285,7 +317,8 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
     size_t desc_b = n * sizeof(zpb_entry), ord_b = n * sizeof(u32);
     size_t res_b = n * (sizeof(int) + sizeof(u64));
     if (!ctx->d_desc.ensure(desc_b) || !ctx->d_order.ensure(ord_b) || !ctx->d_res.ensure(res_b + 64) ||
-        !ctx->d_counter.ensure(256) || !ctx->h_stage.ensure(desc_b + ord_b + res_b + 64 + n * sizeof(FastAux)))
+        !ctx->d_counter.ensure(256) || !ctx->d_order2.ensure(ord_b) || !ctx->d_defer.ensure(ord_b) ||
+        !ctx->h_stage.ensure(desc_b + 2 * ord_b + res_b + 64 + n * sizeof(FastAux)))
         return fail(ctx, ZPB_E_NOMEM, "scratch allocation failed");
 
     // ---- one pass over the descriptors (the GPU idles while the host prepares a batch, so this is kept to a single
@@ -332,6 +365,16 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
     if (slots > 0x7fffffffull) return fail(ctx, ZPB_E_ARG, "too many blocks in one batch");
     for (u32 k = 0; k < 1024; ++k) head[k + 1] += head[k];
     for (u64 i = 0; i < n; ++i) h_order[head[keys[i]]++] = (u32)i;   // counting sort: O(n), stable
+    // The execute kernel starts while the heaviest blocks are still being parsed, so ITS order leads with the
+    // entries that are parsed (almost) at once — stored and highly compressible ones, the cheap end of the list —
+    // and continues with the rest, expensive first as before.
+    u32 *h_order2 = (u32 *)(hs + desc_b + ord_b + res_b + 64 + n * sizeof(FastAux));
+    {
+        u64 ncheap = 0;
+        while (ncheap < n && keys[h_order[n - 1 - ncheap]] >= 1023u - 31u) ++ncheap;   // cost below 32 x 512 B
+        for (u64 k = 0; k < ncheap; ++k) h_order2[k] = h_order[n - 1 - k];
+        for (u64 k = ncheap; k < n; ++k) h_order2[k] = h_order[k - ncheap];
+    }
 
     if (any_zstd && (!ctx->d_zlist.ensure(n * 4) ||
                      !ctx->d_zlit.ensure((size_t)ctx->zs_grid * ZS_WARPS * ZS_LIT_SCRATCH)))
@@ -347,7 +390,7 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
         // ---- scan -> parse -> exec (lz4_fast.cuh), then the general kernel over whatever they declined
         size_t aux_b = n * sizeof(FastAux);
         if (!ctx->d_aux.ensure(aux_b) || !ctx->d_fe.ensure(n * sizeof(FastEntry)) ||
-            !ctx->d_fb.ensure((slots + 1) * sizeof(FastBlock)) || !ctx->d_plist.ensure((slots + 1) * 4) ||
+            !ctx->d_fb.ensure((slots + 1) * sizeof(FastBlock)) || !ctx->d_plist.ensure(3 * (slots + 1) * 4) ||
             !ctx->d_glist.ensure(n * 4) || !ctx->d_fdesc.ensure((ndesc + 4) * 4))
             return fail(ctx, ZPB_E_NOMEM, "fast-path scratch allocation failed");
         CK(ctx, cudaMemcpyAsync(ctx->d_aux.p, h_aux, aux_b, cudaMemcpyHostToDevice, s));
@@ -357,22 +400,63 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
         CK(ctx, cudaEventRecord(ctx->evs[0], s));
         lz4_fast_scan_kernel<<<(u32)((n + 255) / 256), 256, 0, s>>>(
             d_archive, archive_size, d_e, d_ord, (u32)n, (const FastAux *)ctx->d_aux.p, (FastEntry *)ctx->d_fe.p,
-            (FastBlock *)ctx->d_fb.p, (u32 *)ctx->d_plist.p, cnt, (u32 *)ctx->d_glist.p, (u32 *)ctx->d_zlist.p,
+            (FastBlock *)ctx->d_fb.p, (u32 *)ctx->d_plist.p, (u32)(slots + 1), cnt, (u32 *)ctx->d_glist.p, (u32 *)ctx->d_zlist.p,
             d_status, d_digest);
         CK(ctx, cudaGetLastError());
         CK(ctx, cudaEventRecord(ctx->evs[1], s));
-        int k1_ctas = ctx->ctas_per_sm > 0 ? ctx->ctas_per_sm : 3;
-        lz4_fast_parse_kernel<<<ctx->sm_count * k1_ctas, K1_THREADS, K1_THREADS * K1_ROW, s>>>(
-            d_archive, archive_size, (FastBlock *)ctx->d_fb.p, (const u32 *)ctx->d_plist.p, cnt, cnt + 2,
+        // K2 checks K1's verdict per block (lz4_fast.cuh), so it only needs the scan to have finished.  Parse goes to a
+        // high-priority stream and is queued first, so its CTAs (3 per SM) are resident before any of K2's.  K2 runs as
+        // three launches sharing the work counters: two CTAs per SM at once (they fill the SMs as parse CTAs retire and
+        // never wait: an entry whose blocks are not parsed yet is put aside), the third CTA per SM once the parse kernel
+        // has finished, and a last pass over the entries that were put aside.
+        const bool overlap = ctx->overlap != 0;
+        static const int k2_ctas = [] { const char *e = getenv("ZPB_EXEC_CTAS"); int v = e ? atoi(e) : 0; return v > 0 && v <= 8 ? v : FAST_EXEC_CTAS; }();
+        const int k1_ctas = ctx->ctas_per_sm > 0 ? ctx->ctas_per_sm : 3;
+        cudaStream_t sp = overlap ? ctx->stream_p : s;
+        if (overlap) {
+            CK(ctx, cudaMemcpyAsync(ctx->d_order2.p, h_order2, ord_b, cudaMemcpyHostToDevice, s));
+            CK(ctx, cudaEventRecord(ctx->ev_scan, s));
+            CK(ctx, cudaStreamWaitEvent(sp, ctx->ev_scan, 0));
+        }
+        CK(ctx, cudaEventRecord(ctx->ev_p0, sp));
+        lz4_fast_parse_kernel<<<ctx->sm_count * k1_ctas, K1_THREADS, K1_THREADS * K1_ROW, sp>>>(
+            d_archive, archive_size, (FastBlock *)ctx->d_fb.p, (const u32 *)ctx->d_plist.p, (u32)(slots + 1), cnt, cnt + 2,
             (u32 *)ctx->d_fdesc.p);
         CK(ctx, cudaGetLastError());
-        CK(ctx, cudaEventRecord(ctx->evs[2], s));
-        static const int k2_ctas = [] { const char *e = getenv("ZPB_EXEC_CTAS"); int v = e ? atoi(e) : 0; return v > 0 && v <= 8 ? v : FAST_EXEC_CTAS; }();
-        lz4_fast_exec_kernel<<<ctx->sm_count * k2_ctas, 32 * FAST_EXEC_WARPS, FAST_EXEC_SMEM, s>>>(
-            d_archive, archive_size, d_out, d_e, d_ord, (u32)n, cnt + 3, (const FastEntry *)ctx->d_fe.p,
+        CK(ctx, cudaEventRecord(ctx->ev_p1, sp));
+        CK(ctx, cudaEventRecord(ctx->ev_x0, s));
+        const u32 *d_xord = overlap ? (const u32 *)ctx->d_order2.p : d_ord;
+        const int early = overlap ? (k2_ctas > 1 ? k2_ctas - 1 : 1) : k2_ctas;
+        u32 *d_defer = overlap ? (u32 *)ctx->d_defer.p : nullptr;   // cnt[11]: work counter of the last pass, cnt[12]: its length
+        lz4_fast_exec_kernel<<<ctx->sm_count * early, 32 * FAST_EXEC_WARPS, FAST_EXEC_SMEM, s>>>(
+            d_archive, archive_size, d_out, d_e, d_xord, (u32)n, cnt + 3, (const FastEntry *)ctx->d_fe.p,
             (const FastBlock *)ctx->d_fb.p, (const u32 *)ctx->d_fdesc.p, cnt, (u32 *)ctx->d_glist.p, d_status,
-            d_digest, ctx->cur_partials);
+            d_digest, ctx->cur_partials, d_defer, cnt + 12, nullptr);
         CK(ctx, cudaGetLastError());
+        if (overlap) {
+            if (k2_ctas > early) {
+                CK(ctx, cudaStreamWaitEvent(ctx->stream_b, ctx->ev_p1, 0));
+                lz4_fast_exec_kernel<<<ctx->sm_count * (k2_ctas - early), 32 * FAST_EXEC_WARPS, FAST_EXEC_SMEM, ctx->stream_b>>>(
+                    d_archive, archive_size, d_out, d_e, d_xord, (u32)n, cnt + 3, (const FastEntry *)ctx->d_fe.p,
+                    (const FastBlock *)ctx->d_fb.p, (const u32 *)ctx->d_fdesc.p, cnt, (u32 *)ctx->d_glist.p, d_status,
+                    d_digest, ctx->cur_partials, d_defer, cnt + 12, nullptr);
+                CK(ctx, cudaGetLastError());
+                CK(ctx, cudaEventRecord(ctx->ev_xb, ctx->stream_b));
+                CK(ctx, cudaStreamWaitEvent(s, ctx->ev_xb, 0));
+                ctx->launches += 1;
+            } else {
+                CK(ctx, cudaStreamWaitEvent(s, ctx->ev_p1, 0));
+            }
+            // what the early grids put aside (entries reached before their blocks were parsed): usually nothing
+            lz4_fast_exec_kernel<<<ctx->sm_count * k2_ctas, 32 * FAST_EXEC_WARPS, FAST_EXEC_SMEM, s>>>(
+                d_archive, archive_size, d_out, d_e, d_defer, 0u, cnt + 11, (const FastEntry *)ctx->d_fe.p,
+                (const FastBlock *)ctx->d_fb.p, (const u32 *)ctx->d_fdesc.p, cnt, (u32 *)ctx->d_glist.p, d_status,
+                d_digest, ctx->cur_partials, nullptr, nullptr, cnt + 12);
+            CK(ctx, cudaGetLastError());
+            ctx->launches += 1;
+        }
+        CK(ctx, cudaEventRecord(ctx->ev_x1, s));
+        CK(ctx, cudaEventRecord(ctx->evs[2], s));
         CK(ctx, cudaEventRecord(ctx->evs[3], s));
         cudaError_t ge;
         switch (ctx->group) {
@@ -394,6 +478,8 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
         CK(ctx, cudaStreamSynchronize(s));
         CK(ctx, cudaEventElapsedTime(&ctx->unpack_ms, ctx->evs[0], ctx->evs[5]));
         for (int k = 0; k < 4; ++k) CK(ctx, cudaEventElapsedTime(&ctx->stage_ms[k], ctx->evs[k], ctx->evs[k + 1]));
+        CK(ctx, cudaEventElapsedTime(&ctx->stage_ms[1], ctx->ev_p0, ctx->ev_p1));   // parse, on its own stream when overlapped
+        CK(ctx, cudaEventElapsedTime(&ctx->stage_ms[2], ctx->ev_x0, ctx->ev_x1));   // execute: both grids
         CK(ctx, cudaEventElapsedTime(&ctx->zstd_ms, ctx->evs[4], ctx->evs[5]));
         if (digest) memcpy(digest, h_res, n * sizeof(u64));
         if (status) memcpy(status, h_res + n * sizeof(u64), n * sizeof(int));
@@ -532,14 +618,14 @@ extern "C" int zpb_unpack_host(zpb_ctx *ctx, const uint8_t *h_archive, uint64_t 
     while ((int)ctx->workers.size() < W) {
         zpb_ctx *w = zpb_create(ctx->device);
         if (!w) return fail(ctx, ZPB_E_CUDA, "pipeline sub-context creation failed");
-        w->fast = ctx->fast; w->group = ctx->group; w->ctas_per_sm = ctx->ctas_per_sm;
+        w->fast = ctx->fast; w->group = ctx->group; w->ctas_per_sm = ctx->ctas_per_sm; w->overlap = ctx->overlap;
         ctx->workers.push_back(w);
     }
     std::vector<int> rcs(W, ZPB_OK);
     std::vector<std::string> errs(W);
     auto body = [&](int t) {
         zpb_ctx *w = ctx->workers[t];
-        w->fast = ctx->fast; w->group = ctx->group; w->ctas_per_sm = ctx->ctas_per_sm;
+        w->fast = ctx->fast; w->group = ctx->group; w->ctas_per_sm = ctx->ctas_per_sm; w->overlap = ctx->overlap;
         std::vector<zpb_entry> sub;
         std::vector<int32_t> st;
         std::vector<u64> dg;

@@ -51,7 +51,7 @@ EXPORTS = [
     "zpb_abi_version", "zpb_create", "zpb_destroy", "zpb_last_error", "zpb_device_info",
     "zpb_launch_count", "zpb_unpack_device", "zpb_unpack_host", "zpb_xxh3_device", "zpb_xxh3_host",
     "zpb_pack_bound", "zpb_pack_device", "zpb_pack_host", "zpb_last_kernel_ms", "zpb_set_tuning",
-    "zpb_last_stage_ms", "zpb_set_fast_path", "zpb_last_zstd_ms",
+    "zpb_last_stage_ms", "zpb_set_fast_path", "zpb_set_overlap", "zpb_last_zstd_ms",
     "zpb_lz4_frame_index", "zpb_unpack_blocks_device", "zpb_blocks_digest", "zpb_last_chain_ms",
     "zpb_unpack_entry_blocks_host",
 ]
@@ -94,6 +94,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.zpb_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.zpb_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.zpb_set_fast_path.argtypes = [vp, C.c_int]
+    lib.zpb_set_overlap.argtypes = [vp, C.c_int]
     lib.zpb_last_zstd_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.zpb_lz4_frame_index.argtypes = [vp, u64, u64, vp, u64, u64p, C.POINTER(C.c_uint32), u64p]
     lib.zpb_unpack_blocks_device.argtypes = [vp, vp, u64, vp, u64, vp, u64, C.c_uint32, u64, i32p, vp]
@@ -167,6 +168,10 @@ class Context:
     def set_fast_path(self, enabled: bool):
         """False: every entry goes through the general decoder (A/B runs, tests of that kernel)."""
         self._check(self.lib.zpb_set_fast_path(self.h, int(enabled)))
+
+    def set_overlap(self, enabled: bool):
+        """False: scan, parse and execute run back to back on one stream (per-kernel timings are then meaningful)."""
+        self._check(self.lib.zpb_set_overlap(self.h, int(enabled)))
 
     def last_stage_ms(self):
         a = (C.c_float * 4)()
