@@ -426,7 +426,8 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
         CK(ctx, cudaEventRecord(ctx->ev_p1, sp));
         CK(ctx, cudaEventRecord(ctx->ev_x0, s));
         const u32 *d_xord = overlap ? (const u32 *)ctx->d_order2.p : d_ord;
-        const int early = overlap ? (k2_ctas > 1 ? k2_ctas - 1 : 1) : k2_ctas;
+        static const int early_env = [] { const char *e = getenv("ZPB_EARLY_CTAS"); return e ? atoi(e) : 0; }();
+        const int early = overlap ? (early_env > 0 && early_env <= k2_ctas ? early_env : (k2_ctas > 1 ? k2_ctas - 1 : 1)) : k2_ctas;
         u32 *d_defer = overlap ? (u32 *)ctx->d_defer.p : nullptr;   // cnt[11]: work counter of the last pass, cnt[12]: its length
         lz4_fast_exec_kernel<<<ctx->sm_count * early, 32 * FAST_EXEC_WARPS, FAST_EXEC_SMEM, s>>>(
             d_archive, archive_size, d_out, d_e, d_xord, (u32)n, cnt + 3, (const FastEntry *)ctx->d_fe.p,
