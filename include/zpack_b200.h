@@ -175,6 +175,9 @@ uint64_t zpb_pack_bound(uint32_t method, uint64_t size);
 int zpb_pack_device(zpb_ctx *ctx, const uint8_t *d_in, uint64_t in_size, uint8_t *d_out,
                     uint64_t out_size, const zpb_file *files, uint64_t n, uint64_t *comp_size,
                     uint64_t *digest, int32_t *status, void *stream);
+/* The same with host buffers: large batches are cut into chunks over worker streams (H2D of a chunk's input, kernel,
+ * on-device gather of the frames, one D2H, host scatter into the slots at files[i].dst_off); bytes of h_out outside
+ * [dst_off, dst_off + comp_size[i]) are not written. */
 int zpb_pack_host(zpb_ctx *ctx, const uint8_t *h_in, uint64_t in_size, uint8_t *h_out,
                   uint64_t out_size, const zpb_file *files, uint64_t n, uint64_t *comp_size,
                   uint64_t *digest, int32_t *status);
@@ -182,7 +185,9 @@ int zpb_pack_host(zpb_ctx *ctx, const uint8_t *h_in, uint64_t in_size, uint8_t *
 /* last kernel timing (CUDA events on the launching stream), for bench.py's roofline block */
 int zpb_last_kernel_ms(const zpb_ctx *ctx, float *unpack_ms, float *pack_ms);
 
-/* per-stage device time of the last unpack (ms): scan, parse, exec, general-fallback */
+/* per-stage device time of the last unpack (ms): scan, parse, exec, general-fallback.  With the overlap on (the
+ * default, zpb_set_overlap) parse and exec run concurrently, so the two intervals overlap and exec's includes the time
+ * its early grid had to share the SMs with the parse kernel; zpb_last_kernel_ms is first launch to last either way. */
 int zpb_last_stage_ms(const zpb_ctx *ctx, float *ms4);
 /* device time of zstd_unpack_kernel in the last unpack (ms; 0 when the batch had no zstd entry) */
 int zpb_last_zstd_ms(const zpb_ctx *ctx, float *ms);
