@@ -13,12 +13,19 @@
 //                                    The compressed stream is staged per lane through shared memory
 //                                    with cp.async (LDGSTS), four 64-byte chunks ahead of the cursor,
 //                                    so the serial walk never waits on HBM.
-//   K2 exec   one warp per entry     32 sequences at a time, one per lane: every lane re-reads its own
-//                                    token, copies its literals and its match.  Output is assembled in
-//                                    a 4 KiB shared-memory ring per warp; each finished 1 KiB goes out
-//                                    as 16-byte coalesced stores and is folded into XXH3-64 from the
-//                                    same registers (the digest never re-reads HBM).  Near matches read
-//                                    the ring, far matches read flushed output back through L2.
+//   K2 exec   one warp per entry     32 sequences at a time, one per lane.  The compressed bytes come through a
+//                                    per-warp cp.async staging ring; literals and short non-overlapping matches are
+//                                    copied one lane per sequence (word-wise, lane_copy), long / periodic ones by the
+//                                    whole warp in 16-byte units (coop_match); matches that source an earlier match of
+//                                    the same step are redirected through its offset (pointer jumping) so that they
+//                                    read final bytes; far matches are fetched from flushed output with cp.async.
+//                                    Output is assembled in a 4 KiB shared-memory ring per warp; each finished 1 KiB
+//                                    goes out as 16-byte coalesced stores and is folded into XXH3-64 from the same
+//                                    registers (the digest never re-reads HBM).
+//
+// K2 does not wait for K1: K0 sorts blocks into three work lists by weight, K1 (high-priority stream) walks the heavy
+// list on its first CTAs and publishes each verdict behind a fence, K2 (three launches over one work queue, see
+// zpb_api.cu) starts on the entries that are parsed at once and puts aside what is not parsed yet.
 //
 // K0/K1 only ACCEPT: anything unusual (checksummed or multi-frame entries, > 64 KB blocks, any
 // malformed byte, sizes that do not add up) is handed to the general decoder in lz4_decode.cuh,

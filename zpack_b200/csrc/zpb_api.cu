@@ -371,7 +371,8 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
     u32 *h_order2 = (u32 *)(hs + desc_b + ord_b + res_b + 64 + n * sizeof(FastAux));
     {
         u64 ncheap = 0;
-        while (ncheap < n && keys[h_order[n - 1 - ncheap]] >= 1023u - 31u) ++ncheap;   // cost below 32 x 512 B
+        static const u32 front_buckets = [] { const char *e = getenv("ZPB_FRONT_BUCKETS"); int v = e ? atoi(e) : 0; return (u32)(v > 0 && v < 1024 ? v : 32); }();
+        while (ncheap < n && keys[h_order[n - 1 - ncheap]] >= 1024u - front_buckets) ++ncheap;   // cost below front_buckets x 512 B (default 16 KB)
         for (u64 k = 0; k < ncheap; ++k) h_order2[k] = h_order[n - 1 - k];
         for (u64 k = ncheap; k < n; ++k) h_order2[k] = h_order[k - ncheap];
     }
