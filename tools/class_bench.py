@@ -47,6 +47,8 @@ def main():
     ap.add_argument("--independent", action="store_true")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--fast", type=int, default=1)
+    ap.add_argument("--exec-ctas", default="", help="comma list of ZPB_EXEC_CTAS values to sweep (LZ4 execute kernel: 3 or 4)")
+    ap.add_argument("--overlap", default="", help="comma list of 0/1: parse / execute overlap off / on")
     ap.add_argument("--method", default="lz4", choices=["lz4", "zstd"],
                     help="zstd: frames written by the unmodified reference (oracle/_ref), level 3")
     args = ap.parse_args()
@@ -64,8 +66,15 @@ def main():
         d_arch = torch.from_numpy(arch).cuda()
         d_out = torch.empty(out_size, dtype=torch.uint8, device="cuda")
         comp, unc = int(d.comp_size.sum()), int(d.uncomp_size.sum())
-        for g in [int(x) for x in args.groups.split(",")]:
+        sweep = [(g, c, ov) for g in [int(x) for x in args.groups.split(",")]
+                 for c in ([int(x) for x in args.exec_ctas.split(",")] if args.exec_ctas else [0])
+                 for ov in ([int(x) for x in args.overlap.split(",")] if args.overlap else [-1])]
+        for g, xc, ov in sweep:
             ctx.set_tuning(group_lanes=g)
+            if xc:
+                os.environ["ZPB_EXEC_CTAS"] = str(xc)
+            if ov >= 0:
+                ctx.set_overlap(bool(ov))
             ms = []
             for r in range(args.reps + 2):
                 st, dg = ctx.unpack_device(d_arch, len(arch), d_out, out_size, e)
@@ -73,7 +82,7 @@ def main():
                     ms.append(ctx.last_kernel_ms()["unpack_ms"])
             assert (st == 0).all() and np.array_equal(dg, d.hash)
             t = float(np.median(ms))
-            print(json.dumps({"method": args.method, "class": names[cls], "group": g, "kernel_ms": round(t, 4),
+            print(json.dumps({"method": args.method, "class": names[cls], "group": g, "exec_ctas": xc, "overlap": ov, "kernel_ms": round(t, 4),
                               "uncomp_GBps": round(unc / t / 1e6, 1), "traffic_GBps": round((comp + unc) / t / 1e6, 1),
                               "ratio": round(unc / comp, 3), "entries": args.entries,
                               "stages": {k: round(v, 4) for k, v in ctx.last_stage_ms().items()}}), flush=True)

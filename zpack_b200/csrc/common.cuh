@@ -6,7 +6,11 @@
 // never needs a shuffle to agree on what to do next; lanes differ only in which bytes they move.
 #pragma once
 #include <cstdint>
+#ifdef ZPB_SIM
+#include "../../tests/sim/sim_cuda.h"   // CPU emulation of the CUDA names (test infrastructure, see tests/sim/sim_rt.h)
+#else
 #include <cuda_runtime.h>
+#endif
 
 typedef uint8_t u8;
 typedef uint16_t u16;
@@ -42,10 +46,14 @@ ZPB_DEVINL u64 ld64u(const u8 *p) { return (u64)ld32u(p) | ((u64)ld32u(p + 4) <<
 
 // streaming 16-byte accesses (data touched once: keep it out of L1)
 ZPB_DEVINL uint4 ldg128_stream(const void *p) {
+#ifdef ZPB_SIM
+    return *reinterpret_cast<const uint4 *>(p);
+#else
     uint4 r;
     asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
+#endif
 }
 ZPB_DEVINL uint4 ldg128(const void *p) { return *reinterpret_cast<const uint4 *>(p); }
 ZPB_DEVINL void stg128(void *p, uint4 v) { *reinterpret_cast<uint4 *>(p) = v; }

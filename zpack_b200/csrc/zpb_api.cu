@@ -160,6 +160,8 @@ extern "C" zpb_ctx *zpb_create(int device) {
     if (cudaFuncSetAttribute(lz4_fast_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(K1_THREADS * K1_ROW)) != cudaSuccess ||
         cudaFuncSetAttribute(lz4_fast_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(FAST_EXEC_SMEM)) != cudaSuccess ||
+        cudaFuncSetAttribute(lz4_fast_exec_kernel4, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(FAST_EXEC_SMEM)) != cudaSuccess) {
         g_last_error = std::string("kernel attribute setup failed: ") + cudaGetErrorString(cudaGetLastError());
         delete ctx; return nullptr;
@@ -340,6 +342,9 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
         zpb_entry e = entries[i];
         if (e.comp_size != 0 && (e.dst_off > out_size || e.dst_cap > out_size - e.dst_off))
             return fail(ctx, ZPB_E_ARG, "entry output slot exceeds the output buffer");
+        // the kernels store 16 bytes at a time into the slot (include/zpack_b200.h: dst_off is 16-byte aligned)
+        if (e.comp_size != 0 && (((uintptr_t)d_out + e.dst_off) & 15u))
+            return fail(ctx, ZPB_E_ARG, "entry output slot is not 16-byte aligned");
         any_zstd |= e.method == ZPB_METHOD_ZSTD;
         u64 c = (e.method == ZPB_METHOD_NONE || e.comp_size >= e.uncomp_size) ? e.comp_size / 16 : e.comp_size;
         c >>= 9;  // 512-byte cost buckets, descending
@@ -411,7 +416,9 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
         // never wait: an entry whose blocks are not parsed yet is put aside), the third CTA per SM once the parse kernel
         // has finished, and a last pass over the entries that were put aside.
         const bool overlap = ctx->overlap != 0;
-        static const int k2_ctas = [] { const char *e = getenv("ZPB_EXEC_CTAS"); int v = e ? atoi(e) : 0; return v > 0 && v <= 8 ? v : FAST_EXEC_CTAS; }();
+        // resident CTAs per SM of the execute kernel: 3 (80 registers) or 4 (64 registers) — two builds of one body
+        const int k2_ctas = [] { const char *e = getenv("ZPB_EXEC_CTAS"); int v = e ? atoi(e) : 0; return v > 0 && v <= 4 ? v : FAST_EXEC_CTAS; }();
+        const fast_exec_fn exec_kernel = k2_ctas >= 4 ? lz4_fast_exec_kernel4 : lz4_fast_exec_kernel;
         const int k1_ctas = ctx->ctas_per_sm > 0 ? ctx->ctas_per_sm : 3;
         cudaStream_t sp = overlap ? ctx->stream_p : s;
         if (overlap) {
@@ -430,7 +437,7 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
         static const int early_env = [] { const char *e = getenv("ZPB_EARLY_CTAS"); return e ? atoi(e) : 0; }();
         const int early = overlap ? (early_env > 0 && early_env <= k2_ctas ? early_env : (k2_ctas > 1 ? k2_ctas - 1 : 1)) : k2_ctas;
         u32 *d_defer = overlap ? (u32 *)ctx->d_defer.p : nullptr;   // cnt[11]: work counter of the last pass, cnt[12]: its length
-        lz4_fast_exec_kernel<<<ctx->sm_count * early, 32 * FAST_EXEC_WARPS, FAST_EXEC_SMEM, s>>>(
+        exec_kernel<<<ctx->sm_count * early, 32 * FAST_EXEC_WARPS, FAST_EXEC_SMEM, s>>>(
             d_archive, archive_size, d_out, d_e, d_xord, (u32)n, cnt + 3, (const FastEntry *)ctx->d_fe.p,
             (const FastBlock *)ctx->d_fb.p, (const u32 *)ctx->d_fdesc.p, cnt, (u32 *)ctx->d_glist.p, d_status,
             d_digest, ctx->cur_partials, d_defer, cnt + 12, nullptr);
@@ -438,7 +445,7 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
         if (overlap) {
             if (k2_ctas > early) {
                 CK(ctx, cudaStreamWaitEvent(ctx->stream_b, ctx->ev_p1, 0));
-                lz4_fast_exec_kernel<<<ctx->sm_count * (k2_ctas - early), 32 * FAST_EXEC_WARPS, FAST_EXEC_SMEM, ctx->stream_b>>>(
+                exec_kernel<<<ctx->sm_count * (k2_ctas - early), 32 * FAST_EXEC_WARPS, FAST_EXEC_SMEM, ctx->stream_b>>>(
                     d_archive, archive_size, d_out, d_e, d_xord, (u32)n, cnt + 3, (const FastEntry *)ctx->d_fe.p,
                     (const FastBlock *)ctx->d_fb.p, (const u32 *)ctx->d_fdesc.p, cnt, (u32 *)ctx->d_glist.p, d_status,
                     d_digest, ctx->cur_partials, d_defer, cnt + 12, nullptr);
@@ -450,7 +457,7 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
                 CK(ctx, cudaStreamWaitEvent(s, ctx->ev_p1, 0));
             }
             // what the early grids put aside (entries reached before their blocks were parsed): usually nothing
-            lz4_fast_exec_kernel<<<ctx->sm_count * k2_ctas, 32 * FAST_EXEC_WARPS, FAST_EXEC_SMEM, s>>>(
+            exec_kernel<<<ctx->sm_count * k2_ctas, 32 * FAST_EXEC_WARPS, FAST_EXEC_SMEM, s>>>(
                 d_archive, archive_size, d_out, d_e, d_defer, 0u, cnt + 11, (const FastEntry *)ctx->d_fe.p,
                 (const FastBlock *)ctx->d_fb.p, (const u32 *)ctx->d_fdesc.p, cnt, (u32 *)ctx->d_glist.p, d_status,
                 d_digest, ctx->cur_partials, nullptr, nullptr, cnt + 12);
