@@ -54,8 +54,9 @@ def main():
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--sass", action="store_true", help="also list the hottest SASS instructions")
     ap.add_argument("--dump", default=None, help="write the whole kernel, in address order, with per-instruction counts")
+    ap.add_argument("--sass-re", default=None, help="regex on the MANGLED name in the .so (default: the kernel regex)")
     a = ap.parse_args()
-    lines = sass_lines(a.so, a.kernel)
+    lines = sass_lines(a.so, a.sass_re or a.kernel)
     raw = subprocess.run(["ncu", "-i", a.report, "--page", "source", "--csv", "--kernel-name", "regex:" + a.kernel],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))

@@ -72,7 +72,7 @@ def parse(buf) -> Directory:
     esig, cdr_off = struct.unpack_from("<IQ", mv, size - EOCDR_SIZE)
     if esig != SIG_EOCDR:
         raise ArchiveError("bad EOCDR signature")
-    if cdr_off >= size:
+    if cdr_off >= size or cdr_off + CDR_HEADER_SIZE > size - EOCDR_SIZE:
         raise ArchiveError("CDR offset out of range")
     csig, count, block = struct.unpack_from("<IQQ", mv, cdr_off)
     if csig != SIG_CDR:
@@ -82,6 +82,8 @@ def parse(buf) -> Directory:
     names, fixed = [], np.empty((count, 33), np.uint8)
     p, left = cdr_off + CDR_HEADER_SIZE, block
     for i in range(count):
+        if left < 2:
+            raise ArchiveError("bad CDR block size")
         (nl,) = struct.unpack_from("<H", mv, p)
         if ENTRY_FIXED + nl > left:
             raise ArchiveError("bad CDR block size")

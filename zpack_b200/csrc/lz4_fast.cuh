@@ -44,19 +44,24 @@
 
 #include "ptx.cuh"
 
-#define X_RING   4096u   // per-warp output ring (shared memory), aligned to its size: position p lives at rb | (p & X_RMASK)
-#define X_RMASK  4095u
-#define X_MARGIN 64u     // a step never fills the ring closer than this to the oldest byte it may still source from HBM
-#define C_RING   2048u   // per-warp ring for the compressed stream, aligned to its size
-#define C_MASK   2047u
-#define C_ROW    512u    // one bulk copy
-#define C_ROWSH  9
-#define C_ROWS   4u
+#define FAST_RING      4096u
+#define FAST_RMASK     4095u
+#define FAST_LONG      32u     // lit or match >= this: executed cooperatively by the whole warp
+#ifndef FAST_SCR
+#define FAST_SCR       80u     // per-lane staging for a far match: 5 x 16 B cover 15 + 64 bytes
+#define FAST_ST        64u     // far matches up to this length are staged (cp.async from L2)
+#define CR_SIZE        2048u   // per-warp staging ring for the compressed stream
+#define CR_ROW         512u    // one fill: 16 bytes per lane
+#endif
+#define CR_MASK        (CR_SIZE - 1u)
+#define C_ROW          CR_ROW  // one bulk async copy (cp.async.bulk, the TMA unit) = one row of the staging ring
+#define C_ROWSH        9
+#define C_ROWS         (CR_SIZE / CR_ROW)
+#define FAST_WARP_SMEM (FAST_RING + 32u * FAST_SCR + CR_SIZE + 32u)   // + 32: lane_copy's whole-word over-reads past the staging ring stay inside the warp's own region
 #ifndef FAST_EXEC_WARPS
 #define FAST_EXEC_WARPS 8u
 #endif
-// per CTA: rings (4 KiB aligned, hence the pad), then 4 mbarriers per warp
-#define FAST_EXEC_SMEM (4096u + FAST_EXEC_WARPS * (X_RING + C_RING) + FAST_EXEC_WARPS * 32u + 16u)
+#define FAST_EXEC_SMEM (FAST_EXEC_WARPS * FAST_WARP_SMEM + 48u + FAST_EXEC_WARPS * 8u * C_ROWS)   // per CTA, plus slack at both ends; then C_ROWS mbarriers per warp
 
 #define FE_DONE    0u   // status already final (guards, unsupported method)
 #define FE_FAST    1u   // block table filled, goes through K1/K2
@@ -217,42 +222,24 @@ lz4_fast_scan_kernel(const u8 *__restrict__ archive, u64 asz, const zpb_entry *_
 }
 
 // ------------------------------------------------------------------------------------------ lane copy
-// Warp-lockstep copy: every lane moves its own n bytes (0 = idle) from a source of its own — a generic address, in
-// the shared window (rings) or in HBM (output that has left the ring) — to its own place d in shared memory, any
-// alignment, ranges not overlapping.  Head bytes up to the destination's word boundary, then whole words assembled
-// from two aligned source words with a funnel shift, then tail bytes.  The aligned source words may contain bytes
-// outside [s, s+n) (up to 3 before, and the last round reads up to 19 past the last whole word): they are read,
-// never stored — callers keep those addresses inside the ring / the entry's flushed output (see `lane_ok` in K2).
-ZPB_DEVINL void lane_copy(u64 s, u32 d, u32 n) {
+// Warp-lockstep copy inside shared memory: every lane moves its own n bytes (0 = idle) from s to d, any alignment,
+// ranges not overlapping.  Head bytes up to the destination's word boundary, then whole words assembled from two
+// aligned source words with a funnel shift, then tail bytes (ptx.cuh: copy_edges_ss / copy_words_ss).  The aligned
+// source words may contain bytes outside [s, s+n) (up to 3 before; a round reads up to 19 past its last whole word):
+// they are read, never stored — callers keep s + n + LANE_COPY_SLACK inside the region the source lives in.
+ZPB_DEVINL void lane_copy(u32 s, u32 d, u32 n) {
     u32 h = (0u - d) & 3u;
     h = h < n ? h : n;
     const u32 n2 = n - h;
     const u32 nw = n2 >> 2, t = n2 & 3u;
-    const u64 s2 = s + h;
-    const u32 d2 = d + h;                      // word aligned whenever nw > 0
-    const u64 ts = s2 + 4 * nw;
-    const u32 td = d2 + 4 * nw;
-    u32 a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
-    ldgen8_if(h > 0, s, a0); ldgen8_if(h > 1, s + 1, a1); ldgen8_if(h > 2, s + 2, a2);
-    ldgen8_if(t > 0, ts, b0); ldgen8_if(t > 1, ts + 1, b1); ldgen8_if(t > 2, ts + 2, b2);
-    sts8_if(h > 0, d, a0); sts8_if(h > 1, d + 1, a1); sts8_if(h > 2, d + 2, a2);
-    sts8_if(t > 0, td, b0); sts8_if(t > 1, td + 1, b1); sts8_if(t > 2, td + 2, b2);
+    const u32 s2 = s + h, d2 = d + h;            // d2 is word aligned whenever nw > 0
+    copy_edges_ss(h, t, s, d, s2 + 4 * nw, d2 + 4 * nw);
     const u32 maxnw = __reduce_max_sync(0xffffffffu, nw);
-    const u64 sw = s2 & ~3ull;
-    const u32 sh = ((u32)s2 & 3u) << 3;
-    for (u32 kb = 0; kb < maxnw; kb += 4) {    // four whole words per round
-        const u32 rem = nw > kb ? nw - kb : 0u;
-        u32 w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0;
-        ldgen32x5_if(rem > 0, sw + 4 * kb, w0, w1, w2, w3, w4);
-        const u32 da = d2 + 4 * kb;
-        sts32_if(rem > 0, da, __funnelshift_r(w0, w1, sh));
-        sts32_if(rem > 1, da + 4, __funnelshift_r(w1, w2, sh));
-        sts32_if(rem > 2, da + 8, __funnelshift_r(w2, w3, sh));
-        sts32_if(rem > 3, da + 12, __funnelshift_r(w3, w4, sh));
-    }
+    const u32 sw = s2 & ~3u, sh = (s2 & 3u) << 3;
+#pragma unroll 1
+    for (u32 kb = 0; kb < maxnw; kb += 4)        // four whole words per round
+        copy_words_ss(nw > kb ? nw - kb : 0u, sw + 4 * kb, sh, d2 + 4 * kb);
 }
-// how far past s + n the word reads of lane_copy may reach (3 head + 3 round-up + one extra word of the funnel + 12 of a
-// partly used round): callers keep s + n + LANE_COPY_SLACK inside readable memory
 #define LANE_COPY_SLACK 24u
 
 // ------------------------------------------------------------------------------------------ K1
@@ -503,122 +490,27 @@ lz4_fast_parse_kernel(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, co
 }
 
 // ------------------------------------------------------------------------------------------ K2
+
 // K2 starts while K1 is still walking the heaviest blocks (separate streams): everything K1 produces is read through
 // L2 (ld.global.cg / volatile), never through the non-coherent or L1 paths, whose lines could predate K1's stores.
 ZPB_DEVINL u32 ldcg32(const u32 *p) { return __ldcg(p); }
 
+#define FAST_LT  16u   // literal runs up to this go one-lane-per-sequence (from global memory); longer ones warp-wide
 #ifndef FAST_LTR
-#define FAST_LTR 32u   // literal runs up to this go one-lane-per-sequence (word copies out of the staging ring)
+#define FAST_LTR 32u   // the same when the source is the staging ring (word copies)
 #endif
 #ifndef FAST_MT
-#define FAST_MT  64u   // matches up to this go one-lane-per-sequence (non-overlapping, source linear in the ring or in HBM)
+#define FAST_MT  64u   // matches up to this go one-lane-per-sequence (non-overlapping, linear in shared memory)
 #endif
 
 #define DS_FINAL 0u   // source bytes are final (possibly after redirection by `shift`)
 #define DS_CHILD 1u   // source wholly inside lane `parent`'s match: being resolved
 #define DS_HARD  2u   // source straddles pending matches: executed in lane order
 
-// The compressed bytes of the block a warp is executing, staged through a per-warp shared-memory ring of C_ROWS rows
-// of C_ROW bytes.  A row is one 1-D bulk async copy (cp.async.bulk.shared::cluster.global, the TMA unit) issued by
-// lane 0 and tracked by the row slot's mbarrier (expect_tx = the row's bytes); every lane waits on the barrier's
-// phase parity before it reads the row.  Rows are requested one ahead of the step that reads them.  Positions are
-// ring coordinates c = block position + skew, with the global address of coordinate 0 16-byte aligned; bulk copies
-// are clipped to the 16-byte aligned interior of the archive, the (< 16) bytes at either end of the archive are
-// moved by plain loads.
-struct XStage {
-    const u8 *gbase;       // global address of ring coordinate 0
-    const u8 *glo, *ghi;   // the archive
-    const u8 *alo, *ahi;   // its 16-byte aligned interior
-    u32 cb;                // the ring (shared-window address, C_RING aligned)
-    u32 bar;               // C_ROWS mbarriers, 8 bytes each
-    u32 skew;
-    u32 fill;              // rows [.., fill) have been requested
-    u32 waited;            // rows [.., waited) have been waited for
-    u32 nrows;             // rows that cover the block
-    u32 phase;             // bit s: parity of the phase slot s's barrier is in
-    int lane;
-
-    ZPB_DEVINL void init(const u8 *archive, u64 asz, u32 ring, u32 bars, int l) {
-        glo = archive; ghi = archive + asz;
-        alo = (const u8 *)(((uintptr_t)archive + 15u) & ~(uintptr_t)15u);
-        ahi = (const u8 *)((uintptr_t)(archive + asz) & ~(uintptr_t)15u);
-        if (ahi < alo) ahi = alo;
-        cb = ring; bar = bars; lane = l;
-        skew = fill = waited = nrows = phase = 0;
-        gbase = archive;
-        if (lane == 0) {
-            for (u32 s = 0; s < C_ROWS; ++s) mbar_init(bar + 8 * s, 1);
-            mbar_fence_init();
-        }
-        __syncwarp();
-    }
-    ZPB_DEVINL void wait_row() {
-        const u32 s = waited & (C_ROWS - 1u);
-        mbar_wait(bar + 8 * s, (phase >> s) & 1u);
-        phase ^= 1u << s;
-        ++waited;
-    }
-    ZPB_DEVINL void drain() { while (waited < fill) wait_row(); }
-    ZPB_DEVINL void open(const u8 *src, u32 bsz) {
-        drain();                     // a look-ahead row of the previous block may still be in flight
-        __syncwarp();
-        skew = (u32)((uintptr_t)src & 15u);
-        gbase = src - skew;
-        fill = waited = 0;
-        nrows = (bsz + skew + C_ROW - 1u) >> C_ROWSH;
-    }
-    ZPB_DEVINL void request_row() {   // row `fill` -> slot fill % C_ROWS; every reader of the slot's old content is done
-        const u32 s = fill & (C_ROWS - 1u);
-        const u8 *g0 = gbase + ((u64)fill << C_ROWSH), *g1 = g0 + C_ROW;
-        const u8 *lo = g0 > alo ? g0 : alo, *hi = g1 < ahi ? g1 : ahi;
-        const u32 bytes = hi > lo ? (u32)(hi - lo) : 0u;
-        const u32 sdst = cb + s * C_ROW;
-        if (lane == 0) {
-            mbar_arrive_expect_tx(bar + 8 * s, bytes);
-            if (bytes) bulk_g2s(sdst + (u32)(lo - g0), lo, bytes, bar + 8 * s);
-        }
-        // the archive's unaligned ends (at most 15 bytes each, and only in the rows that contain them)
-        if (g0 < alo || g1 > ahi) {
-            const u8 *e0 = g0 > glo ? g0 : glo, *e1 = g1 < ghi ? g1 : ghi;
-            for (const u8 *p = e0 + lane; p < e1; p += 32)
-                if (p < lo || p >= hi) sts8(sdst + (u32)(p - g0), *p);
-        }
-        ++fill;
-    }
-    // Makes rows [r0, r1] readable (r1 - r0 < C_ROWS, the caller checks) and asks for the row after them.
-    ZPB_DEVINL void ensure(u32 r0, u32 r1) {
-        u32 want = r1 + 1u < r0 + C_ROWS ? r1 + 1u : r1;     // one row of look-ahead when the ring has room for it
-        if (want >= nrows) want = nrows ? nrows - 1u : 0u;
-        if (want < r1) want = r1;
-        if (fill > want && waited > r1) return;  // the usual case: requested a step ago, waited for since
-        while (waited < fill && waited < r0) wait_row();   // requested, then skipped by a sequence that went around the ring
-        if (fill < r0) fill = waited = r0;
-        if (fill <= want) {
-            __syncwarp();                        // every lane has finished reading the slots that are filled again
-            while (fill <= want) request_row();
-        }
-        while (waited <= r1) wait_row();
-        __syncwarp();                            // edge bytes written by other lanes
-    }
-    ZPB_DEVINL u32 addr(u32 p) const { return cb | ((p + skew) & C_MASK); }   // block position -> shared-window address
-    ZPB_DEVINL u32 rd(u32 p) const { return lds8(addr(p)); }
-};
-
-// unaligned 16-byte global load assembled from 4-byte-aligned words
-ZPB_DEVINL uint4 ldg128_unaligned(const u8 *p) {
-    const u32 *s = reinterpret_cast<const u32 *>((uintptr_t)p & ~(uintptr_t)3);
-    u32 sh = ((u32)(uintptr_t)p & 3u) * 8u;
-    u32 w0 = s[0], w1 = s[1], w2 = s[2], w3 = s[3];
-    if (sh == 0) return make_uint4(w0, w1, w2, w3);
-    u32 w4 = s[4];
-    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
-                      __funnelshift_r(w3, w4, sh));
-}
-
 struct FastExec {
-    u32 rb;         // this warp's output ring (shared-window address, X_RING aligned): position p lives at rb | (p & X_RMASK)
+    u32 rb;         // this warp's output ring (shared-window address): position p lives at rb + (p & FAST_RMASK)
+    u32 scr_s;      // this lane's far-match staging (shared-window address)
     u8 *gout;       // the entry's final place in HBM (16-byte aligned)
-    const u8 *glo;  // the archive (word reads never start below it)
     u32 done;       // every byte below is final (in the ring and/or in HBM)
     u32 flushed;    // HBM holds [0, flushed); multiple of 1024 until the very end
     u32 rbase;      // ring content below this position is stale (direct stored path went around it)
@@ -628,10 +520,10 @@ struct FastExec {
     int lane;
 
     ZPB_DEVINL u32 ring_lo(u32 hi) const {
-        u32 w = hi > X_RING ? hi - X_RING : 0u;
+        u32 w = hi > FAST_RING ? hi - FAST_RING : 0u;
         return w > rbase ? w : rbase;
     }
-    ZPB_DEVINL u32 ra(u32 pos) const { return rb | (pos & X_RMASK); }
+    ZPB_DEVINL u32 ra(u32 pos) const { return rb + (pos & FAST_RMASK); }
     ZPB_DEVINL u32 rd(u32 pos, u32 lo) const { return pos >= lo ? lds8(ra(pos)) : ldg8_coherent(gout + pos); }
 
     ZPB_DEVINL void hash_init() {
@@ -659,7 +551,7 @@ struct FastExec {
     }
     // one full 1 KiB block: ring -> HBM (16 B per lane, coalesced) and -> XXH3 from the same registers
     ZPB_DEVINL void flush_kib() {
-        u32 a = rb + (flushed & X_RMASK) + lane * 16;
+        u32 a = rb + (flushed & FAST_RMASK) + lane * 16;
         int j = lane & 3;
         u64 s0 = 0, s1 = 0;
         uint4 v0 = lds128(a), v1 = lds128(a + 512);
@@ -679,27 +571,13 @@ struct FastExec {
             __syncwarp();
         }
     }
-    ZPB_DEVINL u32 room() const { return flushed + X_RING - done; }
+    ZPB_DEVINL u32 room() const { return flushed + FAST_RING - done; }
 
-    // warp-wide: ring[O + i] = sp[i], i < L, from global memory (inside a segment: no flush)
-    ZPB_DEVINL void coop_lit_global(u32 O, const u8 *__restrict__ sp, u32 L) const {
-        u32 i = 0;
-        if (L >= 64 && sp >= glo + 4) {
-            // 16-byte destination chunks (aligned ring stores), source bytes assembled from aligned global words; the
-            // last >= 4 bytes are left to the byte loop so that the funnel's fifth word stays inside sp[0..L)
-            const u32 head = (0u - O) & 15u;
-            if ((u32)lane < head) sts8(ra(O + lane), sp[lane]);
-            const u32 n16 = (L - head - 4u) >> 4;
-            const u8 *s0 = sp + head;
-            for (u32 c = lane; c < n16; c += 32) sts128(ra(O + head + 16 * c), ldg128_unaligned(s0 + 16 * c));
-            i = head + 16 * n16;
-        }
-        for (u32 k = i + lane; k < L; k += 32) sts8(ra(O + k), sp[k]);
+    // warp-wide: ring[O + i] = sp[i], i < L (inside a segment: no flush)
+    ZPB_DEVINL void coop_lit(u32 O, const u8 *__restrict__ sp, u32 L) const {
+        for (u32 i = lane; i < L; i += 32) sts8(ra(O + i), sp[i]);
     }
-    // warp-wide: ring[O + i] = staged compressed byte S + i, i < L (S..S+L lies inside the staged rows)
-    ZPB_DEVINL void coop_lit_ring(u32 O, const XStage &cs, u32 S, u32 L) const {
-        for (u32 i = lane; i < L; i += 32) sts8(ra(O + i), cs.rd(S + i));
-    }
+    // warp-wide match: out[MO + i] = out[MO + i - OF], i < ML, everything below MO final
     // 16 source bytes starting at output position p (any alignment), from the ring or from HBM
     ZPB_DEVINL uint4 load16_ring(u32 p) const {
         const u32 b = p & ~3u, sh = (p & 3u) << 3;
@@ -748,16 +626,31 @@ struct FastExec {
             if ((u32)lane < tail) sts8(ra(tpos + lane), rd(tpos - OF + lane, lo));
             return;
         }
-        if (OF >= 32 || OF >= ML) {
-            // 32-byte steps never read what they write; later steps may read earlier ones
-            for (u32 b = 0; b < ML; b += 32) {
-                const u32 i = b + lane;
-                if (i < ML) sts8(ra(MO + i), rd(MO - OF + i, lo));
-                if (OF < ML) __syncwarp();
+        if (MO - OF >= lo) {
+            // whole source still in the ring (the usual dependent match): no HBM select per byte
+            if (OF >= 32) {
+                // 32-byte steps never read what they write; later steps may read earlier ones
+                for (u32 b = 0; b < ML; b += 32) {
+                    const u32 i = b + lane;
+                    if (i < ML) sts8(ra(MO + i), lds8(ra(MO - OF + i)));
+                    if (OF < ML) __syncwarp();
+                }
+            } else {  // period OF < 32: byte i is byte (i mod OF) of the OF bytes before MO
+                u32 k = (u32)lane < OF ? (u32)lane : (u32)lane % OF;
+                const u32 step = 32u % OF;
+                for (u32 i = lane; i < ML; i += 32) {
+                    sts8(ra(MO + i), lds8(ra(MO - OF + k)));
+                    k += step;
+                    if (k >= OF) k -= OF;
+                }
             }
-        } else {  // period OF < 32: byte i is byte (i mod OF) of the OF bytes before MO
+            return;
+        }
+        if (OF >= ML) {
+            for (u32 i = lane; i < ML; i += 32) sts8(ra(MO + i), rd(MO - OF + i, lo));
+        } else {  // periodic with period OF: byte i is byte (i mod OF) of the OF bytes before MO
             u32 k = (u32)lane < OF ? (u32)lane : (u32)lane % OF;
-            const u32 step = 32u % OF;
+            u32 step = OF > 32 ? 32u : 32u % OF;
             for (u32 i = lane; i < ML; i += 32) {
                 sts8(ra(MO + i), rd(MO - OF + k, lo));
                 k += step;
@@ -765,11 +658,11 @@ struct FastExec {
             }
         }
     }
-    // runs too long for the ring: piecewise with flushes in between
+    // the same, for runs too long for the ring: piecewise with flushes in between
     ZPB_DEVINL void stream_lit(const u8 *__restrict__ sp, u32 L) {
         while (L) {
             u32 piece = L < room() ? L : room();
-            coop_lit_global(done, sp, piece);
+            coop_lit(done, sp, piece);
             sp += piece; L -= piece; done += piece;
             flush_full();
         }
@@ -784,27 +677,160 @@ struct FastExec {
     }
 };
 
-// One sequence's control bytes straight from global memory (the rare sequence that is too large for the staging ring;
-// lz4.c:1797-1822, 1845-1860; K1 has validated them): literal length and start, match offset and length (0 for the
-// block's last sequence).
-ZPB_DEVINL void fast_decode_seq_global(const u8 *__restrict__ s, u32 tok, u32 bsz, u32 &lit, u32 &lsrc, u32 &off, u32 &ml) {
-    const u32 t = s[tok];
+
+// The compressed bytes of the block a warp is executing, staged through a per-warp shared-memory ring of C_ROWS rows
+// of C_ROW bytes.  A row is one 1-D bulk async copy (cp.async.bulk.shared::cluster.global, the TMA unit) issued by
+// lane 0 and tracked by the row slot's mbarrier (expect_tx = the row's bytes); every lane waits on the barrier's
+// phase parity before it reads the row.  Rows are requested one ahead of the step that reads them.  Positions are
+// ring coordinates c = block position + skew, with the global address of coordinate 0 16-byte aligned.  A block whose
+// rows all lie inside the 16-byte aligned interior of the archive (every block but those next to its two ends) is
+// `safe`: its rows are whole copies and nothing is clipped; otherwise the copies are clipped to that interior and the
+// (< 16) bytes at either end of the archive are moved by plain loads.
+struct XStage {
+    const u8 *gbase;       // global address of ring coordinate 0
+    u32 cb;                // the ring (shared-window address, C_RING aligned)
+    u32 bar;               // C_ROWS mbarriers, 8 bytes each
+    u32 skew;
+    u32 fill;              // rows [.., fill) have been requested
+    u32 waited;            // rows [.., waited) have been waited for
+    u32 nrows;             // rows that cover the block
+    u32 phase;             // bit s: parity of the phase slot s's barrier is in; bit 31: the block is `safe`
+    u32 lane;
+
+    ZPB_DEVINL void init(u32 ring, u32 bars, u32 l) {
+        cb = ring; bar = bars; lane = l;
+        skew = fill = waited = nrows = phase = 0;
+        gbase = nullptr;
+        if (lane == 0) {
+            for (u32 s = 0; s < C_ROWS; ++s) mbar_init(bar + 8 * s, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+    }
+    ZPB_DEVINL void wait_row() {
+        const u32 s = waited & (C_ROWS - 1u);
+        mbar_wait(bar + 8 * s, (phase >> s) & 1u);
+        phase ^= 1u << s;
+        ++waited;
+    }
+    ZPB_DEVINL void drain() { while (waited < fill) wait_row(); }
+    ZPB_DEVINL void open(const u8 *src, u32 bsz, const u8 *archive, u64 asz) {
+        drain();                     // a look-ahead row of the previous block may still be in flight
+        __syncwarp();
+        skew = (u32)((uintptr_t)src & 15u);
+        gbase = src - skew;
+        fill = waited = 0;
+        nrows = (bsz + skew + C_ROW - 1u) >> C_ROWSH;
+        const u8 *alo = (const u8 *)(((uintptr_t)archive + 15u) & ~(uintptr_t)15u);
+        const u8 *ahi = (const u8 *)((uintptr_t)(archive + asz) & ~(uintptr_t)15u);
+        const bool safe = gbase >= alo && gbase + ((u64)nrows << C_ROWSH) <= ahi;
+        phase = (phase & 0x7fffffffu) | (safe ? 0x80000000u : 0u);
+    }
+    ZPB_DEVINL void request_row(const u8 *archive, u64 asz) {   // row `fill` -> slot fill % C_ROWS; every reader of the slot's old content is done
+        const u32 s = fill & (C_ROWS - 1u);
+        const u32 sdst = cb + s * C_ROW;
+        const u8 *g0 = gbase + ((u64)fill << C_ROWSH);
+        if (phase >> 31) {
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar + 8 * s, C_ROW);
+                bulk_g2s(sdst, g0, C_ROW, bar + 8 * s);
+            }
+        } else {
+            const u8 *glo = archive, *ghi = archive + asz;
+            const u8 *alo = (const u8 *)(((uintptr_t)archive + 15u) & ~(uintptr_t)15u);
+            const u8 *ahi = (const u8 *)((uintptr_t)(archive + asz) & ~(uintptr_t)15u);
+            if (ahi < alo) ahi = alo;
+            const u8 *g1 = g0 + C_ROW;
+            const u8 *lo = g0 > alo ? g0 : alo, *hi = g1 < ahi ? g1 : ahi;
+            const u32 bytes = hi > lo ? (u32)(hi - lo) : 0u;
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar + 8 * s, bytes);
+                if (bytes) bulk_g2s(sdst + (u32)(lo - g0), lo, bytes, bar + 8 * s);
+            }
+            // the archive's unaligned ends (at most 15 bytes each, and only in the rows that contain them)
+            const u8 *e0 = g0 > glo ? g0 : glo, *e1 = g1 < ghi ? g1 : ghi;
+            for (const u8 *p = e0 + lane; p < e1; p += 32)
+                if (p < lo || p >= hi) sts8(sdst + (u32)(p - g0), *p);
+        }
+        ++fill;
+    }
+    // Makes rows [r0, r1] readable (r1 - r0 < C_ROWS, the caller checks) and asks for the row after them.
+    ZPB_DEVINL void ensure(u32 r0, u32 r1, const u8 *archive, u64 asz) {
+        u32 want = r1 + 1u < r0 + C_ROWS ? r1 + 1u : r1;     // one row of look-ahead when the ring has room for it
+        if (want >= nrows) want = nrows - 1u;                // nrows >= 1: a block has at least one byte
+        if (want < r1) want = r1;
+        while (waited < fill && waited < r0) wait_row();   // requested, then skipped by a sequence that went around the ring
+        if (fill < r0) fill = waited = r0;
+        if (fill <= want) {
+            __syncwarp();                        // every lane has finished reading the slots that are filled again
+            while (fill <= want) request_row(archive, asz);
+        }
+        while (waited <= r1) wait_row();
+        __syncwarp();                            // edge bytes written by other lanes
+    }
+    // Makes block positions [s_lo, s_hi) readable through the ring; false when the span does not fit
+    // (the caller then reads global memory for this step).  Warp-uniform arguments and result.
+    ZPB_DEVINL bool prepare(u32 s_lo, u32 s_hi, const u8 *archive, u64 asz) {
+        const u32 r0 = (s_lo + skew) >> C_ROWSH;
+        const u32 r1 = s_hi > s_lo ? (s_hi + skew - 1u) >> C_ROWSH : r0;
+        if (r1 - r0 >= C_ROWS) return false;
+        if (r1 >= waited) ensure(r0, r1, archive, asz);   // else: requested a step ago, waited for since
+        return true;
+    }
+};
+
+
+struct CompRing {     // byte reader over the staging ring
+    u32 rb, skew;
+    ZPB_DEVINL u32 operator()(u32 p) const { return lds8(rb + ((p + skew) & CR_MASK)); }
+};
+struct CompGlobal {   // byte reader over global memory (steps whose span does not fit the ring)
+    const u8 *__restrict__ s;
+    ZPB_DEVINL u32 operator()(u32 p) const { return s[p]; }
+};
+// One sequence's control bytes (lz4.c:1797-1822, 1845-1860; K1 has validated them): literal length and
+// start, match offset and length (0 for the block's last sequence).
+template <class R>
+ZPB_DEVINL void fast_decode_seq(const R rd, u32 tok, u32 bsz, u32 &lit, u32 &lsrc, u32 &off, u32 &ml) {
+    const u32 t = rd(tok);
     u32 p = tok + 1;
     lit = t >> 4;
-    if (lit == 15) { u32 bb; do { bb = s[p++]; lit += bb; } while (bb == 255); }
+    if (lit == 15) { u32 bb; do { bb = rd(p++); lit += bb; } while (bb == 255); }
     lsrc = p;
     p += lit;
-    off = 0; ml = 0;
     if (p < bsz) {
-        off = s[p] | ((u32)s[p + 1] << 8);
+        off = rd(p) | (rd(p + 1) << 8);
         p += 2;
         ml = t & 15;
-        if (ml == 15) { u32 bb; do { bb = s[p++]; ml += bb; } while (bb == 255); }
+        if (ml == 15) { u32 bb; do { bb = rd(p++); ml += bb; } while (bb == 255); }
         ml += 4;
     }
 }
 
-// The execute kernel's body; instantiated twice below, for 3 and for 4 resident CTAs per SM (80 / 64 registers).
+// unaligned 16-byte global load assembled from 4-byte-aligned words
+ZPB_DEVINL uint4 ldg128_unaligned(const u8 *p) {
+    const u32 *s = reinterpret_cast<const u32 *>((uintptr_t)p & ~(uintptr_t)3);
+    u32 sh = ((u32)(uintptr_t)p & 3u) * 8u;
+    u32 w0 = s[0], w1 = s[1], w2 = s[2], w3 = s[3];
+    if (sh == 0) return make_uint4(w0, w1, w2, w3);
+    u32 w4 = s[4];
+    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                      __funnelshift_r(w3, w4, sh));
+}
+
+#define FAST_BYTE4(LD, ST, n, i)                                                        \
+    {                                                                                   \
+        u32 v0_ = 0, v1_ = 0, v2_ = 0, v3_ = 0;                                                       \
+        const bool p0_ = (i) + 0 < (n), p1_ = (i) + 1 < (n), p2_ = (i) + 2 < (n), p3_ = (i) + 3 < (n); \
+        if (p0_) v0_ = LD(0); if (p1_) v1_ = LD(1); if (p2_) v2_ = LD(2); if (p3_) v3_ = LD(3);       \
+        if (p0_) ST(0, v0_); if (p1_) ST(1, v1_); if (p2_) ST(2, v2_); if (p3_) ST(3, v3_);           \
+    }
+
+#ifndef FAST_EXEC_CTAS
+#define FAST_EXEC_CTAS 3
+#endif
+// resident CTAs per SM the kernel is compiled for (registers) and launched with
+
 ZPB_DEVINL void
 lz4_fast_exec_body(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_entry *__restrict__ entries,
                    const u32 *__restrict__ order, u32 n, u32 *counter, const FastEntry *__restrict__ fe,
@@ -814,15 +840,13 @@ lz4_fast_exec_body(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_e
     ZPB_DYN_SMEM(k2_smem);
     if (n_ptr) n = *n_ptr;   // the late pass over the deferred list: its length was only known on the device
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u32 sbase = (smem_window(k2_smem) + 4095u) & ~4095u;
     FastExec x;
     x.lane = lane;
-    x.rb = sbase + warp * X_RING;
-    x.glo = archive;
+    x.rb = smem_window(k2_smem) + 16u + warp * FAST_WARP_SMEM;   // 16 B of slack in front, 32 behind (lane_copy reads whole words)
+    x.scr_s = x.rb + FAST_RING + lane * FAST_SCR;
     const u8 *arch_end = archive + asz;
     XStage cs;
-    cs.init(archive, asz, sbase + FAST_EXEC_WARPS * X_RING + warp * C_RING,
-            sbase + FAST_EXEC_WARPS * (X_RING + C_RING) + warp * (8u * C_ROWS), lane);
+    cs.init(x.rb + FAST_RING + 32u * FAST_SCR, smem_window(k2_smem) + FAST_EXEC_WARPS * FAST_WARP_SMEM + 48u + warp * (8u * C_ROWS), (u32)lane);
 
     for (;;) {
         u32 wslot = 0;
@@ -891,7 +915,7 @@ lz4_fast_exec_body(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_e
             if (__ldcg(&pb->flags) & FB_STORED) {
                 // ---- stored block / NONE entry (lz4frame.c:1534-1572, zpack_read.c:352-368)
                 u32 len = __ldcg(&pb->bsz);
-                if (x.done == x.flushed && (x.done & 1023u) == 0 && (src >= archive + 4 || ((uintptr_t)src & 3u) == 0)) {
+                if (x.done == x.flushed && (x.done & 1023u) == 0) {
                     // direct: HBM -> registers -> XXH3 + HBM, no ring
                     while (len >= 1024 && (x.flushed >> 10) < x.full_blocks && src + 1024 + 16 <= arch_end) {
                         int j = lane & 3;
@@ -919,8 +943,7 @@ lz4_fast_exec_body(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_e
             const u32 obase = x.done;
             const u32 bsz = __ldcg(&pb->bsz);
             const u32 nseq = __ldcg(&pb->nseq);
-            const u32 bout = __ldcg(&pb->out_size);
-            cs.open(src, bsz);
+            cs.open(src, bsz, archive, asz);
             // two steps of descriptors are kept in flight; the compressed bytes come through the staging ring
             u32 d0 = (u32)lane < nseq ? ldcg32(dp + lane) : 0u;
             u32 d1 = 32u + lane < nseq ? ldcg32(dp + 32 + lane) : 0u;
@@ -929,147 +952,177 @@ lz4_fast_exec_body(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_e
                 const u32 d = d0;
                 d0 = d1;
                 d1 = s0i + 64 + lane < nseq ? ldcg32(dp + s0i + 64 + lane) : 0u;
-                // where this sequence ends = where the next one starts (the block's end for the last one)
-                u32 dn = __shfl_down_sync(0xffffffffu, d, 1);
-                const u32 dn0 = __shfl_sync(0xffffffffu, d0, 0);
-                if (lane == 31) dn = dn0;
-                const bool last = s0i + lane + 1 == nseq;
-                const u32 tok = d & 0xFFFFu;
-                const u32 tokn = last ? bsz : dn & 0xFFFFu;
-                const u32 o = obase + (d >> 16);
-                const u32 sz = have ? (last ? bout : dn >> 16) - (d >> 16) : 0u;   // literal + match bytes
-
+                // compressed bytes this step reads: from its first token to the next step's first token
+                const u32 s_lo = __shfl_sync(0xffffffffu, d & 0xFFFFu, 0);
+                const u32 s_nx = __shfl_sync(0xffffffffu, d0 & 0xFFFFu, 0);
+                const bool in_ring = cs.prepare(s_lo, s0i + 32 < nseq ? s_nx : bsz, archive, asz);   // warp-uniform
+                u32 lit = 0, lsrc = 0, off = 0, ml = 0, o = 0;
+                if (have) {
+                    o = obase + (d >> 16);
+                    if (in_ring) fast_decode_seq(CompRing{cs.cb, cs.skew}, d & 0xFFFFu, bsz, lit, lsrc, off, ml);
+                    else fast_decode_seq(CompGlobal{src}, d & 0xFFFFu, bsz, lit, lsrc, off, ml);
+                }
+                const u32 sz = lit + ml;
+                const u32 mo = o + lit, msrc = mo - off;
+                const u8 *__restrict__ sp = src + lsrc;
+                // matches whose whole source is already in HBM: fetch it now, asynchronously, into this lane's
+                // scratch (16-byte pieces straight from L2; up to 5 cover any alignment of <= 64 bytes)
+                const u32 abase = msrc & ~15u;
+                const bool staged = have && ml > 0 && ml <= FAST_ST && msrc + ml <= x.flushed;
+                if (staged) {
+                    const u32 np = ((msrc - abase) + ml + 15u) >> 4;
+                    const u8 *g = x.gout + abase;
+                    cp_async_pieces_cg(np, x.scr_s, g);
+                }
+                else if (have && ml > 0 && msrc < x.flushed) {
+                    // longer match reaching back into flushed output: pull its lines towards L1 now, the
+                    // warp-wide copy that needs them runs later in this step
+                    u32 pe = msrc + ml < x.flushed ? msrc + ml : x.flushed;
+                    if (pe > msrc + 512) pe = msrc + 512;
+                    for (u32 a = msrc & ~127u; a < pe; a += 128) prefetch_l1(x.gout + a);
+                }
+                cp_async_commit();
+                // ---- same-step dependencies.  A match whose source lies inside the output of an earlier
+                // match of this step would have to wait for it; instead, when the source range is wholly inside
+                // that match (the usual case: repeated words, records), it is redirected through the parent's
+                // offset (out[x] = out[x - off_k] holds for every x of the parent's match), parents' shifts are
+                // composed by pointer jumping, and the match reads bytes that are already final.
+                u32 shift = 0, dstate = DS_FINAL;
+                {
+                    const u32 o_first = __shfl_sync(0xffffffffu, o, 0);
+                    const bool has_mm = have && ml > 0;
+                    const u32 send_ = msrc + ml < mo ? msrc + ml : mo;
+                    const bool inside = has_mm && send_ > o_first && msrc < o;
+                    if (__any_sync(0xffffffffu, inside)) {
+                        const u32 okey = have ? o : 0xFFFFFFFFu;
+                        u32 k = 0;   // largest lane whose sequence starts at or below msrc
+#pragma unroll
+                        for (u32 st = 16; st; st >>= 1) {
+                            const u32 ot = __shfl_sync(0xffffffffu, okey, k + st);
+                            if (ot <= msrc) k += st;
+                        }
+                        const u32 mo_k = __shfl_sync(0xffffffffu, mo, k), e_k = __shfl_sync(0xffffffffu, o + sz, k),
+                                  off_k = __shfl_sync(0xffffffffu, off, k);
+                        u32 parent = 0;
+                        if (inside) {
+                            if (msrc < o_first) dstate = DS_HARD;                 // straddles the step start
+                            else if (send_ <= mo_k) dstate = DS_FINAL;           // inside lane k's literals
+                            else if (msrc >= mo_k && send_ <= e_k && off_k >= e_k - mo_k && off >= ml) {
+                                dstate = DS_CHILD; parent = k; shift = off_k;
+                            } else dstate = DS_HARD;
+                        }
+                        while (__any_sync(0xffffffffu, dstate == DS_CHILD)) {
+                            const u32 pst = __shfl_sync(0xffffffffu, dstate, parent),
+                                      psh = __shfl_sync(0xffffffffu, shift, parent),
+                                      pp = __shfl_sync(0xffffffffu, parent, parent);
+                            if (dstate == DS_CHILD) {
+                                if (pst == DS_HARD) { dstate = DS_HARD; shift = 0; }
+                                else { shift += psh; parent = pp; if (pst == DS_FINAL) dstate = DS_FINAL; }
+                            }
+                        }
+                    }
+                }
+                bool parked = false;
                 u32 todo = __ballot_sync(0xffffffffu, have);
                 while (todo) {
                     const int first = __ffs(todo) - 1;
-                    // ---- the run of sequences this round executes: their compressed bytes fit the staging ring
-                    // (counted from the row of the first one) and their output fits the output ring
-                    const u32 c_first = __shfl_sync(0xffffffffu, tok, first) + cs.skew;
-                    const u32 r0 = c_first >> C_ROWSH;
-                    const bool fits = ((todo >> lane) & 1u) && tokn + cs.skew <= ((r0 + C_ROWS) << C_ROWSH) &&
-                                      o + sz + X_MARGIN <= x.flushed + X_RING;
-                    const u32 seg = __ballot_sync(0xffffffffu, fits);   // both bounds are monotone: a prefix of todo
+                    const bool fits = ((todo >> lane) & 1u) && (o + sz <= x.flushed + FAST_RING);
+                    const u32 seg = __ballot_sync(0xffffffffu, fits);   // o + sz is monotone: a prefix of todo
                     if (!((seg >> first) & 1u)) {
-                        // ---- one sequence larger than a ring: streamed by the whole warp, control bytes from global memory
-                        const u32 T = __shfl_sync(0xffffffffu, tok, first);
-                        u32 L, S, O, ML;
-                        fast_decode_seq_global(src, T, bsz, L, S, O, ML);
+                        // ---- one sequence larger than the ring: streamed, whole warp
+                        u32 L = __shfl_sync(0xffffffffu, lit, first), S = __shfl_sync(0xffffffffu, lsrc, first);
+                        u32 O = __shfl_sync(0xffffffffu, off, first), ML = __shfl_sync(0xffffffffu, ml, first);
                         x.stream_lit(src + S, L);
                         if (ML) x.stream_match(O, ML);
                         todo &= ~(1u << first);
                         continue;
                     }
+                    // ---- a run of sequences that fits the ring: literals first (they depend on nothing) ...
                     const bool in = (seg >> lane) & 1u;
                     const int last_lane = 31 - __clz(seg);
-                    const u32 c_end = __shfl_sync(0xffffffffu, tokn, last_lane) + cs.skew;
                     const u32 seg_end = __shfl_sync(0xffffffffu, o + sz, last_lane);
-                    cs.ensure(r0, (c_end - 1u) >> C_ROWSH);
-
-                    // ---- sequence fields (lz4.c:1797-1822, 1845-1860; K1 has validated the bytes): the token gives one
-                    // of the two lengths outright, the other is what is left of the sequence's output
-                    u32 lit = 0, lsrc = 0, off = 0, ml = 0;
-                    if (in) {
-                        const u32 t = cs.rd(tok);
-                        const u32 l0 = t >> 4, m0 = t & 15u;
-                        if (last) { lit = sz; ml = 0; }
-                        else if (l0 < 15u) { lit = l0; ml = sz - lit; }
-                        else if (m0 < 15u) { ml = m0 + 4u; lit = sz - ml; }
-                        else {   // both lengths extended: walk the literal-length bytes
-                            u32 p = tok + 1, bb;
-                            lit = 15u;
-                            do { bb = cs.rd(p++); lit += bb; } while (bb == 255u);
-                            ml = sz - lit;
-                        }
-                        lsrc = tok + 1u + (l0 == 15u ? 1u + (lit - 15u) / 255u : 0u);
-                        if (ml) off = cs.rd(lsrc + lit) | (cs.rd(lsrc + lit + 1u) << 8);
-                    }
-                    const u32 mo = o + lit, msrc = mo - off;
                     const u32 lo = x.ring_lo(seg_end);
-
-                    // ---- same-step dependencies.  A match whose source lies inside the output of an earlier
-                    // match of this step would have to wait for it; instead, when the source range is wholly inside
-                    // that match (the usual case: repeated words, records), it is redirected through the parent's
-                    // offset (out[x] = out[x - off_k] holds for every x of the parent's match), parents' shifts are
-                    // composed by pointer jumping, and the match reads bytes that are already final.
-                    u32 shift = 0, dstate = DS_FINAL;
                     {
-                        const u32 o_first = __shfl_sync(0xffffffffu, o, first);
-                        const bool has_mm = in && ml > 0;
-                        const u32 send_ = msrc + ml < mo ? msrc + ml : mo;
-                        const bool inside = has_mm && send_ > o_first && msrc < o;
-                        if (__any_sync(0xffffffffu, inside)) {
-                            // keys are monotone over the lanes: 0 for sequences of earlier rounds, o inside the run, +inf behind it
-                            const u32 okey = in ? o : (lane < first ? 0u : 0xFFFFFFFFu);
-                            u32 k = 0;   // largest lane whose key is at or below msrc
-#pragma unroll
-                            for (u32 st = 16; st; st >>= 1) {
-                                const u32 ot = __shfl_sync(0xffffffffu, okey, k + st);
-                                if (ot <= msrc) k += st;
+                        const u32 da = x.ra(o);
+                        const u32 cq = (lsrc + cs.skew) & CR_MASK;    // literal source in the staging ring
+                        const bool lane_lit = in && (o & FAST_RMASK) + lit <= FAST_RING &&
+                                              (in_ring ? lit <= FAST_LTR && cq + lit <= CR_SIZE : lit <= FAST_LT);
+                        const u32 mylit = lane_lit ? lit : 0u;
+                        if (in_ring) {
+                            lane_copy(cs.cb + cq, da, mylit);
+                        } else {
+                            const u32 maxlit = __reduce_max_sync(0xffffffffu, mylit);
+#define STL(u, v) sts8(dai + u, v)
+#define LDL(u) ((u32)spi[u])
+                            for (u32 i = 0; i < maxlit; i += 4) {
+                                const u8 *spi = sp + i;
+                                const u32 dai = da + i;
+                                FAST_BYTE4(LDL, STL, mylit, i)
                             }
-                            const u32 mo_k = __shfl_sync(0xffffffffu, mo, k), e_k = __shfl_sync(0xffffffffu, o + sz, k),
-                                      off_k = __shfl_sync(0xffffffffu, off, k);
-                            u32 parent = 0;
-                            if (inside) {
-                                if (msrc < o_first) dstate = DS_HARD;                 // straddles the step start
-                                else if (send_ <= mo_k) dstate = DS_FINAL;           // inside lane k's literals
-                                else if (msrc >= mo_k && send_ <= e_k && off_k >= e_k - mo_k && off >= ml) {
-                                    dstate = DS_CHILD; parent = k; shift = off_k;
-                                } else dstate = DS_HARD;
-                            }
-                            while (__any_sync(0xffffffffu, dstate == DS_CHILD)) {
-                                const u32 pst = __shfl_sync(0xffffffffu, dstate, parent),
-                                          psh = __shfl_sync(0xffffffffu, shift, parent),
-                                          pp = __shfl_sync(0xffffffffu, parent, parent);
-                                if (dstate == DS_CHILD) {
-                                    if (pst == DS_HARD) { dstate = DS_HARD; shift = 0; }
-                                    else { shift += psh; parent = pp; if (pst == DS_FINAL) dstate = DS_FINAL; }
-                                }
-                            }
+#undef LDL
+#undef STL
                         }
-                    }
-
-                    // ---- literals first (they depend on nothing): one lane per run out of the staging ring, the
-                    // few long ones (or ones that wrap a ring) by the whole warp
-                    {
-                        const u32 sa = cs.addr(lsrc);
-                        const bool lane_lit = in && lit > 0 && lit <= FAST_LTR && (o & X_RMASK) + lit <= X_RING &&
-                                              (sa & C_MASK) + lit + LANE_COPY_SLACK <= C_RING;
-                        lane_copy(shared_to_generic(sa), x.ra(o), lane_lit ? lit : 0u);
                         u32 cm = __ballot_sync(0xffffffffu, in && lit > 0 && !lane_lit);
                         while (cm) {
-                            const int r = __ffs(cm) - 1;
+                            int r = __ffs(cm) - 1;
                             cm &= cm - 1;
-                            const u32 O = __shfl_sync(0xffffffffu, o, r), S = __shfl_sync(0xffffffffu, lsrc, r),
-                                      L = __shfl_sync(0xffffffffu, lit, r);
-                            x.coop_lit_ring(O, cs, S, L);
+                            u32 O = __shfl_sync(0xffffffffu, o, r), S = __shfl_sync(0xffffffffu, lsrc, r),
+                                L = __shfl_sync(0xffffffffu, lit, r);
+                            if (in_ring) {
+                                for (u32 i = lane; i < L; i += 32) sts8(x.ra(O + i), lds8(cs.cb + ((S + cs.skew + i) & CR_MASK)));
+                            } else {
+                                x.coop_lit(O, src + S, L);
+                            }
                         }
                     }
-                    // ---- then matches.  Everything whose source bytes are final (before this step, in literal
+                    if (!parked) {   // far-match sources requested at decode time have landed in the scratch
+                        cp_async_wait_all();
+                        parked = true;
+                    }
+                    // ... then matches.  Everything whose source bytes are final (before this step, in literal
                     // regions, or redirected there by the dependency pass above) goes first: one lane per short
                     // match, warp-wide for the longer ones, in any order.  What is left (DS_HARD: a source that
                     // straddles pending matches) runs warp-wide in lane order.
                     const bool has_m = in && ml > 0;
-                    const u32 pend = __ballot_sync(0xffffffffu, has_m);
+                    const u32 esrc = msrc - shift;
+                    const bool near_lin = esrc >= lo && (esrc & FAST_RMASK) + ml <= FAST_RING;
+                    const bool from_scr = staged && shift == 0;
+                    const u32 offe = off + shift;
+                    const bool lane_ok = has_m && dstate == DS_FINAL && ml <= FAST_MT && offe >= ml &&
+                                         (mo & FAST_RMASK) + ml <= FAST_RING && (from_scr || near_lin);
+                    const u32 sa = from_scr ? x.scr_s + (msrc - abase) : x.ra(esrc);
+                    const u32 dm = x.ra(mo);
                     __syncwarp();
+                    const u32 pend = __ballot_sync(0xffffffffu, has_m);
                     if (pend) {
-                        const u32 esrc = msrc - shift;
-                        const u32 offe = off + shift;
-                        const bool src_ring = esrc >= lo && (esrc & X_RMASK) + ml + LANE_COPY_SLACK <= X_RING;
-                        const bool src_hbm = esrc + ml + LANE_COPY_SLACK <= x.flushed;   // HBM holds everything below `flushed`
-                        const bool lane_ok = has_m && dstate == DS_FINAL && ml <= FAST_MT && offe >= ml &&
-                                             (mo & X_RMASK) + ml <= X_RING && (src_ring || src_hbm);
-                        const u64 sg = src_ring ? shared_to_generic(x.ra(esrc)) : global_to_generic(x.gout + esrc);
-                        lane_copy(sg, x.ra(mo), lane_ok ? ml : 0u);
                         const u32 elmask = __ballot_sync(0xffffffffu, lane_ok);
+                        if (elmask) lane_copy(sa, dm, lane_ok ? ml : 0u);
                         u32 rest = pend & ~elmask;
-                        if (rest) {
-                            const u32 hardmask = __ballot_sync(0xffffffffu, has_m && dstate == DS_HARD);
-                            while (rest) {
-                                const int r = __ffs(rest) - 1;
-                                rest &= rest - 1;
-                                if ((hardmask >> r) & 1u) __syncwarp();   // needs what earlier lanes have just written
-                                const u32 MO = __shfl_sync(0xffffffffu, mo, r), OF = __shfl_sync(0xffffffffu, offe, r),
-                                          ML = __shfl_sync(0xffffffffu, ml, r);
+                        const u32 hardmask = __ballot_sync(0xffffffffu, has_m && dstate == DS_HARD);
+                        const u32 scr_src = from_scr ? sa : 0u;   // linear copy of the source in the scratch
+                        while (rest) {
+                            int r = __ffs(rest) - 1;
+                            rest &= rest - 1;
+                            if ((hardmask >> r) & 1u) __syncwarp();   // needs what earlier lanes have just written
+                            const u32 MO = __shfl_sync(0xffffffffu, mo, r), OF = __shfl_sync(0xffffffffu, offe, r),
+                                      ML = __shfl_sync(0xffffffffu, ml, r), SS = __shfl_sync(0xffffffffu, scr_src, r);
+                            if (SS && OF >= ML) {
+                                // far source, fetched at decode time (ML <= FAST_ST = 64)
+                                const u32 dd = MO + lane;
+                                u32 v0 = 0, v1 = 0;
+                                if ((u32)lane < ML) v0 = lds8(SS + lane);
+                                if ((u32)lane + 32 < ML) v1 = lds8(SS + lane + 32);
+                                if ((u32)lane < ML) sts8(x.ra(dd), v0);
+                                if ((u32)lane + 32 < ML) sts8(x.ra(dd + 32), v1);
+                            } else if (ML <= 64 && OF >= ML && MO - OF >= lo) {
+                                // the common case: short, source still in the ring, no self-overlap
+                                const u32 a = MO - OF + lane, dd = MO + lane;
+                                u32 v0 = 0, v1 = 0;
+                                if ((u32)lane < ML) v0 = lds8(x.ra(a));
+                                if ((u32)lane + 32 < ML) v1 = lds8(x.ra(a + 32));
+                                if ((u32)lane < ML) sts8(x.ra(dd), v0);
+                                if ((u32)lane + 32 < ML) sts8(x.ra(dd + 32), v1);
+                            } else {
                                 x.coop_match(MO, OF, ML, lo);
                             }
                         }
@@ -1135,15 +1188,11 @@ lz4_fast_exec_body(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_e
     cs.drain();   // no bulk copy may outlive the CTA's shared memory
 }
 
-#ifndef FAST_EXEC_CTAS
-#define FAST_EXEC_CTAS 3
-#endif
 #define FAST_EXEC_ARGS const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_entry *__restrict__ entries,            \
                        const u32 *__restrict__ order, u32 n, u32 *counter, const FastEntry *__restrict__ fe,               \
                        const FastBlock *__restrict__ fb, const u32 *__restrict__ desc, u32 *counters, u32 *general_list,    \
                        int *status, u64 *digest, u64 *partials, u32 *defer_list, u32 *defer_cnt, const u32 *n_ptr
 #define FAST_EXEC_PASS archive, asz, out, entries, order, n, counter, fe, fb, desc, counters, general_list, status, digest,  \
                        partials, defer_list, defer_cnt, n_ptr
-__global__ void __launch_bounds__(32 * FAST_EXEC_WARPS, 3) lz4_fast_exec_kernel(FAST_EXEC_ARGS) { lz4_fast_exec_body(FAST_EXEC_PASS); }
-__global__ void __launch_bounds__(32 * FAST_EXEC_WARPS, 4) lz4_fast_exec_kernel4(FAST_EXEC_ARGS) { lz4_fast_exec_body(FAST_EXEC_PASS); }
+__global__ void __launch_bounds__(32 * FAST_EXEC_WARPS, FAST_EXEC_CTAS) lz4_fast_exec_kernel(FAST_EXEC_ARGS) { lz4_fast_exec_body(FAST_EXEC_PASS); }
 typedef void (*fast_exec_fn)(FAST_EXEC_ARGS);

@@ -160,8 +160,6 @@ extern "C" zpb_ctx *zpb_create(int device) {
     if (cudaFuncSetAttribute(lz4_fast_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(K1_THREADS * K1_ROW)) != cudaSuccess ||
         cudaFuncSetAttribute(lz4_fast_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(FAST_EXEC_SMEM)) != cudaSuccess ||
-        cudaFuncSetAttribute(lz4_fast_exec_kernel4, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(FAST_EXEC_SMEM)) != cudaSuccess) {
         g_last_error = std::string("kernel attribute setup failed: ") + cudaGetErrorString(cudaGetLastError());
         delete ctx; return nullptr;
@@ -416,9 +414,8 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
         // never wait: an entry whose blocks are not parsed yet is put aside), the third CTA per SM once the parse kernel
         // has finished, and a last pass over the entries that were put aside.
         const bool overlap = ctx->overlap != 0;
-        // resident CTAs per SM of the execute kernel: 3 (80 registers) or 4 (64 registers) — two builds of one body
-        const int k2_ctas = [] { const char *e = getenv("ZPB_EXEC_CTAS"); int v = e ? atoi(e) : 0; return v > 0 && v <= 4 ? v : FAST_EXEC_CTAS; }();
-        const fast_exec_fn exec_kernel = k2_ctas >= 4 ? lz4_fast_exec_kernel4 : lz4_fast_exec_kernel;
+        const int k2_ctas = [] { const char *e = getenv("ZPB_EXEC_CTAS"); int v = e ? atoi(e) : 0; return v > 0 && v <= FAST_EXEC_CTAS ? v : FAST_EXEC_CTAS; }();
+        const fast_exec_fn exec_kernel = lz4_fast_exec_kernel;
         const int k1_ctas = ctx->ctas_per_sm > 0 ? ctx->ctas_per_sm : 3;
         cudaStream_t sp = overlap ? ctx->stream_p : s;
         if (overlap) {

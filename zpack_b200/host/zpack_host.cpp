@@ -15,6 +15,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <stdexcept>
 #include <vector>
 
 #include "../../include/zpack_b200.h"
@@ -211,6 +212,7 @@ int zpack_read_file_entries_memory(const zpack_u8 *b, zpack_file_entry **entries
 int zpack_read_cdr_memory(const zpack_u8 *b, size_t size_left, zpack_file_entry **entries, zpack_u64 *count, zpack_u64 *total_cs,
                           zpack_u64 *total_us) {
     zpack_u64 n = 0, block = 0;
+    if (size_left < ZPK_CDR_HEADER_BYTES) return ZPACK_ERROR_BLOCK_SIZE_INVALID;   // the header itself must be inside the buffer
     int rc = zpack_read_cdr_header_memory(b, &n, &block);
     if (rc) return rc;
     if (block > size_left || ZPK_CDR_HEADER_BYTES > size_left - block) return ZPACK_ERROR_BLOCK_SIZE_INVALID;
@@ -226,9 +228,14 @@ int zpack_read_cdr(FILE *fp, zpack_u64 cdr_offset, zpack_file_entry **entries, z
     int rc = zpack_read_cdr_header_memory(hdr, &n, &block);
     if (rc) return rc;
     if (n == 0) return ZPACK_OK;
+    // `block` is an untrusted 64-bit field: it cannot exceed what the file holds behind the CDR header
+    if (fseeko(fp, 0, SEEK_END) != 0) return ZPACK_ERROR_SEEK_FAILED;
+    const zpack_u64 fsize = (zpack_u64)ftello(fp);
+    if (cdr_offset > fsize || fsize - cdr_offset < ZPK_CDR_HEADER_BYTES || block > fsize - cdr_offset - ZPK_CDR_HEADER_BYTES)
+        return ZPACK_ERROR_BLOCK_SIZE_INVALID;
     std::vector<zpack_u8> body;
-    try { body.resize((size_t)block); } catch (const std::bad_alloc &) { return ZPACK_ERROR_MALLOC_FAILED; }
-    if (block && fread(body.data(), 1, (size_t)block, fp) != block) return ZPACK_ERROR_READ_FAILED;
+    try { body.resize((size_t)block); } catch (const std::exception &) { return ZPACK_ERROR_MALLOC_FAILED; }
+    if (!read_at(fp, cdr_offset + ZPK_CDR_HEADER_BYTES, body.data(), (size_t)block, &err)) return err;
     return zpack_read_file_entries_memory(body.data(), entries, n, block, count, total_cs, total_us);
 }
 
@@ -276,11 +283,12 @@ int zpack_read_raw_file(zpack_reader *r, zpack_file_entry *e, zpack_u8 *buffer, 
 int zpack_read_file(zpack_reader *r, zpack_file_entry *e, zpack_u8 *buffer, size_t max_size, void *) {
     if (e->comp_size == 0) return ZPACK_OK;                                          // :328
     if (max_size < e->uncomp_size) return ZPACK_ERROR_BUFFER_TOO_SMALL;              // :329
-    if (e->offset + e->comp_size >= r->file_size) return ZPACK_ERROR_FILE_OFFSET_INVALID;  // :331 (strict)
+    // :331 (strict: offset + comp_size < file_size), written so that it cannot wrap
+    if (e->offset >= r->file_size || e->comp_size >= r->file_size - e->offset) return ZPACK_ERROR_FILE_OFFSET_INVALID;
     if (!known_method(e->comp_method)) return ZPACK_ERROR_COMP_METHOD_INVALID;       // :459-461
     if (r->file) {                                                                   // :336-344
         std::vector<zpack_u8> comp;
-        try { comp.resize((size_t)e->comp_size); } catch (const std::bad_alloc &) { return ZPACK_ERROR_MALLOC_FAILED; }
+        try { comp.resize((size_t)e->comp_size); } catch (const std::exception &) { return ZPACK_ERROR_MALLOC_FAILED; }
         int rc = zpack_read_raw_file(r, e, comp.data(), comp.size());
         if (rc) return rc;
         return gpu_unpack_one(comp.data(), e->comp_size, buffer, max_size, e, &r->last_return);
@@ -299,7 +307,7 @@ int zpack_read_files(zpack_reader *r, zpack_file_entry *entries, zpack_u64 n, zp
         const zpack_file_entry &e = entries[i];
         d[i].src_off = e.offset; d[i].comp_size = e.comp_size; d[i].dst_off = dst_off[i]; d[i].dst_cap = dst_cap[i];
         d[i].uncomp_size = e.uncomp_size; d[i].hash = e.hash; d[i].method = e.comp_method;
-        if (e.comp_size && e.offset + e.comp_size >= r->file_size) d[i].src_off = ~0ull;   // -> FILE_OFFSET_INVALID
+        if (e.comp_size && (e.offset >= r->file_size || e.comp_size >= r->file_size - e.offset)) d[i].src_off = ~0ull;   // -> FILE_OFFSET_INVALID
     }
     std::lock_guard<std::mutex> lk(g_gpu_lock);
     zpb_ctx *g = gpu();
@@ -348,7 +356,7 @@ int zpack_read_file_stream(zpack_reader *r, zpack_file_entry *e, zpack_stream *s
     if (!known_method(e->comp_method)) return ZPACK_ERROR_COMP_METHOD_INVALID;
     if (s->total_in == 0) {   // a new entry starts (:524-525 resets the hash state here)
         st->loaded = false; st->pos = 0; st->verdict = ZPACK_OK;
-        try { st->data.assign((size_t)e->uncomp_size, 0); } catch (const std::bad_alloc &) { return ZPACK_ERROR_MALLOC_FAILED; }
+        try { st->data.assign((size_t)e->uncomp_size, 0); } catch (const std::exception &) { return ZPACK_ERROR_MALLOC_FAILED; }
         int rc = zpack_read_file(r, e, st->data.data(), st->data.size(), nullptr);
         if (rc && rc != ZPACK_ERROR_FILE_HASH_MISMATCH) return rc;
         st->verdict = rc;
@@ -465,7 +473,7 @@ int zpack_write_files(zpack_writer *w, zpack_file *files, zpack_u64 file_count) 
         std::vector<uint64_t> csz(n), dig(n);
         std::vector<int32_t> st(n);
         try { in.resize((size_t)in_bytes + 16); out.resize((size_t)out_bytes + 16); }
-        catch (const std::bad_alloc &) { return ZPACK_ERROR_MALLOC_FAILED; }
+        catch (const std::exception &) { return ZPACK_ERROR_MALLOC_FAILED; }
         for (size_t k = 0; k < n; ++k)
             if (files[i + k].size) memcpy(in.data() + d[k].src_off, files[i + k].buffer, (size_t)files[i + k].size);
         {
@@ -502,7 +510,7 @@ int zpack_write_files_from_archive(zpack_writer *w, zpack_reader *r, zpack_file_
         const zpack_file_entry &s = entries[i];
         const zpack_u8 *src;
         if (r->file) {
-            try { if (tmp.size() < s.comp_size) tmp.resize((size_t)s.comp_size); } catch (const std::bad_alloc &) { return ZPACK_ERROR_MALLOC_FAILED; }
+            try { if (tmp.size() < s.comp_size) tmp.resize((size_t)s.comp_size); } catch (const std::exception &) { return ZPACK_ERROR_MALLOC_FAILED; }
             int rc = zpack_read_raw_file(r, entries + i, tmp.data(), tmp.size());
             if (rc) return rc;
             src = tmp.data();
@@ -535,7 +543,7 @@ int zpack_write_file_stream(zpack_writer *w, zpack_compress_options *opt, zpack_
     if (!st) return ZPACK_ERROR_STREAM_INVALID;
     if (s->total_in == 0) st->data.clear();
     try { st->data.insert(st->data.end(), s->next_in, s->next_in + s->avail_in); }
-    catch (const std::bad_alloc &) { return ZPACK_ERROR_MALLOC_FAILED; }
+    catch (const std::exception &) { return ZPACK_ERROR_MALLOC_FAILED; }
     s->next_in += s->avail_in;
     s->total_in += s->avail_in;
     s->avail_in = 0;
@@ -568,7 +576,7 @@ int zpack_write_cdr_ex(zpack_writer *w, zpack_file_entry *entries, zpack_u64 fil
         block += l;
     }
     std::vector<zpack_u8> b;
-    try { b.resize((size_t)(ZPK_CDR_HEADER_BYTES + block)); } catch (const std::bad_alloc &) { return ZPACK_ERROR_MALLOC_FAILED; }
+    try { b.resize((size_t)(ZPK_CDR_HEADER_BYTES + block)); } catch (const std::exception &) { return ZPACK_ERROR_MALLOC_FAILED; }
     put32(b.data(), ZPK_SIG_CDR);
     put64(b.data() + 4, file_count);
     put64(b.data() + 12, block);
