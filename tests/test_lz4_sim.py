@@ -154,3 +154,45 @@ def test_golden_lz4_cases(sim, oracle, lz4_cases):
             assert status[i] == -1000, (names[i], status[i])   # declined, not mis-decoded
     declined = {names[i] for i in range(len(names)) if status[i] != 0}
     assert all(any(t in k for t in ("sums", "256k", "4m")) for k in declined), declined
+
+
+def test_split_parse_on_sparse_matches(sim, oracle):
+    """Blocks the four-way split parse cannot join (mostly literals, a match every few hundred bytes: a walk that starts
+    inside a literal run stays off the true chain) must be walked again unsplit and still decode."""
+    rng = np.random.default_rng(11)
+    frames, plain = [], []
+    for k in range(4):
+        base = rng.integers(0, 256, size=131072, dtype=np.uint8)
+        for _ in range(150 * (k + 1)):                       # sprinkle short repeats
+            p = int(rng.integers(100, 131072 - 40)); q = int(rng.integers(0, p - 20)); n = int(rng.integers(6, 30))
+            base[p:p + n] = base[q:q + n]
+        frames.append(oracle.lz4f_encode_port(base, 0, independent=False))
+        plain.append(base)
+    check(sim, oracle, frames, plain, seed=3)
+
+
+def test_corrupted_frames_are_declined_not_misdecoded(sim, oracle):
+    """Bit flips inside the blocks of reference-format frames: the emulation's bounds checks must stay silent (memory
+    safety of the speculative walks on garbage), and every entry must end as decoded-and-verified, hash mismatch, or
+    handed to the general decoder — never as OK with wrong bytes."""
+    rng = np.random.default_rng(5)
+    frames, plain = [], []
+    for i in range(12):
+        b = corpus.entry_bytes(1 + 2 * (i % 2), 131072)      # text and records
+        f = oracle.lz4f_encode_port(b, 0, independent=False).copy()
+        for _ in range(1 + i % 3):
+            p = int(rng.integers(11, len(f) - 4))
+            f[p] ^= 1 << int(rng.integers(0, 8))
+        frames.append(f)
+        plain.append(b)
+    hashes = [oracle.xxh3_port(b) for b in plain]
+    arch = container.assemble([f"e{i}" for i in range(len(frames))], frames, [len(b) for b in plain], hashes, [2] * len(frames))
+    e = container.parse(arch).entries()
+    out_size = int((e["dst_off"] + e["dst_cap"]).max())
+    out, status, digest, races, ngen = run(sim, arch, e, out_size, seed=9)
+    assert races == 0
+    for i, b in enumerate(plain):
+        assert status[i] in (0, 15, -1000), status[i]
+        if status[i] == 0:
+            o = int(e["dst_off"][i])
+            assert np.array_equal(out[o:o + len(b)], b)

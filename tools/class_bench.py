@@ -38,6 +38,15 @@ def build(cls, n, size, indep, method=2):
     return container.assemble([f"{i}" for i in range(n)], frames, [size] * n, hashes, [method] * n)
 
 
+def _counters(ctx):
+    import ctypes as C
+    if not hasattr(ctx.lib, "zpb_debug_counters"):
+        return None
+    a = (C.c_uint32 * 16)()
+    ctx.lib.zpb_debug_counters(C.c_void_p(ctx.h), a)
+    return {"heavy": a[8], "medium": a[9], "light": a[10], "split_retries": a[14], "general": a[1]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--entries", type=int, default=4096)
@@ -85,7 +94,8 @@ def main():
             print(json.dumps({"method": args.method, "class": names[cls], "group": g, "exec_ctas": xc, "overlap": ov, "kernel_ms": round(t, 4),
                               "uncomp_GBps": round(unc / t / 1e6, 1), "traffic_GBps": round((comp + unc) / t / 1e6, 1),
                               "ratio": round(unc / comp, 3), "entries": args.entries,
-                              "stages": {k: round(v, 4) for k, v in ctx.last_stage_ms().items()}}), flush=True)
+                              "stages": {k: round(v, 4) for k, v in ctx.last_stage_ms().items()},
+                              "counters": _counters(ctx)}), flush=True)
             if hasattr(ctx.lib, "zpb_debug_zstd_profile"):  # developer build (-DZPB_ZS_PROFILE)
                 import ctypes as C
                 a = (C.c_uint64 * 8)()

@@ -10,24 +10,18 @@
 //                                    LZ4_decompress_generic, lz4.c:1797-2151), validates them, and
 //                                    emits one 32-bit descriptor per sequence:
 //                                    token position | output position << 16 (both block-relative).
-//                                    The compressed stream is staged per lane through a 256-byte shared-memory
-//                                    ring filled by cp.async; the ring is topped up by the whole warp at once every
-//                                    K1_TOPUP sequences (one wait per top-up, on a group issued a top-up earlier),
-//                                    so an iteration of the serial walk is two dependent shared-memory reads and
-//                                    never waits on HBM.
-//   K2 exec   one warp per entry     32 sequences at a time, one per lane.  The compressed bytes arrive through a
-//                                    per-warp ring filled by 1-D bulk async copies (cp.async.bulk -> the TMA unit,
-//                                    completion on an mbarrier per 512-byte row, issued by one lane, one row ahead).
-//                                    Sequence fields come from the token byte and the neighbouring descriptors
-//                                    (literal + match length = difference of output positions), so length-extension
-//                                    bytes are not re-read.  Literals and short non-overlapping matches are copied one
-//                                    lane per sequence, word-wise (lane_copy; match sources that have left the ring
-//                                    are read from HBM/L2 by the same generic loads), long / periodic ones by the
+//                                    The compressed stream is staged per lane through shared memory
+//                                    with cp.async (LDGSTS), four 64-byte chunks ahead of the cursor,
+//                                    so the serial walk never waits on HBM.
+//   K2 exec   one warp per entry     32 sequences at a time, one per lane.  The compressed bytes come through a
+//                                    per-warp cp.async staging ring; literals and short non-overlapping matches are
+//                                    copied one lane per sequence (word-wise, lane_copy), long / periodic ones by the
 //                                    whole warp in 16-byte units (coop_match); matches that source an earlier match of
 //                                    the same step are redirected through its offset (pointer jumping) so that they
-//                                    read final bytes.  Output is assembled in a 4 KiB shared-memory ring per warp;
-//                                    each finished 1 KiB goes out as 16-byte coalesced stores and is folded into
-//                                    XXH3-64 from the same registers (the digest never re-reads HBM).
+//                                    read final bytes; far matches are fetched from flushed output with cp.async.
+//                                    Output is assembled in a 4 KiB shared-memory ring per warp; each finished 1 KiB
+//                                    goes out as 16-byte coalesced stores and is folded into XXH3-64 from the same
+//                                    registers (the digest never re-reads HBM).
 //
 // K2 does not wait for K1: K0 sorts blocks into three work lists by weight, K1 (high-priority stream) walks the heavy
 // list on its first CTAs and publishes each verdict behind a fence, K2 (three launches over one work queue, see
@@ -41,7 +35,6 @@
 #include "common.cuh"
 #include "xxh3.cuh"
 #include "lz4_decode.cuh"
-
 #include "ptx.cuh"
 
 #define FAST_RING      4096u
@@ -54,20 +47,18 @@
 #define CR_ROW         512u    // one fill: 16 bytes per lane
 #endif
 #define CR_MASK        (CR_SIZE - 1u)
-#define C_ROW          CR_ROW  // one bulk async copy (cp.async.bulk, the TMA unit) = one row of the staging ring
-#define C_ROWSH        9
-#define C_ROWS         (CR_SIZE / CR_ROW)
 #define FAST_WARP_SMEM (FAST_RING + 32u * FAST_SCR + CR_SIZE + 32u)   // + 32: lane_copy's whole-word over-reads past the staging ring stay inside the warp's own region
 #ifndef FAST_EXEC_WARPS
 #define FAST_EXEC_WARPS 8u
 #endif
-#define FAST_EXEC_SMEM (FAST_EXEC_WARPS * FAST_WARP_SMEM + 48u + FAST_EXEC_WARPS * 8u * C_ROWS)   // per CTA, plus slack at both ends; then C_ROWS mbarriers per warp
+#define FAST_EXEC_SMEM (FAST_EXEC_WARPS * FAST_WARP_SMEM + 48u)   // per CTA, plus slack at both ends
 
 #define FE_DONE    0u   // status already final (guards, unsupported method)
 #define FE_FAST    1u   // block table filled, goes through K1/K2
 #define FE_GENERAL 2u   // handed to the general kernel
 #define FE_ZSTD    3u   // handed to the zstd kernel (zstd_decode.cuh)
 
+#define FAST_DESC_PER_BLOCK 460ull
 #define K1_HEAVY   (24u << 10)   // compressed block bytes: heavy / medium / light parse work lists
 #define K1_MEDIUM  (6u << 10)
 
@@ -97,7 +88,7 @@ struct FastBlock {    // K0 -> K1 -> K2, 32 bytes
     u64 src;          // archive offset of the block payload
     u64 desc_off;     // index of its first descriptor (multiple of 4)
     u32 bsz;          // payload bytes
-    u32 flags;        // FB_* | max backward reach before the block start << 8
+    u32 flags;        // FB_*
     u32 nseq;         // K1
     u32 out_size;     // K1 (stored: = bsz)
 };
@@ -130,7 +121,7 @@ __device__ __noinline__ bool fast_scan_lz4(const u8 *src, u64 n, const zpb_entry
         if (bsz == 0 || bsz > 65536u || bsz > n - ip || nb == a.nslots) return false;
         FastBlock b;
         b.src = e.src_off + ip;
-        b.desc_off = a.desc_base + (((ip / 3) + 12ull * nb + 3ull) & ~3ull);
+        b.desc_off = a.desc_base + (((ip / 3) + FAST_DESC_PER_BLOCK * nb + 3ull) & ~3ull);
         b.bsz = bsz;
         b.flags = (bh >> 31) ? FB_STORED : 0u;
         b.nseq = 0;
@@ -221,26 +212,89 @@ lz4_fast_scan_kernel(const u8 *__restrict__ archive, u64 asz, const zpb_entry *_
     fe[idx] = f;
 }
 
-// ------------------------------------------------------------------------------------------ lane copy
-// Warp-lockstep copy inside shared memory: every lane moves its own n bytes (0 = idle) from s to d, any alignment,
-// ranges not overlapping.  Head bytes up to the destination's word boundary, then whole words assembled from two
-// aligned source words with a funnel shift, then tail bytes (ptx.cuh: copy_edges_ss / copy_words_ss).  The aligned
-// source words may contain bytes outside [s, s+n) (up to 3 before; a round reads up to 19 past its last whole word):
-// they are read, never stored — callers keep s + n + LANE_COPY_SLACK inside the region the source lives in.
-ZPB_DEVINL void lane_copy(u32 s, u32 d, u32 n) {
+// Warp-lockstep copy inside shared memory: every lane moves its own n bytes (0 = idle) from s to d, any
+// alignment, ranges not overlapping.  Head bytes up to the destination's word boundary, then whole words
+// assembled from two aligned source words with a funnel shift, then tail bytes: 4 instructions per word
+// instead of 12 per 4 bytes of a byte loop.  The source words may straddle bytes outside [s, s+n) (and the
+// last round may read up to four words past it): they are read, never stored.
+ZPB_DEVINL void lane_copy(u32 s, u32 d, u32 n) {   // idle lanes: n = 0 (s, d are not dereferenced)
     u32 h = (0u - d) & 3u;
     h = h < n ? h : n;
     const u32 n2 = n - h;
     const u32 nw = n2 >> 2, t = n2 & 3u;
     const u32 s2 = s + h, d2 = d + h;            // d2 is word aligned whenever nw > 0
-    copy_edges_ss(h, t, s, d, s2 + 4 * nw, d2 + 4 * nw);
+    const u32 ts = s2 + 4 * nw, td = d2 + 4 * nw;
+    // edge bytes (<= 3 before the first whole word, <= 3 after the last): predicated, no branches
+#ifdef ZPB_SIM
+    copy_edges_ss(h, t, s, d, ts, td);
+#else
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p0, p1, p2, q0, q1, q2;\n\t"
+        ".reg .b32 a0, a1, a2, b0, b1, b2;\n\t"
+        "setp.gt.u32 p0, %0, 0;\n\t"
+        "setp.gt.u32 p1, %0, 1;\n\t"
+        "setp.gt.u32 p2, %0, 2;\n\t"
+        "setp.gt.u32 q0, %1, 0;\n\t"
+        "setp.gt.u32 q1, %1, 1;\n\t"
+        "setp.gt.u32 q2, %1, 2;\n\t"
+        "@p0 ld.shared.u8 a0, [%2];\n\t"
+        "@p1 ld.shared.u8 a1, [%2+1];\n\t"
+        "@p2 ld.shared.u8 a2, [%2+2];\n\t"
+        "@q0 ld.shared.u8 b0, [%4];\n\t"
+        "@q1 ld.shared.u8 b1, [%4+1];\n\t"
+        "@q2 ld.shared.u8 b2, [%4+2];\n\t"
+        "@p0 st.shared.u8 [%3], a0;\n\t"
+        "@p1 st.shared.u8 [%3+1], a1;\n\t"
+        "@p2 st.shared.u8 [%3+2], a2;\n\t"
+        "@q0 st.shared.u8 [%5], b0;\n\t"
+        "@q1 st.shared.u8 [%5+1], b1;\n\t"
+        "@q2 st.shared.u8 [%5+2], b2;\n\t"
+        "}" ::"r"(h), "r"(t), "r"(s), "r"(d), "r"(ts), "r"(td) : "memory");
+#endif
     const u32 maxnw = __reduce_max_sync(0xffffffffu, nw);
     const u32 sw = s2 & ~3u, sh = (s2 & 3u) << 3;
-#pragma unroll 1
-    for (u32 kb = 0; kb < maxnw; kb += 4)        // four whole words per round
-        copy_words_ss(nw > kb ? nw - kb : 0u, sw + 4 * kb, sh, d2 + 4 * kb);
+    for (u32 kb = 0; kb < maxnw; kb += 4) {      // four whole words per round
+        const u32 rem = nw > kb ? nw - kb : 0u;
+        const u32 sa = sw + 4 * kb, da = d2 + 4 * kb;
+        u32 a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+#ifdef ZPB_SIM
+        if (rem > 0) { a0 = lds32_loose(sa); a1 = lds32_loose(sa + 4); a2 = lds32_loose(sa + 8); a3 = lds32_loose(sa + 12); a4 = lds32_loose(sa + 16); }
+#else
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.gt.u32 p, %5, 0;\n\t"
+            "@p ld.shared.u32 %0, [%6];\n\t"
+            "@p ld.shared.u32 %1, [%6+4];\n\t"
+            "@p ld.shared.u32 %2, [%6+8];\n\t"
+            "@p ld.shared.u32 %3, [%6+12];\n\t"
+            "@p ld.shared.u32 %4, [%6+16];\n\t"
+            "}" : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4) : "r"(rem), "r"(sa) : "memory");
+#endif
+        const u32 w0 = __funnelshift_r(a0, a1, sh), w1 = __funnelshift_r(a1, a2, sh),
+                  w2 = __funnelshift_r(a2, a3, sh), w3 = __funnelshift_r(a3, a4, sh);
+#ifdef ZPB_SIM
+        if (rem > 0) sts32(da, w0);
+        if (rem > 1) sts32(da + 4, w1);
+        if (rem > 2) sts32(da + 8, w2);
+        if (rem > 3) sts32(da + 12, w3);
+#else
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p0, p1, p2, p3;\n\t"
+            "setp.gt.u32 p0, %0, 0;\n\t"
+            "setp.gt.u32 p1, %0, 1;\n\t"
+            "setp.gt.u32 p2, %0, 2;\n\t"
+            "setp.gt.u32 p3, %0, 3;\n\t"
+            "@p0 st.shared.u32 [%1], %2;\n\t"
+            "@p1 st.shared.u32 [%1+4], %3;\n\t"
+            "@p2 st.shared.u32 [%1+8], %4;\n\t"
+            "@p3 st.shared.u32 [%1+12], %5;\n\t"
+            "}" ::"r"(rem), "r"(da), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+#endif
+    }
 }
-#define LANE_COPY_SLACK 24u
 
 // ------------------------------------------------------------------------------------------ K1
 #define K1_THREADS 256
@@ -326,52 +380,101 @@ struct LaneStage {
     ZPB_DEVINL u32 rd(u32 q) const { return lds8(row_s + (q & 255u)); }
 };
 
-__global__ void __launch_bounds__(K1_THREADS)
-lz4_fast_parse_kernel(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, const u32 *__restrict__ parse_list,
-                      u32 plist_cap, const u32 *__restrict__ counters, u32 *work_counter, u32 *desc) {
+// One parse kernel, two shapes.  J = 1: a lane walks a whole block (light blocks: nothing to gain from splitting).
+// J = 4: the four lanes of a group walk the four quarters of one block at the same time, which cuts the serial walk of
+// a heavy block — the floor of this kernel, whatever the batch size — to a quarter.  Lane 0 starts at the block's
+// first token; lanes 1-3 start at byte j * bsz / 4, which is almost never a token.  LZ4 token streams re-synchronise:
+// a walk that starts on an arbitrary byte lands on a true sequence boundary within a few sequences and stays on the true
+// chain from there.  So each lane keeps walking past the start of the next quarter until it stands on a position the
+// next lane has also visited (a merge over the next lane's descriptor list, two pointers): from that JOIN on the next
+// lane's list is the truth, and everything the next lane emitted before it is discarded.  Output positions of a
+// speculative lane are relative to its own start; the join fixes the base (all arithmetic mod 2^16 for the 16-bit
+// descriptor field, in full precision for the block's decoded size).  A lane that does not join within K1_MERGE_MAX
+// sequences, or a speculative walk that runs off the block, hands the block to the unsplit kernel, which walks it again
+// from its first byte.  When the four lanes of a block have finished, the warp moves the valid parts of segments 1-3
+// down behind segment 0 (output positions made absolute), so that K2 sees one flat descriptor list per block.
+#ifndef K1_MERGE_MAX
+#define K1_MERGE_MAX 96u
+#endif
+#define K1_SEG_SLACK 112u     // descriptor slots per segment beyond (compressed bytes / 3): the overrun until the join
+
+ZPB_DEVINL u32 k1_seg_start(u32 bsz, u32 j, u32 J) { return J == 1 ? 0u : (u32)(((u64)bsz * j) / J); }
+ZPB_DEVINL u32 k1_seg_desc(u32 bsz, u32 j, u32 J) {   // first descriptor slot of segment j (multiple of 4)
+    return J == 1 ? 0u : ((k1_seg_start(bsz, j, J) / 3u + K1_SEG_SLACK * j) + 3u) & ~3u;
+}
+
+#ifdef ZPB_SIM
+#define K1_WHY(code) do { if (getenv("SIM_K1_WHY")) fprintf(stderr, "sim: k1 slot %u seg %u: %s (q %u qstop %u qend %u nseq %u mptr %u msteps %u)\n", slot, sj, code, q - skew, qstop - skew, qend - skew, nseq, mptr, msteps); } while (0)
+#else
+#define K1_WHY(code) do { } while (0)
+#endif
+#define K1M_WALK  0u
+#define K1M_MERGE 1u
+#define K1M_DONE  2u   // joined (or, last segment, reached the block's end cleanly)
+#define K1M_FAIL  3u
+
+template <int J>
+ZPB_DEVINL void
+lz4_fast_parse_body(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, u32 *parse_list,
+                    u32 plist_cap, u32 *counters, u32 *work_counter, u32 *desc, u32 all_lists) {
+    // J = 4 walks the heavy list, then the medium one; J = 1 the light one — or, when the batch is so large that even
+    // unsplit walks fill the GPU (all_lists: the host decides), all three, heavy first (K0 sorts blocks by compressed size)
+    const u32 n_heavy = (J == 4 || all_lists) ? counters[8] : 0u;
+    const u32 n_medium = (J == 4 || all_lists) ? counters[9] : 0u;
+    const u32 nitems = J == 4 ? n_heavy + n_medium : n_heavy + n_medium + counters[10];
     ZPB_DYN_SMEM(k1_smem);
-    const int lane = threadIdx.x & 31;
+    const u32 lane = threadIdx.x & 31u;
+    const u32 sj = lane & (J - 1);                 // this lane's segment
     const u32 row_s = smem_window(k1_smem) + threadIdx.x * K1_ROW;
-    const u32 n_heavy = counters[8], n_medium = counters[9], nitems = n_heavy + n_medium + counters[10];
-    const u32 nlanes = gridDim.x * blockDim.x;
+    const u32 ngroups = gridDim.x * blockDim.x / J;
+    const u32 gmask = J == 1 ? (1u << lane) : (0xFu << (lane & ~3u));   // the lanes of this lane's group
     bool active = false, exhausted = false, first = true;
     LaneStage sg;
     sg.gbase = archive; sg.glo = archive; sg.ghi = archive + asz; sg.row_s = row_s; sg.nreq = sg.avail = sg.klo = sg.khi = 0;
     // all positions below are ring coordinates (block position + skew)
-    u32 slot = 0, skew = 0, qend = 0, q = 0, op = 0, nseq = 0, reach = 0, last_ms = 0;
+    u32 slot = 0, skew = 0, qend = 0, qstop = 0, q = 0, op = 0, nseq = 0, last_ms = 0, mode = K1M_DONE;
+    u32 mptr = 0, msteps = 0, jtok = 0, jop = 0, bszv = 0;
     bool had_match = false;
     u32 b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-    u32 *dout = nullptr;
+    u32 *dout = nullptr;     // this segment's descriptor region
     u32 it = 0;
 
     for (;;) {
-        u32 idle = __ballot_sync(0xffffffffu, !active);
-        if (idle) {
+        // ---- groups whose lanes are all idle take the next block
+        const u32 idle = __ballot_sync(0xffffffffu, !active);
+        u32 gidle = idle;                                  // bit g*J set: group g idle
+        if (J == 4) { gidle &= gidle >> 1; gidle &= gidle >> 2; gidle &= 0x11111111u; }
+        if (gidle) {
             if (!exhausted) {
-                // first item: by position in the grid (CTA c walks items [256c, 256c + 256): the heavy list lands on
-                // the first CTAs); afterwards from the shared counter, which starts behind the statically dealt items
+                // first item: by position in the grid (the heavy end of the list lands on the first CTAs); afterwards
+                // from the shared counter, which starts behind the statically dealt items
+                const u32 ng = (u32)__popc(gidle);
                 u32 base;
                 if (first) {
-                    base = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u));
+                    base = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) / J;
                     first = false;
                 } else {
                     base = 0;
-                    int leader = __ffs(idle) - 1;
-                    if (lane == leader) base = atomicAdd(work_counter, (u32)__popc(idle));
-                    base = __shfl_sync(0xffffffffu, base, leader) + nlanes;
+                    const int leader = __ffs(gidle) - 1;
+                    if ((int)lane == leader) base = atomicAdd(work_counter, ng);
+                    base = __shfl_sync(0xffffffffu, base, leader) + ngroups;
                 }
-                if (base + __popc(idle) > nitems) exhausted = true;
-                if (!active) {
-                    u32 w = base + __popc(idle & ((1u << lane) - 1u));
+                if (base + ng > nitems) exhausted = true;
+                if ((gidle >> (lane & ~(J - 1))) & 1u) {
+                    const u32 w = base + (u32)__popc(gidle & ((1u << (lane & ~(J - 1))) - 1u));
                     if (w < nitems) {
                         slot = w < n_heavy ? parse_list[w]
                              : w < n_heavy + n_medium ? parse_list[(u64)plist_cap + (w - n_heavy)]
                                                       : parse_list[2ull * plist_cap + (w - n_heavy - n_medium)];
-                        FastBlock B = fb[slot];
-                        dout = desc + B.desc_off;
+                        const FastBlock B = fb[slot];
+                        bszv = B.bsz;
                         skew = sg.open(archive, asz, B.src, row_s);
-                        q = skew; qend = B.bsz + skew;
-                        op = 0; nseq = 0; reach = 0; last_ms = 0; had_match = false;
+                        qend = B.bsz + skew;
+                        q = skew + k1_seg_start(B.bsz, sj, J);
+                        qstop = sj + 1 < J ? skew + k1_seg_start(B.bsz, sj + 1, J) : qend;
+                        dout = desc + B.desc_off + k1_seg_desc(B.bsz, sj, J);
+                        op = 0; nseq = 0; last_ms = 0; had_match = false;
+                        mode = K1M_WALK; mptr = 0; msteps = 0; jtok = 0; jop = 0;
                         active = true;
                         sg.need(q, q + 1);       // the first four chunks, waited for
                     }
@@ -379,8 +482,109 @@ lz4_fast_parse_kernel(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, co
             }
             if (__ballot_sync(0xffffffffu, active) == 0) break;
         }
-        if ((it++ % K1_TOPUP) == 0) sg.topup(active, q);   // warp-uniform
-        if (!active) continue;
+        if ((it++ % K1_TOPUP) == 0) sg.topup(active && mode < K1M_DONE, q);   // warp-uniform
+
+        // ---- a lane that has passed the start of the next quarter looks for its position in the next lane's list
+        if (J == 4) {
+            const bool merging = active && mode == K1M_MERGE;
+            if (__any_sync(0xffffffffu, merging)) {
+                __syncwarp();                                                   // the next lane's descriptor stores
+                const u32 nx_n = __shfl_down_sync(0xffffffffu, nseq, 1);
+                const u32 nx_mode = __shfl_down_sync(0xffffffffu, mode, 1);
+                if (merging) {
+                    const u32 *nd = desc + fb[slot].desc_off + k1_seg_desc(bszv, sj + 1, J);
+                    const u32 avail_n = nx_mode >= K1M_DONE ? nx_n : nx_n & ~3u;   // descriptors of the next lane that are in memory
+                    const u32 tq = q - skew;
+                    u32 dv = 0xFFFFFFFFu;
+                    while (mptr < avail_n && ((dv = __ldcg(nd + mptr)) & 0xFFFFu) < tq) ++mptr;
+                    if (mptr < avail_n && (dv & 0xFFFFu) == tq) {
+                        mode = K1M_DONE; jtok = tq; jop = dv >> 16;             // joined: the next lane's list is valid from mptr on
+                        const u32 r = nseq & 3u;                                // descriptors still in the shift register
+                        if (r == 1) dout[nseq - 1] = b3;
+                        else if (r == 2) { dout[nseq - 2] = b2; dout[nseq - 1] = b3; }
+                        else if (r == 3) { dout[nseq - 3] = b1; dout[nseq - 2] = b2; dout[nseq - 1] = b3; }
+                    } else if (nx_mode == K1M_FAIL || (mptr >= avail_n && nx_mode >= K1M_DONE) || ++msteps > K1_MERGE_MAX) {
+                        K1_WHY(nx_mode == K1M_FAIL ? "next lane failed" : msteps > K1_MERGE_MAX ? "merge timeout" : "next list exhausted");
+                        mode = K1M_FAIL;
+                    }
+                }
+            }
+        }
+        // ---- block verdict, when every lane of a group has finished (warp-uniform: the shuffles need every lane)
+        if (J == 4) {
+            const u32 fin_mask = __ballot_sync(0xffffffffu, !active || mode >= K1M_DONE);
+            const bool gdone = active && (fin_mask & gmask) == gmask;
+            if (__any_sync(0xffffffffu, gdone)) {
+                const u32 g0 = lane & ~3u;
+                u32 ok = mode == K1M_DONE ? 1u : 0u;
+                ok &= __shfl_xor_sync(0xffffffffu, ok, 1);
+                ok &= __shfl_xor_sync(0xffffffffu, ok, 2);
+                // bases: base_0 = 0, base_{j+1} = (base_j + op_j at the join) - (the next lane's relative position there)
+                const u32 delta = op - jop;
+                u32 base = 0;
+#pragma unroll
+                for (u32 kk = 1; kk < 4; ++kk) {
+                    const u32 pb_ = __shfl_sync(0xffffffffu, base, g0 + kk - 1), pd = __shfl_sync(0xffffffffu, delta, g0 + kk - 1);
+                    if (sj == kk) base = pb_ + pd;
+                }
+                const u32 pfirst = __shfl_up_sync(0xffffffffu, mptr, 1);      // where the previous lane joined this lane's list
+                const u32 firstv = sj == 0 ? 0u : pfirst;
+                const u32 cnt = nseq > firstv ? nseq - firstv : 0u;
+                u32 total = cnt;
+                total += __shfl_xor_sync(0xffffffffu, total, 1);
+                total += __shfl_xor_sync(0xffffffffu, total, 2);
+                // decoded size = the last lane's end, in full precision: bases are known mod 2^16 only, so it is the previous
+                // lane's join (an absolute position below 2^16) plus what the last lane has produced since (below 2^16)
+                const u32 abs_join = base + op;
+                const u32 pj = __shfl_up_sync(0xffffffffu, abs_join, 1), pjop = __shfl_up_sync(0xffffffffu, jop, 1);
+                const u32 out_size = __shfl_sync(0xffffffffu, (pj & 0xFFFFu) + ((op - pjop) & 0xFFFFu), g0 + 3);
+                // ---- one flat list per block: the valid part of segments 1..3 moves down behind segment 0 (in place: the
+                // destination is always below the source), output positions made absolute on the way.  All 32 lanes copy,
+                // one finished group at a time.
+                const u32 srcv = k1_seg_desc(bszv, sj, J) + firstv;            // this segment's first valid descriptor, block-relative
+                u32 gm = __ballot_sync(0xffffffffu, gdone && sj == 0);
+                while (gm) {
+                    const int gl = __ffs(gm) - 1;                               // lane 0 of the group being compacted
+                    gm &= gm - 1;
+                    const u32 okg = __shfl_sync(0xffffffffu, ok, gl), osz = __shfl_sync(0xffffffffu, out_size, gl);
+                    u32 *const bd = reinterpret_cast<u32 *>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)dout, gl));
+                    u32 dst = __shfl_sync(0xffffffffu, cnt, gl);                // segment 0 is in place
+                    const bool good = okg && osz <= 65536u;
+#pragma unroll 1
+                    for (int kk = 1; kk < 4 && good; ++kk) {
+                        const u32 sv = __shfl_sync(0xffffffffu, srcv, gl + kk), cv = __shfl_sync(0xffffffffu, cnt, gl + kk),
+                                  bv = __shfl_sync(0xffffffffu, base, gl + kk);
+                        __syncwarp();                                           // the segments' own stores, and the previous move
+                        for (u32 i0 = 0; i0 < cv; i0 += 32) {
+                            const u32 i = i0 + lane;
+                            u32 v = 0;
+                            if (i < cv) v = __ldcg(bd + sv + i);
+                            __syncwarp();                                       // every load of the chunk before any store of it
+                            if (i < cv) bd[dst + i] = (v & 0xFFFFu) | (((v >> 16) + bv) << 16);
+                        }
+                        dst += cv;
+                    }
+                }
+                if (gdone) {
+                    if (sj == 3) {
+                        if (!ok || out_size > 65536u) {
+                            // No join within reach (few, long sequences: a walk started inside a long literal run stays off
+                            // the true chain), or a genuinely bad block: the unsplit kernel, which runs after this one,
+                            // walks it again from its first byte and has the verdict.
+                            parse_list[2ull * plist_cap + atomicAdd(&counters[10], 1u)] = slot;
+                            atomicAdd(&counters[14], 1u);   // statistics: blocks the split walk gave back
+                        } else {
+                            fb[slot].nseq = total;
+                            fb[slot].out_size = out_size;
+                            __threadfence();   // K2 may already be running (it polls `flags`): descriptors and sizes first, verdict last
+                            *reinterpret_cast<volatile u32 *>(&fb[slot].flags) = FB_PARSED;
+                        }
+                    }
+                    active = false;
+                }
+            }
+        }
+        if (!(active && mode <= K1M_MERGE)) continue;
 
         // ---- one sequence (control bytes only; mirrors lz4.c:1797-2151 + the spec's end rules)
         bool bad = false, fin = false;
@@ -406,12 +610,11 @@ lz4_fast_parse_kernel(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, co
                     ++nseq;
                     if ((nseq & 3u) == 0) *reinterpret_cast<uint4 *>(dout + nseq - 4) = make_uint4(b0, b1, b2, b3);
                     op += lit;
-                    if (off > op && off - op > reach) reach = off - op;
                     last_ms = op;
                     had_match = true;
                     op += ml;
                     q = pq + (mx ? 3u : 2u);
-                    if (off == 0 || op > 65536u || q >= qend) bad = true;
+                    if ((off == 0 && sj == 0) || (J == 1 && op > 65536u) || q >= qend) bad = true;   // a speculative walk may read anything; K2 checks the offsets it executes
                 }
             }
         }
@@ -435,11 +638,12 @@ lz4_fast_parse_kernel(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, co
                 ++nseq;
                 if ((nseq & 3u) == 0) *reinterpret_cast<uint4 *>(dout + nseq - 4) = make_uint4(b0, b1, b2, b3);
                 p += lit; op += lit;
-                if (op > 65536u) bad = true;
+                if (J == 1 && op > 65536u) bad = true;
                 else if (p == qend) {
                     // final sequence: literals only.  Spec end rules (lz4_Block_format.md:108-137) as
                     // sufficient conditions for the reference's capacity-based checks (lz4.c:2055-2077,2139).
                     if (had_match && (lit < 5 || op - last_ms < 12)) bad = true;
+                    if (J == 4 && sj != 3) bad = true;            // a quarter that reaches the block's end without a join
                     fin = true;
                 } else if (p + 8 > qend) {
                     bad = true;                                   // lz4.c:2055: must have been the last
@@ -459,12 +663,11 @@ lz4_fast_parse_kernel(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, co
                         if (b == 255) bad = true;
                     }
                     ml += 4;
-                    if (off == 0) bad = true;
-                    if (off > op && off - op > reach) reach = off - op;
+                    if (off == 0 && sj == 0) bad = true;
                     last_ms = op;
                     had_match = true;
                     op += ml;
-                    if (op > 65536u || p >= qend) bad = true;
+                    if ((J == 1 && op > 65536u) || p >= qend) bad = true;
                     q = p;
                     if (!bad) sg.need(q, q + 1);                  // the next token
                 }
@@ -472,6 +675,7 @@ lz4_fast_parse_kernel(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, co
         } else if (!bad && q + 1 > sg.avail) {
             sg.need(q, q + 1);
         }
+        if (J == 4 && !bad && !fin && mode == K1M_WALK && q >= qstop && sj != 3) mode = K1M_MERGE;
         if (bad || fin) {
             if (!bad) {
                 u32 r = nseq & 3u;  // descriptors still in the shift register
@@ -479,14 +683,30 @@ lz4_fast_parse_kernel(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, co
                 else if (r == 2) { dout[nseq - 2] = b2; dout[nseq - 1] = b3; }
                 else if (r == 3) { dout[nseq - 3] = b1; dout[nseq - 2] = b2; dout[nseq - 1] = b3; }
             }
-            fb[slot].nseq = nseq;
-            fb[slot].out_size = op;
-            __threadfence();   // K2 may already be running (it polls `flags`): descriptors and sizes first, verdict last
-            *reinterpret_cast<volatile u32 *>(&fb[slot].flags) = (bad ? FB_BAD : FB_PARSED) | (reach << 8);
             cp_async_wait_all();
-            active = false;
+            if (J == 1) {
+                fb[slot].nseq = nseq;
+                fb[slot].out_size = op;
+                __threadfence();   // K2 may already be running (it polls `flags`): descriptors and sizes first, verdict last
+                *reinterpret_cast<volatile u32 *>(&fb[slot].flags) = bad ? FB_BAD : FB_PARSED;
+                active = false;
+            } else {
+                if (bad) K1_WHY("walk hit an invalid construct");
+                mode = bad ? K1M_FAIL : K1M_DONE;
+            }
         }
     }
+}
+
+__global__ void __launch_bounds__(K1_THREADS)
+lz4_fast_parse_kernel(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, u32 *parse_list,
+                      u32 plist_cap, u32 *counters, u32 *work_counter, u32 *desc, u32 all_lists) {
+    lz4_fast_parse_body<1>(archive, asz, fb, parse_list, plist_cap, counters, work_counter, desc, all_lists);
+}
+__global__ void __launch_bounds__(K1_THREADS)
+lz4_fast_parse4_kernel(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, u32 *parse_list,
+                       u32 plist_cap, u32 *counters, u32 *work_counter, u32 *desc) {
+    lz4_fast_parse_body<4>(archive, asz, fb, parse_list, plist_cap, counters, work_counter, desc, 0u);
 }
 
 // ------------------------------------------------------------------------------------------ K2
@@ -582,15 +802,21 @@ struct FastExec {
     ZPB_DEVINL uint4 load16_ring(u32 p) const {
         const u32 b = p & ~3u, sh = (p & 3u) << 3;
         const u32 w0 = lds32_loose(ra(b)), w1 = lds32_loose(ra(b + 4)), w2 = lds32_loose(ra(b + 8)), w3 = lds32_loose(ra(b + 12)),
-                  w4 = lds32_loose(ra(b + 16));
+                  w4 = lds32_loose(ra(b + 16));   // whole words around the source: bytes of neighbouring copies are read, never stored
         return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
                           __funnelshift_r(w3, w4, sh));
     }
     ZPB_DEVINL uint4 load16_hbm(u32 p) const {   // plain ld.global: the buffer is written by this kernel
         const u8 *g = gout + (p & ~3u);
         const u32 sh = (p & 3u) << 3;
-        const u32 w0 = ldg32_coherent(g), w1 = ldg32_coherent(g + 4), w2 = ldg32_coherent(g + 8), w3 = ldg32_coherent(g + 12),
-                  w4 = ldg32_coherent(g + 16);
+#ifdef ZPB_SIM
+        const u32 w0 = ldg32_coherent(g), w1 = ldg32_coherent(g + 4), w2 = ldg32_coherent(g + 8), w3 = ldg32_coherent(g + 12), w4 = ldg32_coherent(g + 16);
+#else
+        u32 w0, w1, w2, w3, w4;
+        asm volatile("ld.global.u32 %0, [%5];\n\tld.global.u32 %1, [%5+4];\n\tld.global.u32 %2, [%5+8];\n\t"
+                     "ld.global.u32 %3, [%5+12];\n\tld.global.u32 %4, [%5+16];"
+                     : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3), "=r"(w4) : "l"(g) : "memory");
+#endif
         return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
                           __funnelshift_r(w3, w4, sh));
     }
@@ -677,109 +903,78 @@ struct FastExec {
     }
 };
 
+ZPB_DEVINL void cp_async16_cg(u32 smem_addr, const void *gptr) {   // L2 only: coherent with this kernel's own stores
+#ifdef ZPB_SIM
+    sim::cp_async(smem_addr, gptr, 16, 16);
+#else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+#endif
+}
 
-// The compressed bytes of the block a warp is executing, staged through a per-warp shared-memory ring of C_ROWS rows
-// of C_ROW bytes.  A row is one 1-D bulk async copy (cp.async.bulk.shared::cluster.global, the TMA unit) issued by
-// lane 0 and tracked by the row slot's mbarrier (expect_tx = the row's bytes); every lane waits on the barrier's
-// phase parity before it reads the row.  Rows are requested one ahead of the step that reads them.  Positions are
-// ring coordinates c = block position + skew, with the global address of coordinate 0 16-byte aligned.  A block whose
-// rows all lie inside the 16-byte aligned interior of the archive (every block but those next to its two ends) is
-// `safe`: its rows are whole copies and nothing is clipped; otherwise the copies are clipped to that interior and the
-// (< 16) bytes at either end of the archive are moved by plain loads.
-struct XStage {
-    const u8 *gbase;       // global address of ring coordinate 0
-    u32 cb;                // the ring (shared-window address, C_RING aligned)
-    u32 bar;               // C_ROWS mbarriers, 8 bytes each
+// The compressed bytes of the block a warp is executing, staged through a per-warp shared-memory ring:
+// rows of CR_ROW bytes (16 per lane, cp.async), requested one row ahead of the step that reads them, so
+// the per-lane token / length / offset / literal reads of K2 are shared-memory reads.  Positions are
+// "ring coordinates" c = block position + skew, with the global address of coordinate 0 16-byte aligned.
+struct CompStage {
+    const u8 *gbase;     // global address of ring coordinate 0
+    const u8 *glo, *ghi; // readable range (the archive)
+    u32 rb;              // the ring (shared-window address)
     u32 skew;
-    u32 fill;              // rows [.., fill) have been requested
-    u32 waited;            // rows [.., waited) have been waited for
-    u32 nrows;             // rows that cover the block
-    u32 phase;             // bit s: parity of the phase slot s's barrier is in; bit 31: the block is `safe`
-    u32 lane;
+    u32 fill;            // rows below this coordinate have been requested (multiple of CR_ROW)
+    u32 pending;         // cp.async groups committed since the last full wait (warp-uniform)
+    int lane;
 
-    ZPB_DEVINL void init(u32 ring, u32 bars, u32 l) {
-        cb = ring; bar = bars; lane = l;
-        skew = fill = waited = nrows = phase = 0;
-        gbase = nullptr;
-        if (lane == 0) {
-            for (u32 s = 0; s < C_ROWS; ++s) mbar_init(bar + 8 * s, 1);
-            mbar_fence_init();
-        }
-        __syncwarp();
-    }
-    ZPB_DEVINL void wait_row() {
-        const u32 s = waited & (C_ROWS - 1u);
-        mbar_wait(bar + 8 * s, (phase >> s) & 1u);
-        phase ^= 1u << s;
-        ++waited;
-    }
-    ZPB_DEVINL void drain() { while (waited < fill) wait_row(); }
-    ZPB_DEVINL void open(const u8 *src, u32 bsz, const u8 *archive, u64 asz) {
-        drain();                     // a look-ahead row of the previous block may still be in flight
+    ZPB_DEVINL void open(const u8 *src) {
+        cp_async_wait_all();         // a look-ahead row of the previous block may still be in flight
         __syncwarp();
         skew = (u32)((uintptr_t)src & 15u);
         gbase = src - skew;
-        fill = waited = 0;
-        nrows = (bsz + skew + C_ROW - 1u) >> C_ROWSH;
-        const u8 *alo = (const u8 *)(((uintptr_t)archive + 15u) & ~(uintptr_t)15u);
-        const u8 *ahi = (const u8 *)((uintptr_t)(archive + asz) & ~(uintptr_t)15u);
-        const bool safe = gbase >= alo && gbase + ((u64)nrows << C_ROWSH) <= ahi;
-        phase = (phase & 0x7fffffffu) | (safe ? 0x80000000u : 0u);
+        fill = 0;
+        pending = 0;
     }
-    ZPB_DEVINL void request_row(const u8 *archive, u64 asz) {   // row `fill` -> slot fill % C_ROWS; every reader of the slot's old content is done
-        const u32 s = fill & (C_ROWS - 1u);
-        const u32 sdst = cb + s * C_ROW;
-        const u8 *g0 = gbase + ((u64)fill << C_ROWSH);
-        if (phase >> 31) {
-            if (lane == 0) {
-                mbar_arrive_expect_tx(bar + 8 * s, C_ROW);
-                bulk_g2s(sdst, g0, C_ROW, bar + 8 * s);
-            }
-        } else {
-            const u8 *glo = archive, *ghi = archive + asz;
-            const u8 *alo = (const u8 *)(((uintptr_t)archive + 15u) & ~(uintptr_t)15u);
-            const u8 *ahi = (const u8 *)((uintptr_t)(archive + asz) & ~(uintptr_t)15u);
-            if (ahi < alo) ahi = alo;
-            const u8 *g1 = g0 + C_ROW;
-            const u8 *lo = g0 > alo ? g0 : alo, *hi = g1 < ahi ? g1 : ahi;
-            const u32 bytes = hi > lo ? (u32)(hi - lo) : 0u;
-            if (lane == 0) {
-                mbar_arrive_expect_tx(bar + 8 * s, bytes);
-                if (bytes) bulk_g2s(sdst + (u32)(lo - g0), lo, bytes, bar + 8 * s);
-            }
-            // the archive's unaligned ends (at most 15 bytes each, and only in the rows that contain them)
-            const u8 *e0 = g0 > glo ? g0 : glo, *e1 = g1 < ghi ? g1 : ghi;
-            for (const u8 *p = e0 + lane; p < e1; p += 32)
-                if (p < lo || p >= hi) sts8(sdst + (u32)(p - g0), *p);
+    ZPB_DEVINL void request_row() {
+        const u32 c = fill + 16u * lane;
+        const u8 *g = gbase + c;
+        const u32 sdst = rb + (c & CR_MASK);
+        if (16u * lane >= CR_ROW) {
+        } else if (g >= glo && g + 16 <= ghi) {
+#ifdef ZPB_SIM
+            sim::cp_async(sdst, g, 16, 16);
+#else
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(g) : "memory");
+#endif
+        } else if (g + 16 > glo && g < ghi) {   // straddles an end of the archive: byte by byte
+            for (u32 k = 0; k < 16; ++k)
+                if (g + k >= glo && g + k < ghi) sts8(sdst + k, g[k]);
         }
-        ++fill;
-    }
-    // Makes rows [r0, r1] readable (r1 - r0 < C_ROWS, the caller checks) and asks for the row after them.
-    ZPB_DEVINL void ensure(u32 r0, u32 r1, const u8 *archive, u64 asz) {
-        u32 want = r1 + 1u < r0 + C_ROWS ? r1 + 1u : r1;     // one row of look-ahead when the ring has room for it
-        if (want >= nrows) want = nrows - 1u;                // nrows >= 1: a block has at least one byte
-        if (want < r1) want = r1;
-        while (waited < fill && waited < r0) wait_row();   // requested, then skipped by a sequence that went around the ring
-        if (fill < r0) fill = waited = r0;
-        if (fill <= want) {
-            __syncwarp();                        // every lane has finished reading the slots that are filled again
-            while (fill <= want) request_row(archive, asz);
-        }
-        while (waited <= r1) wait_row();
-        __syncwarp();                            // edge bytes written by other lanes
+        cp_async_commit();
+        fill += CR_ROW;
+        ++pending;
     }
     // Makes block positions [s_lo, s_hi) readable through the ring; false when the span does not fit
     // (the caller then reads global memory for this step).  Warp-uniform arguments and result.
-    ZPB_DEVINL bool prepare(u32 s_lo, u32 s_hi, const u8 *archive, u64 asz) {
-        const u32 r0 = (s_lo + skew) >> C_ROWSH;
-        const u32 r1 = s_hi > s_lo ? (s_hi + skew - 1u) >> C_ROWSH : r0;
-        if (r1 - r0 >= C_ROWS) return false;
-        if (r1 >= waited) ensure(r0, r1, archive, asz);   // else: requested a step ago, waited for since
+    ZPB_DEVINL bool prepare(u32 s_lo, u32 s_hi, u32 bsz) {
+        const u32 rlo = (s_lo + skew) & ~(CR_ROW - 1u);
+        const u32 rhi = (s_hi + skew + CR_ROW - 1u) & ~(CR_ROW - 1u);
+        if (rhi - rlo > CR_SIZE) return false;
+        if (fill < rlo) {            // rows nobody needs (after a step that went around the ring)
+            cp_async_wait_all();
+            pending = 0;
+            __syncwarp();
+            fill = rlo;
+        }
+        while (fill < rhi) request_row();
+        u32 ahead = 0;
+        if (fill + CR_ROW - rlo <= CR_SIZE && fill < bsz + skew) { request_row(); ahead = 1; }   // one row of look-ahead
+        else if (fill > rhi) ahead = 1;                                                          // requested by the previous step
+        if (pending > ahead) {
+            if (ahead) cp_async_wait_1(); else cp_async_wait_all();
+            pending = ahead;
+        }
+        __syncwarp();
         return true;
     }
 };
-
-
 struct CompRing {     // byte reader over the staging ring
     u32 rb, skew;
     ZPB_DEVINL u32 operator()(u32 p) const { return lds8(rb + ((p + skew) & CR_MASK)); }
@@ -818,6 +1013,17 @@ ZPB_DEVINL uint4 ldg128_unaligned(const u8 *p) {
                       __funnelshift_r(w3, w4, sh));
 }
 
+#ifdef ZPB_SIM
+template <int OFF> ZPB_DEVINL void sts8o(u32 a, u32 v) { sts8(a + OFF, v); }
+template <int OFF> ZPB_DEVINL u32 ldg8nc(const u8 *p) { return p[OFF]; }
+#else
+template <int OFF> ZPB_DEVINL void sts8o(u32 a, u32 v) {
+    asm volatile("st.shared.u8 [%0+%2], %1;" ::"r"(a), "r"(v), "n"(OFF) : "memory");
+}
+template <int OFF> ZPB_DEVINL u32 ldg8nc(const u8 *p) {   // read-only data (the archive), explicit addressing
+    u32 v; asm volatile("ld.global.nc.u8 %0, [%1+%2];" : "=r"(v) : "l"(p), "n"(OFF)); return v;
+}
+#endif
 #define FAST_BYTE4(LD, ST, n, i)                                                        \
     {                                                                                   \
         u32 v0_ = 0, v1_ = 0, v2_ = 0, v3_ = 0;                                                       \
@@ -831,12 +1037,12 @@ ZPB_DEVINL uint4 ldg128_unaligned(const u8 *p) {
 #endif
 // resident CTAs per SM the kernel is compiled for (registers) and launched with
 
-ZPB_DEVINL void
-lz4_fast_exec_body(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_entry *__restrict__ entries,
-                   const u32 *__restrict__ order, u32 n, u32 *counter, const FastEntry *__restrict__ fe,
-                   const FastBlock *__restrict__ fb, const u32 *__restrict__ desc, u32 *counters,
-                   u32 *general_list, int *status, u64 *digest, u64 *partials, u32 *defer_list, u32 *defer_cnt,
-                   const u32 *n_ptr) {
+__global__ void __launch_bounds__(32 * FAST_EXEC_WARPS, FAST_EXEC_CTAS)
+lz4_fast_exec_kernel(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_entry *__restrict__ entries,
+                     const u32 *__restrict__ order, u32 n, u32 *counter, const FastEntry *__restrict__ fe,
+                     const FastBlock *__restrict__ fb, const u32 *__restrict__ desc, u32 *counters,
+                     u32 *general_list, int *status, u64 *digest, u64 *partials, u32 *defer_list, u32 *defer_cnt,
+                     const u32 *n_ptr) {
     ZPB_DYN_SMEM(k2_smem);
     if (n_ptr) n = *n_ptr;   // the late pass over the deferred list: its length was only known on the device
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -845,8 +1051,13 @@ lz4_fast_exec_body(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_e
     x.rb = smem_window(k2_smem) + 16u + warp * FAST_WARP_SMEM;   // 16 B of slack in front, 32 behind (lane_copy reads whole words)
     x.scr_s = x.rb + FAST_RING + lane * FAST_SCR;
     const u8 *arch_end = archive + asz;
-    XStage cs;
-    cs.init(x.rb + FAST_RING + 32u * FAST_SCR, smem_window(k2_smem) + FAST_EXEC_WARPS * FAST_WARP_SMEM + 48u + warp * (8u * C_ROWS), (u32)lane);
+    CompStage cs;
+    cs.lane = lane;
+    cs.rb = x.rb + FAST_RING + 32u * FAST_SCR;
+    cs.glo = archive;
+    cs.ghi = arch_end;
+    cs.fill = cs.pending = cs.skew = 0;
+    cs.gbase = archive;
 
     for (;;) {
         u32 wslot = 0;
@@ -877,8 +1088,6 @@ lz4_fast_exec_body(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_e
                 const u32 bflags = __ldcg(&pb->flags);
                 if (!(bflags & FB_STORED)) {
                     if (!(bflags & FB_PARSED) || (bflags & FB_BAD)) ok = false;
-                    u32 reach = (bflags >> 8) & 0xFFFFu;
-                    if (reach > (f.linked == FE_LINK_WINDOW ? before : 0ull)) ok = false;   // lz4.c:2093 with the frame's prefix
                 }
                 before += __ldcg(&pb->out_size);
             }
@@ -943,7 +1152,7 @@ lz4_fast_exec_body(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_e
             const u32 obase = x.done;
             const u32 bsz = __ldcg(&pb->bsz);
             const u32 nseq = __ldcg(&pb->nseq);
-            cs.open(src, bsz, archive, asz);
+            cs.open(src);
             // two steps of descriptors are kept in flight; the compressed bytes come through the staging ring
             u32 d0 = (u32)lane < nseq ? ldcg32(dp + lane) : 0u;
             u32 d1 = 32u + lane < nseq ? ldcg32(dp + 32 + lane) : 0u;
@@ -955,15 +1164,18 @@ lz4_fast_exec_body(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_e
                 // compressed bytes this step reads: from its first token to the next step's first token
                 const u32 s_lo = __shfl_sync(0xffffffffu, d & 0xFFFFu, 0);
                 const u32 s_nx = __shfl_sync(0xffffffffu, d0 & 0xFFFFu, 0);
-                const bool in_ring = cs.prepare(s_lo, s0i + 32 < nseq ? s_nx : bsz, archive, asz);   // warp-uniform
+                const bool in_ring = cs.prepare(s_lo, s0i + 32 < nseq ? s_nx : bsz, bsz);   // warp-uniform
                 u32 lit = 0, lsrc = 0, off = 0, ml = 0, o = 0;
                 if (have) {
                     o = obase + (d >> 16);
-                    if (in_ring) fast_decode_seq(CompRing{cs.cb, cs.skew}, d & 0xFFFFu, bsz, lit, lsrc, off, ml);
+                    if (in_ring) fast_decode_seq(CompRing{cs.rb, cs.skew}, d & 0xFFFFu, bsz, lit, lsrc, off, ml);
                     else fast_decode_seq(CompGlobal{src}, d & 0xFFFFu, bsz, lit, lsrc, off, ml);
                 }
                 const u32 sz = lit + ml;
                 const u32 mo = o + lit, msrc = mo - off;
+                // a match that reaches below the window (lz4.c:2093: the frame's prefix when the blocks are linked) or has
+                // offset 0: not something this path decodes — the entry goes to the general decoder, which has the exact verdict
+                if (__any_sync(0xffffffffu, ml > 0 && (off == 0 || off > mo - (f.linked == FE_LINK_WINDOW ? 0u : obase)))) goto bail_entry;
                 const u8 *__restrict__ sp = src + lsrc;
                 // matches whose whole source is already in HBM: fetch it now, asynchronously, into this lane's
                 // scratch (16-byte pieces straight from L2; up to 5 cover any alignment of <= 64 bytes)
@@ -972,14 +1184,21 @@ lz4_fast_exec_body(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_e
                 if (staged) {
                     const u32 np = ((msrc - abase) + ml + 15u) >> 4;
                     const u8 *g = x.gout + abase;
-                    cp_async_pieces_cg(np, x.scr_s, g);
+                    cp_async16_cg(x.scr_s, g);
+                    if (np > 1) cp_async16_cg(x.scr_s + 16, g + 16);
+                    if (np > 2) {
+                        cp_async16_cg(x.scr_s + 32, g + 32);
+                        if (np > 3) cp_async16_cg(x.scr_s + 48, g + 48);
+                        if (np > 4) cp_async16_cg(x.scr_s + 64, g + 64);
+                    }
                 }
                 else if (have && ml > 0 && msrc < x.flushed) {
                     // longer match reaching back into flushed output: pull its lines towards L1 now, the
                     // warp-wide copy that needs them runs later in this step
                     u32 pe = msrc + ml < x.flushed ? msrc + ml : x.flushed;
                     if (pe > msrc + 512) pe = msrc + 512;
-                    for (u32 a = msrc & ~127u; a < pe; a += 128) prefetch_l1(x.gout + a);
+                    for (u32 a = msrc & ~127u; a < pe; a += 128)
+                        prefetch_l1(x.gout + a);
                 }
                 cp_async_commit();
                 // ---- same-step dependencies.  A match whose source lies inside the output of an earlier
@@ -1049,11 +1268,11 @@ lz4_fast_exec_body(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_e
                                               (in_ring ? lit <= FAST_LTR && cq + lit <= CR_SIZE : lit <= FAST_LT);
                         const u32 mylit = lane_lit ? lit : 0u;
                         if (in_ring) {
-                            lane_copy(cs.cb + cq, da, mylit);
+                            lane_copy(cs.rb + cq, da, mylit);
                         } else {
                             const u32 maxlit = __reduce_max_sync(0xffffffffu, mylit);
-#define STL(u, v) sts8(dai + u, v)
-#define LDL(u) ((u32)spi[u])
+#define STL(u, v) sts8o<u>(dai, v)
+#define LDL(u) ldg8nc<u>(spi)
                             for (u32 i = 0; i < maxlit; i += 4) {
                                 const u8 *spi = sp + i;
                                 const u32 dai = da + i;
@@ -1069,7 +1288,7 @@ lz4_fast_exec_body(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_e
                             u32 O = __shfl_sync(0xffffffffu, o, r), S = __shfl_sync(0xffffffffu, lsrc, r),
                                 L = __shfl_sync(0xffffffffu, lit, r);
                             if (in_ring) {
-                                for (u32 i = lane; i < L; i += 32) sts8(x.ra(O + i), lds8(cs.cb + ((S + cs.skew + i) & CR_MASK)));
+                                for (u32 i = lane; i < L; i += 32) sts8(x.ra(O + i), lds8(cs.rb + ((S + cs.skew + i) & CR_MASK)));
                             } else {
                                 x.coop_lit(O, src + S, L);
                             }
@@ -1077,6 +1296,7 @@ lz4_fast_exec_body(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_e
                     }
                     if (!parked) {   // far-match sources requested at decode time have landed in the scratch
                         cp_async_wait_all();
+                        cs.pending = 0;
                         parked = true;
                     }
                     // ... then matches.  Everything whose source bytes are final (before this step, in literal
@@ -1134,6 +1354,18 @@ lz4_fast_exec_body(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_e
             }
         }
 
+        if (false) {
+        bail_entry:
+            // nothing of this entry has been reported yet: the general decoder starts it over (a block of the sharded
+            // path declines instead: the caller re-reads the entry through zpb_unpack_device)
+            __syncwarp();
+            cp_async_wait_all();
+            if (lane == 0) {
+                if (partial) { status[idx] = ST_NOT_AVAILABLE; digest[idx] = 0; }
+                else general_list[atomicAdd(&counters[1], 1u)] = idx;
+            }
+            continue;
+        }
         // ---- finish: last bytes to HBM, XXH3 tail (xxhash.h:3701-3747) from the ring, verdict
         __syncwarp();
         u64 dg;
@@ -1185,14 +1417,6 @@ lz4_fast_exec_body(const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_e
             digest[idx] = partial ? 0ull : dg;
         }
     }
-    cs.drain();   // no bulk copy may outlive the CTA's shared memory
 }
-
-#define FAST_EXEC_ARGS const u8 *__restrict__ archive, u64 asz, u8 *out, const zpb_entry *__restrict__ entries,            \
-                       const u32 *__restrict__ order, u32 n, u32 *counter, const FastEntry *__restrict__ fe,               \
-                       const FastBlock *__restrict__ fb, const u32 *__restrict__ desc, u32 *counters, u32 *general_list,    \
-                       int *status, u64 *digest, u64 *partials, u32 *defer_list, u32 *defer_cnt, const u32 *n_ptr
-#define FAST_EXEC_PASS archive, asz, out, entries, order, n, counter, fe, fb, desc, counters, general_list, status, digest,  \
-                       partials, defer_list, defer_cnt, n_ptr
-__global__ void __launch_bounds__(32 * FAST_EXEC_WARPS, FAST_EXEC_CTAS) lz4_fast_exec_kernel(FAST_EXEC_ARGS) { lz4_fast_exec_body(FAST_EXEC_PASS); }
-typedef void (*fast_exec_fn)(FAST_EXEC_ARGS);
+typedef void (*fast_exec_fn)(const u8 *__restrict__, u64, u8 *, const zpb_entry *__restrict__, const u32 *__restrict__, u32, u32 *, const FastEntry *__restrict__,
+                             const FastBlock *__restrict__, const u32 *__restrict__, u32 *, u32 *, int *, u64 *, u64 *, u32 *, u32 *, const u32 *);

@@ -159,6 +159,8 @@ extern "C" zpb_ctx *zpb_create(int device) {
     if (const char *e = getenv("ZPB_OVERLAP")) ctx->overlap = atoi(e);
     if (cudaFuncSetAttribute(lz4_fast_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(K1_THREADS * K1_ROW)) != cudaSuccess ||
+        cudaFuncSetAttribute(lz4_fast_parse4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(K1_THREADS * K1_ROW)) != cudaSuccess ||
         cudaFuncSetAttribute(lz4_fast_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(FAST_EXEC_SMEM)) != cudaSuccess) {
         g_last_error = std::string("kernel attribute setup failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -246,6 +248,13 @@ extern "C" int zpb_debug_zstd_profile(unsigned long long *out8) {
     return cudaMemcpyToSymbol(g_zs_prof, z, sizeof z) == cudaSuccess ? ZPB_OK : ZPB_E_CUDA;
 }
 #endif
+
+// developer statistics of the last unpack call: the device-side counters (lz4_fast.cuh: [8..10] parse list lengths,
+// [14] blocks the split walk gave back to the unsplit kernel, [1] entries handed to the general decoder)
+extern "C" int zpb_debug_counters(zpb_ctx *ctx, unsigned *out16) {
+    if (!ctx || !out16 || !ctx->d_counter.p) return ZPB_E_ARG;
+    return cudaMemcpy(out16, ctx->d_counter.p, 64, cudaMemcpyDeviceToHost) == cudaSuccess ? ZPB_OK : ZPB_E_CUDA;
+}
 
 extern "C" int zpb_set_overlap(zpb_ctx *ctx, int enabled) {
     if (!ctx) return ZPB_E_ARG;
@@ -354,10 +363,10 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
             if (e.method == ZPB_METHOD_NONE) ns = 1;
             else if (e.method == ZPB_M_LZ4_BLOCK) {
                 ns = 1;
-                nd = ((e.comp_size / 3 + 20) + 3) & ~3ull;
+                nd = ((e.comp_size / 3 + FAST_DESC_PER_BLOCK + 20) + 3) & ~3ull;
             } else if (e.method == ZPB_METHOD_LZ4) {
                 ns = (u32)(e.uncomp_size >> 16) + 2;
-                nd = ((e.comp_size / 3 + 12ull * ns + 8) + 3) & ~3ull;
+                nd = ((e.comp_size / 3 + FAST_DESC_PER_BLOCK * ns + 8) + 3) & ~3ull;
             }
         }
         h_aux[i].desc_base = ndesc; h_aux[i].slot_base = (u32)slots; h_aux[i].nslots = ns;
@@ -424,9 +433,23 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
             CK(ctx, cudaStreamWaitEvent(sp, ctx->ev_scan, 0));
         }
         CK(ctx, cudaEventRecord(ctx->ev_p0, sp));
+        // The split walk (four lanes per heavy / medium block, a quarter of the serial floor; lz4_fast_parse_body<4>) is
+        // opt-in (ZPB_PARSE_SPLIT=1).  Measured on B200 (profiles/r2_summary.md): a batch that already fills the GPU's lanes
+        // gains nothing (131 072 blocks: 2.9 ms split vs 2.2 ms unsplit, the merge is extra work), and a small batch gains
+        // only when NO block has to be given back to the unsplit kernel — one such block (0.03 % of text blocks, 2 % of
+        // fixed-stride records, whose false walks can phase-lock) costs the whole serial floor again.
+        static const int split_env = [] { const char *e = getenv("ZPB_PARSE_SPLIT"); return e ? atoi(e) : 0; }();
+        const bool split = split_env != 0;
+        if (split) {
+            lz4_fast_parse4_kernel<<<ctx->sm_count * k1_ctas, K1_THREADS, K1_THREADS * K1_ROW, sp>>>(
+                d_archive, archive_size, (FastBlock *)ctx->d_fb.p, (u32 *)ctx->d_plist.p, (u32)(slots + 1), cnt, cnt + 2,
+                (u32 *)ctx->d_fdesc.p);
+            CK(ctx, cudaGetLastError());
+            ctx->launches += 1;
+        }
         lz4_fast_parse_kernel<<<ctx->sm_count * k1_ctas, K1_THREADS, K1_THREADS * K1_ROW, sp>>>(
-            d_archive, archive_size, (FastBlock *)ctx->d_fb.p, (const u32 *)ctx->d_plist.p, (u32)(slots + 1), cnt, cnt + 2,
-            (u32 *)ctx->d_fdesc.p);
+            d_archive, archive_size, (FastBlock *)ctx->d_fb.p, (u32 *)ctx->d_plist.p, (u32)(slots + 1), cnt, cnt + 13,
+            (u32 *)ctx->d_fdesc.p, split ? 0u : 1u);
         CK(ctx, cudaGetLastError());
         CK(ctx, cudaEventRecord(ctx->ev_p1, sp));
         CK(ctx, cudaEventRecord(ctx->ev_x0, s));
