@@ -46,6 +46,14 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _emit(args, line):
+    """The contract line: printed, unless this run is a nested measurement for the `configs` block of another line."""
+    if getattr(args, "nested", False):
+        args.result = line
+    else:
+        print(json.dumps(line))
+
+
 # ------------------------------------------------------------------ archive preparation (untimed)
 def _pack_shard(args):
     """Worker: generate entries [lo,hi) and pack them with the CPU checker's LZ4 frame writer.
@@ -126,6 +134,9 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ reference arm (CPU)
+_REF_OUT = None
+
+
 def cpu_unpack_throughput(arch, d, n_sample, threads, repeat=1, method=2):
     """The reference's own zpack_read_file (oracle/_ref) — or the port when _ref is absent — over
     `n_sample` entries split across `threads` host threads, one dctx each (lib/zpack.h:335-341).
@@ -138,19 +149,24 @@ def cpu_unpack_throughput(arch, d, n_sample, threads, repeat=1, method=2):
     if not use_ref and method == 1:
         threads = 1  # the port's zstd context is a single static object
     size = int(d.uncomp_size[:n_sample].max())
-    outs = [np.empty(size, np.uint8) for _ in range(threads)]
     bad = [0] * threads
     if use_ref:
+        # "each calling zpack_read_file into a preallocated output slice" — ONE output of n_sample slots,
+        # entry i decoded into slot i, so that the decoded bytes land in host DRAM as the GPU arm's do
+        global _REF_OUT
+        if _REF_OUT is None or len(_REF_OUT) < n_sample * size:
+            _REF_OUT = np.empty(n_sample * size, np.uint8)
         rd = O.RefReader(arch)
         drv = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_driver.so"))
-        drv.ref_unpack_range.restype = C.c_long
-        drv.ref_unpack_range.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p,
-                                         C.c_size_t, C.c_int, C.c_void_p]
+        drv.ref_unpack_slices.restype = C.c_long
+        drv.ref_unpack_slices.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p,
+                                          C.c_size_t, C.c_int, C.c_void_p]
         ents = C.cast(rd.r.file_entries, C.c_void_p)
 
         def work(t):
-            bad[t] = drv.ref_unpack_range(C.byref(rd.r), ents, t, n_sample, threads, outs[t].ctypes.data, size, method, None)
+            bad[t] = drv.ref_unpack_slices(C.byref(rd.r), ents, t, n_sample, threads, _REF_OUT.ctypes.data, size, method, None)
     else:
+        outs = [np.empty(size, np.uint8) for _ in range(threads)]
         lib = O.port()
         lib.orc_unpack_range.restype = C.c_long
         lib.orc_unpack_range.argtypes = [C.c_void_p] * 6 + [C.c_size_t] * 3 + [C.c_void_p, C.c_size_t, C.c_void_p]
@@ -180,8 +196,8 @@ def run_reference(args):
         return
     from zpack_b200 import container
     cores = os.cpu_count() or 1
-    n_sample = args.ref_entries
     wl = WORKLOADS[args.workload]
+    n_sample = args.ref_entries or args.entries or wl["entries"]
     if args.workload == "c3":
         data, _, _ = build_corpus(n_sample, ENTRY_SIZE, 0, cores)
         for _ in range(args.warmup):
@@ -213,10 +229,13 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": 1e3 * float(d.uncomp_size.sum()) / (value * 1e9),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "impl": "reference",
-            "config": {"workload": f"{wl['what']}, sample of {n_sample} x 128 KiB entries "
-                                   "(zpk-synth-v1), reference zpack_read_file on host cores"},
+            "config": {"workload": f"{wl['what']}, {n_sample} entries x 128 KiB "
+                                   f"({float(d.uncomp_size.sum()) / 2**30:.2f} GiB uncompressed), zpk-synth-v1, reference zpack_read_file on host "
+                                   "cores, every entry decoded into its own slice of one preallocated output",
+                       "entries": n_sample, "entry_bytes": ENTRY_SIZE},
             "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": kind,
-                             "sample": f"{n_sample} entries x 128 KiB per step, {cores} threads, one dctx each"},
+                             "sample": f"the whole {n_sample}-entry archive per step, {cores} threads, one dctx each, "
+                                       "entry i -> slot i of one output buffer"},
             "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -271,7 +290,8 @@ def run_c5(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl = WORKLOADS["c5"]
     nblk = args.entries or wl["entries"]
     bs = 65536
@@ -292,18 +312,26 @@ def run_c5(args):
     d_out = torch.empty(shard_bytes, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
 
+    # The only data that moves between GPUs: the 64-byte XXH3 accumulator state, rank r -> rank r + 1, once per read.
+    # It goes through a host-memory mailbox (a shared-memory file mapped by every rank; one 128-byte slot per receiver:
+    # sequence number, "has a state" flag, 8 accumulators) — no NCCL, no collective on the data path (north_star).
+    mbox, seq = None, [0]
+    if world > 1:
+        path = f"/dev/shm/zpb_relay_{os.environ.get('MASTER_PORT', '0')}"
+        if rank == 0:
+            np.zeros(world * 16, np.uint64).tofile(path)
+        dist.barrier()
+        mbox = np.memmap(path, dtype=np.uint64, mode="r+", shape=(world, 16))
+
     def send(dst, acc):
-        t = torch.zeros(9, dtype=torch.int64)
-        if acc is not None:
-            t[0] = 1
-            t[1:] = torch.from_numpy(np.asarray(acc, np.uint64).view(np.int64))
-        dist.send(t.cuda(), dst)
+        mbox[dst, 2:10] = 0 if acc is None else np.asarray(acc, np.uint64)
+        mbox[dst, 1] = 0 if acc is None else 1
+        mbox[dst, 0] = seq[0]          # published last: x86 stores become visible in program order
 
     def recv(src):
-        t = torch.zeros(9, dtype=torch.int64, device="cuda")
-        dist.recv(t, src)
-        t = t.cpu()
-        return t[1:].numpy().view(np.uint64).copy() if int(t[0]) else None
+        while int(mbox[rank, 0]) != seq[0]:
+            pass
+        return np.array(mbox[rank, 2:10], np.uint64) if int(mbox[rank, 1]) else None
 
     times = {"decode": [], "chain": [], "stages": []}
 
@@ -312,6 +340,7 @@ def run_c5(args):
         assert st == 0, f"shard declined: {st}"
         times["decode"].append(ctx.last_kernel_ms()["unpack_ms"])
         times["stages"].append(ctx.last_stage_ms())
+        seq[0] += 1
         dg = shard.relay_digest(rank, world, lambda a: ctx.blocks_digest(a, pos, total, d_out, stream), send, recv)
         times["chain"].append(ctx.last_chain_ms())
         return dg
@@ -459,8 +488,8 @@ def run_c5(args):
             line["cpu_baseline"] = {"value": len(plain) / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": kind,
                                     "sample": f"first {nb} blocks ({len(plain) >> 20} MiB) of the same entry through zpack_read_file, "
                                               "1 thread (one entry = one LZ4F_decompress loop + one XXH3 pass)"}
-        print(json.dumps(line))
-    if world > 1:
+        _emit(args, line)
+    if world > 1 and not getattr(args, "nested", False):
         dist.destroy_process_group()
     ctx.close()
 
@@ -477,12 +506,24 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     wl = WORKLOADS[args.workload]
-    n_per_gpu = args.entries or wl["entries"]  # weak scaling: every GPU unpacks its own shard of `entries` entries
+    # Strong scaling (the default; BASELINE config 2: ONE archive of `entries` entries at 1 / 2 / 4 / 8 GPUs): the archive's
+    # entries are cut into `world` contiguous runs balanced by decoded bytes (zpack_b200/shard.py, the rule of
+    # zpb_group_partition) and rank r unpacks run r — it builds and holds only that run's share of the archive.
+    # --scaling weak: every rank unpacks its own archive of `entries` entries (the round-1 measurement).
+    n_total = args.entries or wl["entries"]
+    strong = args.scaling == "strong"
+    if strong:
+        from zpack_b200 import shard
+        lo_e, hi_e = shard.partition(np.full(n_total, ENTRY_SIZE), world)[rank]
+        n_per_gpu, first_entry = hi_e - lo_e, lo_e
+    else:
+        n_per_gpu, first_entry = n_total, rank * n_total
     t_prep = time.time()
-    arch = build_archive(n_per_gpu, ENTRY_SIZE, first=rank * n_per_gpu, independent=args.independent,
+    arch = build_archive(n_per_gpu, ENTRY_SIZE, first=first_entry, independent=args.independent,
                          workers=max(1, (os.cpu_count() or 1) // world), method=wl["method"])
     d = container.parse(arch)
     entries = d.entries()
@@ -568,30 +609,54 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_verify = (time.perf_counter() - t0) / args.e2e_steps
         assert (st3 == 0).all() and np.array_equal(dg3, d.hash)
+        # what the link itself allows on this box, measured here: pinned D2H and H2D of up to 1 GiB (CUDA events)
+        nb = min(out_size, len(arch), 1 << 30)
+        pcie = {}
+        for name, dst, src in (("d2h_GBps", h_out[:nb], d_out[:nb]), ("h2d_GBps", d_out[:nb], h_out[:nb])):
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                dst.copy_(src, non_blocking=True)
+            b.record()
+            torch.cuda.synchronize()
+            pcie[name] = 3 * nb / (a.elapsed_time(b) * 1e-3) / 1e9
     clocks = sampler.stop() if rank == 0 else None
 
     stages = {k: float(np.mean([s[k] for s in stage_ms])) for k in stage_ms[0]}
     t = torch.tensor([ms_total, float(np.mean(kernel_ms)), e2e or 0.0, stages[wl["stage"]], e2e_verify or 0.0],
                      dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(uncomp_bytes), float(comp_bytes), float(n_per_gpu), float(stages.get("parse_ms", 0.0)),
+                        float(stages.get("exec_ms", 0.0))], dtype=torch.float64, device="cuda")
+    per_rank = [tot.clone() for _ in range(world)]
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_gather(per_rank, tot)
     ms_total, all_kern_ms, e2e_s, kern_ms, e2e_verify_s = [float(x) for x in t.cpu()]
+    per_rank = [[float(v) for v in x.cpu()] for x in per_rank]
+    job_uncomp = sum(x[0] for x in per_rank)       # what ALL ranks decoded per step
+    job_comp = sum(x[1] for x in per_rank)
 
     if rank == 0:
         peak, peak_src = peaks()
         ms_step = ms_total / args.steps
-        value = world * uncomp_bytes / (ms_step * 1e-3) / 1e9
-        algo_bytes = comp_bytes + uncomp_bytes
+        value = job_uncomp / (ms_step * 1e-3) / 1e9
+        algo_bytes = comp_bytes + uncomp_bytes     # this rank's launch (the roofline is per kernel launch)
         achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
         cores = os.cpu_count() or 1
         line = {"metric": wl["metric"], "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": f"{wl['what']}, {n_per_gpu} entries x 128 KiB per GPU "
-                                       f"({uncomp_bytes / 2**30:.2f} GiB uncompressed, ratio {uncomp_bytes / comp_bytes:.3f}), zpk-synth-v1"
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": f"{wl['what']}, " + (f"ONE archive of {n_total} entries x 128 KiB cut into {world} contiguous runs "
+                                                            f"({job_uncomp / 2**30:.2f} GiB uncompressed in all, ratio {job_uncomp / job_comp:.3f})" if strong else
+                                                            f"{n_per_gpu} entries x 128 KiB per GPU ({uncomp_bytes / 2**30:.2f} GiB uncompressed each, "
+                                                            f"ratio {uncomp_bytes / comp_bytes:.3f})") + ", zpk-synth-v1"
                                        + (f", {'independent' if args.independent else 'reference-format linked'} 64 KB blocks"
                                           if wl["method"] == 2 else ""),
-                           "entries_per_gpu": n_per_gpu, "entry_bytes": ENTRY_SIZE, "sharding": f"entries x{world}, no collective",
+                           "entries_per_gpu": n_per_gpu, "entries_per_rank": [int(x[2]) for x in per_rank], "entry_bytes": ENTRY_SIZE,
+                           "sharding": f"entries x{world}, contiguous runs balanced by decoded bytes, no collective",
+                           "per_rank_parse_exec_ms": [[round(x[3], 3), round(x[4], 3)] for x in per_rank],
                            "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)",
                            "pipeline": ("scan -> parse || exec (3 grids sharing one work queue; the first starts with the parse kernel) -> general fallback, 6 launches per step" if wl["method"] == 2
                                         else "scan -> zstd_unpack_kernel (warp per entry), 5 launches per step"),
@@ -610,11 +675,14 @@ def run_ours(args):
                                             f"whose sum is {float(np.mean(kernel_ms_serial)):.3f} ms"},
                 "gpu_launches": int(launches), "clocks": clocks}
         if args.e2e:
-            line["e2e"] = {"value": world * uncomp_bytes / e2e_s / 1e9, "unit": "GB/s",
+            line["e2e"] = {"value": job_uncomp / e2e_s / 1e9, "unit": "GB/s",
                            "h2d_bytes_per_step": comp_bytes + entries.nbytes, "d2h_bytes_per_step": uncomp_bytes + 12 * len(entries),
                            "how": "zpb_unpack_host, pinned host buffers: chunked H2D / kernels / D2H of every decoded byte, "
-                                  "overlapped on 6 streams; PCIe-bound (D2H of every decoded byte)"}
-            line["e2e_verify_only"] = {"value": world * uncomp_bytes / e2e_verify_s / 1e9, "unit": "GB/s",
+                                  "overlapped on 6 streams; PCIe-bound (D2H of every decoded byte)",
+                           # the link's own ceiling for this step on rank 0's GPU: every decoded byte has to cross it
+                           "pcie_probe": {k: round(v, 2) for k, v in pcie.items()},
+                           "pcie_ceiling_GBps_per_gpu": round(uncomp_bytes / ((uncomp_bytes + 12 * len(entries)) / (pcie["d2h_GBps"] * 1e9)) / 1e9, 2)}
+            line["e2e_verify_only"] = {"value": job_uncomp / e2e_verify_s / 1e9, "unit": "GB/s",
                                        "h2d_bytes_per_step": comp_bytes + entries.nbytes, "d2h_bytes_per_step": 12 * len(entries),
                                        "how": "same call with ZPB_F_DISCARD (the `zpack t` integrity test): status + digest come back, "
                                               "decoded bytes stay on the device"}
@@ -625,8 +693,8 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": "GB/s", "cores": cores, "kind": kind,
                                     "sample": f"first {n_s} entries of the same archive, {cores} threads; "
                                               f"single-thread: {v1:.3f} GB/s"}
-        print(json.dumps(line))
-    if world > 1:
+        _emit(args, line)
+    if world > 1 and not getattr(args, "nested", False):
         dist.destroy_process_group()
     ctx.close()
 
@@ -709,7 +777,8 @@ def run_c3(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl = WORKLOADS["c3"]
     n = args.entries or wl["entries"]
     size = ENTRY_SIZE
@@ -824,8 +893,8 @@ def run_c3(args):
             line["cpu_baseline"] = {"value": v, "unit": "GB/s", "cores": cores, "kind": kind, "ratio": ratio,
                                     "sample": f"first {min(n, args.ref_entries)} files, {cores} independent writers "
                                               f"(zpack_write_archive, level 0); single writer: {v1:.3f} GB/s"}
-        print(json.dumps(line))
-    if world > 1:
+        _emit(args, line)
+    if world > 1 and not getattr(args, "nested", False):
         dist.destroy_process_group()
     ctx.close()
 
@@ -853,16 +922,44 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-entries", type=int, default=32768)
-    ap.add_argument("--ref-entries", type=int, default=16384)
+    ap.add_argument("--ref-entries", type=int, default=0, help="entries of the reference arm's archive (default: the workload's own count)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): ONE archive cut over the ranks; weak: one archive of --entries per rank")
+    ap.add_argument("--no-configs", dest="configs", action="store_false",
+                    help="skip the C3 / C4 / C5 block that the default single-GPU C2 line carries")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "c5":
-        run_c5(args)
-    elif args.workload == "c3":
-        run_c3(args)
-    else:
-        run_ours(args)
+        return
+    runner = {"c5": run_c5, "c3": run_c3}.get(args.workload, run_ours)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not (args.workload == "c2" and args.configs and world == 1 and not args.entries):
+        runner(args)
+        return
+    # The default single-GPU line: C2 (the configuration the metric is quoted on), and — measured in this same process
+    # after C2's timed region, at reduced sizes so that the whole run stays within minutes — the other BASELINE
+    # configurations the GPU path covers, so that the driver's record holds them too.
+    import copy
+    args.nested = True
+    runner(args)
+    line = args.result
+    block = {}
+    for key, fn, n_small, what in (("c3", run_c3, 16384, "LZ4 pack, 16384 files x 128 KiB (2 GiB)"),
+                                   ("c4", run_ours, 8192, "zstd level-3 unpack + verify, 8192 entries x 128 KiB (1 GiB), frames written by the reference"),
+                                   ("c5", run_c5, 16384, "one LZ4 entry of 16384 independent 64 KB blocks (1 GiB), block-sharded read")):
+        sub = copy.copy(args)
+        sub.workload, sub.entries, sub.steps, sub.warmup, sub.no_cpu, sub.e2e_steps, sub.result = key, n_small, 5, 3, True, 2, None
+        try:
+            fn(sub)
+            r = sub.result
+            block[key] = {"workload": what, "metric": r["metric"], "value": r["value"], "unit": r["unit"], "ms_per_step": r["ms_per_step"],
+                          "roofline_frac": r.get("roofline", {}).get("frac"), "kernel": r.get("roofline", {}).get("kernel"),
+                          "e2e": (r.get("e2e") or {}).get("value"), "gpu_launches": r.get("gpu_launches"),
+                          **({"ratio": r["config"].get("ratio")} if isinstance(r.get("config"), dict) and "ratio" in r["config"] else {})}
+        except Exception as ex:   # a configuration that cannot run here (e.g. no oracle/_ref for the zstd archive) says so
+            block[key] = {"workload": what, "unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+    line["configs"] = block
+    print(json.dumps(line))
 
 
 if __name__ == "__main__":

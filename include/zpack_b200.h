@@ -199,6 +199,30 @@ int zpb_set_fast_path(zpb_ctx *ctx, int enabled);
  * 0: scan, parse, execute back to back on one stream — what per-kernel timings (zpb_last_stage_ms) are meaningful for. */
 int zpb_set_overlap(zpb_ctx *ctx, int enabled);
 
+/* several GPUs of one box, one call ------------------------------------------------------------ */
+/* What a multi-GPU caller of the reference's read / write loops binds: the per-entry loop of a batch reader
+ * (zpack_read_file over the entries of an archive, /root/reference/lib/zpack_read.c:326-471, which the reference allows from
+ * several threads with one context each, lib/zpack.h:335-341) and zpack_write_files (lib/zpack_write.c:280-343), spread over
+ * the GPUs of the box.  Entries / files are independent: a batch is cut into contiguous runs in archive order, balanced by
+ * decoded bytes, one run per device, each driven from its own host thread through zpb_unpack_host / zpb_pack_host.
+ * No collective, no peer traffic (there is nothing to reduce); every device copies only the archive range it needs. */
+typedef struct zpb_group zpb_group;
+zpb_group  *zpb_group_create(const int *devices, int n);        /* devices == NULL or n <= 0: every visible device */
+void        zpb_group_destroy(zpb_group *g);
+int         zpb_group_size(const zpb_group *g);
+zpb_ctx    *zpb_group_ctx(zpb_group *g, int k);                  /* the k-th device's context (tuning, timings) */
+const char *zpb_group_last_error(const zpb_group *g);
+/* order[n]: the entries in archive order; cuts[world + 1]: device k takes order[cuts[k] .. cuts[k+1]) */
+int zpb_group_partition(const zpb_entry *entries, uint64_t n, int world, uint64_t *order, uint64_t *cuts);
+int zpb_group_unpack_host(zpb_group *g, const uint8_t *h_archive, uint64_t archive_size, uint8_t *h_out,
+                          uint64_t out_size, const zpb_entry *entries, uint64_t n, int32_t *status, uint64_t *digest);
+int zpb_group_pack_host(zpb_group *g, const uint8_t *h_in, uint64_t in_size, uint8_t *h_out, uint64_t out_size,
+                        const zpb_file *files, uint64_t n, uint64_t *comp_size, uint64_t *digest, int32_t *status);
+int zpb_group_last_ms(const zpb_group *g, float *ms, int cap);   /* wall time of each device's share of the last call */
+/* pinned host memory for the *_host entry points (pageable buffers make their copies synchronous) */
+void *zpb_host_alloc(uint64_t bytes);
+void  zpb_host_free(void *p);
+
 /* tuning knobs: lanes per dependency chain (4, 8, 16, 32; 0 = keep) and resident CTAs per SM
  * (0 = occupancy API, -1 = keep).  Defaults can also come from ZPB_GROUP / ZPB_CTAS_PER_SM. */
 int zpb_set_tuning(zpb_ctx *ctx, int group_lanes, int ctas_per_sm);

@@ -210,6 +210,18 @@ def zstd_compress_ref(data, level: int = 3) -> np.ndarray:
     return out[:n].copy()
 
 
+def zstd_decompress_ref(comp, size: int) -> np.ndarray:
+    """ZSTD_decompress of the unmodified reference (zstd 1.5.0)."""
+    a = np.ascontiguousarray(np.frombuffer(comp, np.uint8) if not isinstance(comp, np.ndarray) else comp)
+    lib = ref()
+    lib.ZSTD_decompress.restype = C.c_size_t
+    lib.ZSTD_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    out = np.zeros(max(size, 1), np.uint8)
+    n = lib.ZSTD_decompress(_u8(out), size, _u8(a), len(a))
+    assert not lib.ZSTD_isError(n), "reference zstd decoder rejects the frame"
+    return out[:n].copy()
+
+
 def write_archive_ref(names, buffers, method: int, level: int) -> np.ndarray:
     """zpack_write_archive into a heap writer (lib/zpack_write.c:818) — the reference's own packer."""
     lib = ref()

@@ -29,3 +29,21 @@ long ref_unpack_range(void *reader, uint8_t *entries, size_t first, size_t end, 
     if (bytes_done) *bytes_done = total;
     return bad;
 }
+
+/* The same, BASELINE.md §4's shape: entry i is decoded into ITS OWN slice of one preallocated output,
+ * out_base + i * slot_bytes (so the decoded bytes really land in host DRAM, like the GPU arm's D2H target). */
+long ref_unpack_slices(void *reader, uint8_t *entries, size_t first, size_t end, size_t stride,
+                       uint8_t *out_base, size_t slot_bytes, int method, uint64_t *bytes_done) {
+    void *dctx = zpack_create_dctx(method);
+    long bad = 0;
+    uint64_t total = 0;
+    for (size_t i = first; i < end; i += stride) {
+        uint8_t *e = entries + 48 * i;
+        int rc = zpack_read_file(reader, e, out_base + i * slot_bytes, slot_bytes, dctx);
+        if (rc != 0) ++bad;
+        total += *(uint64_t *)(e + 24); /* uncomp_size */
+    }
+    zpack_free_dctx(method, dctx);
+    if (bytes_done) *bytes_done = total;
+    return bad;
+}

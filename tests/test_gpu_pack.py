@@ -115,7 +115,23 @@ def test_none_method_and_error_statuses(gpu_ctx, oracle):
     assert (status == 0).all()
     for b, fr, dg in zip(bufs, frames, digest):
         assert np.array_equal(fr, b) and int(dg) == oracle.xxh3_port(b)
-    _, _, _, _, status = _pack(gpu_ctx, [1000], method=1)          # zstd compressor: not built
+    # zstd: valid frames of Raw_Blocks (the entropy-coding compressor is SURVEY §8(f) row 3); the unmodified reference
+    # decoder and our GPU decoder must both read them back
+    sizes = [0, 1, 1000, 131072, 131073, 400000]
+    bufs, frames, comp, digest, status = _pack(gpu_ctx, sizes, method=1)
+    assert (status == 0).all(), status
+    for b, fr, dg in zip(bufs, frames, digest):
+        assert int(dg) == oracle.xxh3_port(b)
+        rc, got = oracle.zstd_decode_port(fr, len(b))
+        assert rc == 0 and np.array_equal(got[:len(b)], b)
+        if oracle.have_ref():
+            assert np.array_equal(oracle.zstd_decompress_ref(fr, len(b)), b)
+    arch = container.assemble([f"z{i}" for i in range(len(bufs))], frames, [len(b) for b in bufs], digest, [1] * len(bufs))
+    e = container.parse(arch).entries()
+    out = np.zeros(int((e["dst_off"] + e["dst_cap"]).max()) + 16, np.uint8)
+    st, dg2 = gpu_ctx.unpack_host(arch, len(arch), out, len(out), e)
+    assert (st == 0).all(), st
+    _, _, _, _, status = _pack(gpu_ctx, [1000], method=2, level=9)   # LZ4 HC levels: not built, never a silent downgrade
     assert list(status) == [24]
     _, _, _, _, status = _pack(gpu_ctx, [1000], method=9)
     assert list(status) == [19]

@@ -67,3 +67,26 @@ def test_two_rank_gloo_sharding():
     [p.join(60) for p in ps]
     assert [(r[1], r[2]) for r in res] == [(0, 500), (500, 1000)]
     assert all(r[3] == 11.0 and r[4] == 1000.0 for r in res)          # max-over-ranks time, whole-job count
+
+
+def test_c_abi_partition_equals_the_python_rule():
+    """zpb_group_partition (C++, what libzpack.so's batched read uses) against shard.partition on the same sizes:
+    contiguous, covering, and balanced to within one entry of the ideal split."""
+    from zpack_b200 import lib as zlib
+    rng = np.random.default_rng(7)
+    for n, world in ((0, 3), (1, 4), (17, 2), (1000, 8), (65536, 8), (5, 8)):
+        e = np.zeros(n, zlib.Entry)
+        e["uncomp_size"] = rng.integers(0, 300000, n)
+        e["comp_size"] = np.maximum(1, e["uncomp_size"] // 2)
+        e["src_off"] = 10 + np.concatenate([[0], np.cumsum(e["comp_size"])[:-1]]) if n else 0
+        perm = rng.permutation(n)                       # callers need not pass archive order
+        order, cuts = zlib.group_partition(np.ascontiguousarray(e[perm]), world)
+        assert cuts[0] == 0 and cuts[-1] == n and (np.diff(cuts.astype(np.int64)) >= 0).all()
+        assert sorted(order.tolist()) == list(range(n))
+        assert (np.diff(e[perm]["src_off"][order.astype(np.int64)].astype(np.int64)) >= 0).all()   # archive order
+        if n >= world * 4:
+            total = float(e["uncomp_size"].sum())
+            sizes = e[perm]["uncomp_size"][order.astype(np.int64)]
+            for k in range(world):
+                share = float(sizes[int(cuts[k]):int(cuts[k + 1])].sum())
+                assert abs(share - total / world) <= 300000 + 1, (n, world, k, share, total / world)

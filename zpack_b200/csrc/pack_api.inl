@@ -9,6 +9,8 @@ extern "C" uint64_t zpb_pack_bound(uint32_t method, uint64_t size) {
     // (same role as LZ4F_compressBound at lib/zpack_write.c:141; an empty file is 11 bytes, as in the reference)
     if (method == ZPB_METHOD_LZ4) return 7 + 4 * ((size + 65535) / 65536) + size + 4;
     if (method == ZPB_METHOD_NONE) return size;
+    // zstd: frame header 14 + per 128 KB block a 3-byte header + raw payload (pack_kernel.cuh writes Raw_Blocks)
+    if (method == ZPB_METHOD_ZSTD) return 14 + 3 * (size ? (size + 131071) / 131072 : 1) + size;
     return 0;
 }
 

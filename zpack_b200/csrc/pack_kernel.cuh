@@ -197,6 +197,7 @@ lz4_pack_kernel(const u8 *__restrict__ in, u64 in_size, u8 *out, u64 out_size, c
         } else if (f.method == ZPB_METHOD_LZ4) {
             const u64 nblocks = (f.size + 65535) >> 16;
             if (f.dst_cap < 7 + 4 * nblocks + f.size + 4) st = ZPB_ST_COMPRESS_FAILED;  // LZ4F_compressBound role
+            else if (f.level >= 3) st = ST_NOT_AVAILABLE;   // lz4frame.c:799-807 selects LZ4 HC from level 3 on: not built; never a silent downgrade
             else {
                 const u8 *src = in + f.src_off;
                 u8 *dst = out + f.dst_off;
@@ -217,6 +218,7 @@ lz4_pack_kernel(const u8 *__restrict__ in, u64 in_size, u8 *out, u64 out_size, c
                     u32 c = pk_compress_block(bsrc, blen, dst + op + 4, blen - 1, table, accel, lane);
                     u32 hdr = c;
                     if (c == 0) {                                       // stored (lz4frame.c:750-754)
+                        __syncwarp();                                   // the abandoned attempt's bytes sit where the copy writes
                         group_copy<32>(g, dst + op + 4, bsrc, blen);
                         c = blen;
                         hdr = blen | 0x80000000u;
@@ -233,7 +235,34 @@ lz4_pack_kernel(const u8 *__restrict__ in, u64 in_size, u8 *out, u64 out_size, c
                 csz = op;
             }
         } else if (f.method == ZPB_METHOD_ZSTD) {
-            st = ST_NOT_AVAILABLE;                                     // zstd compressor: SURVEY §8(f) row 3
+            // A VALID zstd frame without entropy coding: Raw_Blocks of up to 128 KB (zstd_compression_format.md:320-404;
+            // what ZSTD_compress itself emits for incompressible input, zstd_compress.c ZSTD_noCompressBlock).  It keeps the
+            // writer usable for ZPACK_COMPRESSION_ZSTD (the reference reader and CLI accept the archives) until the dfast +
+            // FSE / Huffman encoder of SURVEY §8(f) row 3 exists; the ratio is 1.0 and is reported as such.
+            const u64 nblocks = f.size ? (f.size + 131071) >> 17 : 1;
+            if (f.dst_cap < 14 + 3 * nblocks + f.size) st = ZPB_ST_COMPRESS_FAILED;
+            else {
+                const u8 *src = in + f.src_off;
+                u8 *dst = out + f.dst_off;
+                if (lane == 0) {
+                    // magic; FHD: 8-byte frame content size, no single-segment, no checksum, no dictionary; window 128 KB
+                    dst[0] = 0x28; dst[1] = 0xB5; dst[2] = 0x2F; dst[3] = 0xFD; dst[4] = 0xC0; dst[5] = 0x38;
+                    for (int k = 0; k < 8; ++k) dst[6 + k] = (u8)(f.size >> (8 * k));
+                }
+                u64 op = 14;
+                Xxh3Stream<32> hs;
+                hs.init(src, f.size, g);
+                for (u64 b = 0; b < nblocks; ++b) {
+                    const u32 blen = (u32)(f.size - (b << 17) < 131072 ? f.size - (b << 17) : 131072);
+                    const u32 hdr = (b + 1 == nblocks ? 1u : 0u) | (blen << 3);      // last | Raw_Block | size
+                    if (lane == 0) { dst[op] = (u8)hdr; dst[op + 1] = (u8)(hdr >> 8); dst[op + 2] = (u8)(hdr >> 16); }
+                    group_copy<32>(g, dst + op + 3, src + (b << 17), blen);
+                    op += 3 + blen;
+                    hs.advance((b << 17) + blen, g);
+                }
+                dg = hs.finish(g);
+                csz = op;
+            }
         } else {
             st = ST_METHOD_INVALID;
         }

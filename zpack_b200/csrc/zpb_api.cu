@@ -726,3 +726,6 @@ extern "C" int zpb_xxh3_host(zpb_ctx *ctx, const uint8_t *h_data, uint64_t lengt
 
 // ------------------------------------------------------------------------------------ pack
 #include "pack_api.inl"
+
+// ------------------------------------------------------------------------------------ several GPUs, one call
+#include "group_api.inl"

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <new>
 #include <stdexcept>
@@ -31,15 +32,56 @@ inline void put16(zpack_u8 *p, zpack_u16 v) { p[0] = (zpack_u8)v; p[1] = (zpack_
 inline void put32(zpack_u8 *p, zpack_u32 v) { for (int i = 0; i < 4; ++i) p[i] = (zpack_u8)(v >> (8 * i)); }
 inline void put64(zpack_u8 *p, zpack_u64 v) { for (int i = 0; i < 8; ++i) p[i] = (zpack_u8)(v >> (8 * i)); }
 
-// ---- the process-wide GPU context (calls are serialised; buffer-mode readers stay thread-safe)
-std::mutex g_gpu_lock;
-zpb_ctx *g_gpu = nullptr;
-zpb_ctx *gpu() {
-    if (!g_gpu) {
-        const char *dev = getenv("ZPACK_GPU_DEVICE");
-        g_gpu = zpb_create(dev ? atoi(dev) : 0);
+// ---- GPU contexts.  Per-entry calls (zpack_read_file, the stream calls, zpack_write_files) use a context that belongs to
+// the calling thread — the reference lets a buffer-mode reader be used from several threads with one decompression
+// context each (lib/zpack.h:335-341), and nothing here serialises them; threads are dealt round-robin over the visible
+// GPUs (ZPACK_GPU_DEVICE pins one).  The batched read uses every GPU at once through one process-wide group.
+std::atomic<int> g_next_device{0};
+struct ThreadCtx {
+    zpb_ctx *c = nullptr;
+    zpack_u8 *pin_in = nullptr, *pin_out = nullptr;     // pinned staging of zpack_write_files
+    size_t pin_in_cap = 0, pin_out_cap = 0;
+    ~ThreadCtx() {
+        zpb_host_free(pin_in); zpb_host_free(pin_out);
+        if (c) zpb_destroy(c);
     }
-    return g_gpu;
+    bool ensure_pins(size_t in_bytes, size_t out_bytes) {
+        if (in_bytes > pin_in_cap) { zpb_host_free(pin_in); pin_in = (zpack_u8 *)zpb_host_alloc(in_bytes); pin_in_cap = pin_in ? in_bytes : 0; }
+        if (out_bytes > pin_out_cap) { zpb_host_free(pin_out); pin_out = (zpack_u8 *)zpb_host_alloc(out_bytes); pin_out_cap = pin_out ? out_bytes : 0; }
+        return pin_in && pin_out;
+    }
+};
+thread_local ThreadCtx t_ctx;
+zpb_ctx *gpu() {
+    if (!t_ctx.c) {
+        const char *dev = getenv("ZPACK_GPU_DEVICE");
+        if (dev) t_ctx.c = zpb_create(atoi(dev));
+        else {
+            // round-robin over the devices that exist: probe upwards from the next index, wrap to 0 on failure
+            const int k = g_next_device.fetch_add(1);
+            static std::atomic<int> ndev{0};
+            int n = ndev.load();
+            if (n == 0) {            // first caller counts the devices by creating the group once
+                zpb_group *g = zpb_group_create(nullptr, 0);
+                n = g ? zpb_group_size(g) : 1;
+                zpb_group_destroy(g);
+                ndev.store(n > 0 ? n : 1);
+                n = ndev.load();
+            }
+            t_ctx.c = zpb_create(k % n);
+        }
+    }
+    return t_ctx.c;
+}
+std::mutex g_group_lock;
+zpb_group *g_group = nullptr;
+zpb_group *gpu_group() {      // call with g_group_lock held
+    if (!g_group) {
+        const char *dev = getenv("ZPACK_GPU_DEVICE");
+        if (dev) { int d = atoi(dev); g_group = zpb_group_create(&d, 1); }
+        else g_group = zpb_group_create(nullptr, 0);
+    }
+    return g_group;
 }
 int g_ctx_token;  // zpack_create_cctx / _dctx hand out its address: contexts are opaque to callers
 
@@ -108,7 +150,6 @@ bool known_method(int m) { return m == ZPACK_COMPRESSION_NONE || m == ZPACK_COMP
 // One entry through the GPU: compressed bytes `comp` -> dst[0..max_size).  Returns an enum zpack_result.
 int gpu_unpack_one(const zpack_u8 *comp, zpack_u64 comp_size, zpack_u8 *dst, size_t max_size, const zpack_file_entry *e,
                    size_t *last_return) {
-    std::lock_guard<std::mutex> lk(g_gpu_lock);
     zpb_ctx *g = gpu();
     if (!g) return ZPACK_ERROR_MALLOC_FAILED;
     zpb_entry d;
@@ -297,22 +338,45 @@ int zpack_read_file(zpack_reader *r, zpack_file_entry *e, zpack_u8 *buffer, size
     return gpu_unpack_one(r->buffer + e->offset, e->comp_size, buffer, max_size, e, &r->last_return);   // :345-346
 }
 
+// The batched read (the extension SURVEY F7 asks for: the reference's API reads one entry per call): every entry of the
+// batch decoded and verified by ONE call that uses every visible GPU (zpb_group_unpack_host).  Buffer-mode readers hand
+// their archive over as it is; file-mode readers have the entries' compressed bytes read into one staging buffer first.
 int zpack_read_files(zpack_reader *r, zpack_file_entry *entries, zpack_u64 n, zpack_u8 *out, zpack_u64 out_size,
                      const zpack_u64 *dst_off, const zpack_u64 *dst_cap, int *status) {
-    if (!r->buffer) return ZPACK_ERROR_ARCHIVE_NOT_LOADED;        // batch reads want the archive in memory
-    std::vector<zpb_entry> d((size_t)n);
-    std::vector<int32_t> st((size_t)n, 0);
+    if (!r->buffer && !r->file) return ZPACK_ERROR_ARCHIVE_NOT_LOADED;
+    std::vector<zpb_entry> d;
+    std::vector<int32_t> st;
+    std::vector<zpack_u8> staged;
+    try {
+        d.resize((size_t)n); st.assign((size_t)n, 0);
+        if (!r->buffer) {
+            zpack_u64 total = 0;
+            for (zpack_u64 i = 0; i < n; ++i)
+                if (entries[i].comp_size && entries[i].offset < r->file_size && entries[i].comp_size < r->file_size - entries[i].offset)
+                    total += (entries[i].comp_size + 15) & ~15ull;
+            staged.resize((size_t)total + 16);
+        }
+    } catch (const std::exception &) { return ZPACK_ERROR_MALLOC_FAILED; }
+    zpack_u64 pos = 0;
     for (zpack_u64 i = 0; i < n; ++i) {
         memset(&d[i], 0, sizeof(zpb_entry));
         const zpack_file_entry &e = entries[i];
         d[i].src_off = e.offset; d[i].comp_size = e.comp_size; d[i].dst_off = dst_off[i]; d[i].dst_cap = dst_cap[i];
         d[i].uncomp_size = e.uncomp_size; d[i].hash = e.hash; d[i].method = e.comp_method;
-        if (e.comp_size && (e.offset >= r->file_size || e.comp_size >= r->file_size - e.offset)) d[i].src_off = ~0ull;   // -> FILE_OFFSET_INVALID
+        if (e.comp_size && (e.offset >= r->file_size || e.comp_size >= r->file_size - e.offset)) { d[i].src_off = ~0ull; continue; }   // -> FILE_OFFSET_INVALID
+        if (!r->buffer && e.comp_size) {
+            int err;
+            if (!read_at(r->file, e.offset, staged.data() + pos, (size_t)e.comp_size, &err)) return err;
+            d[i].src_off = pos;
+            pos += (e.comp_size + 15) & ~15ull;
+        }
     }
-    std::lock_guard<std::mutex> lk(g_gpu_lock);
-    zpb_ctx *g = gpu();
+    std::lock_guard<std::mutex> lk(g_group_lock);
+    zpb_group *g = gpu_group();
     if (!g) return ZPACK_ERROR_MALLOC_FAILED;
-    if (zpb_unpack_host(g, r->buffer, r->file_size, out, out_size, d.data(), n, st.data(), nullptr) != ZPB_OK)
+    const zpack_u8 *arch = r->buffer ? r->buffer : staged.data();
+    const zpack_u64 asz = r->buffer ? r->file_size : staged.size();
+    if (zpb_group_unpack_host(g, arch, asz, out, out_size, d.data(), n, st.data(), nullptr) != ZPB_OK)
         return ZPACK_ERROR_DECOMPRESS_FAILED;
     int worst = ZPACK_OK;
     for (zpack_u64 i = 0; i < n; ++i) {
@@ -457,7 +521,6 @@ int zpack_write_files(zpack_writer *w, zpack_file *files, zpack_u64 file_count) 
         while (j < file_count && (j == i || in_bytes + files[j].size <= (256ull << 20))) {
             const int m = files[j].options->method;
             if (!known_method(m)) { if (j == i) return ZPACK_ERROR_COMP_METHOD_INVALID; break; }
-            if (m == ZPACK_COMPRESSION_ZSTD) { if (j == i) return ZPACK_ERROR_NOT_AVAILABLE; break; }
             zpb_file f;
             memset(&f, 0, sizeof f);
             f.src_off = in_bytes; f.size = files[j].size;
@@ -469,21 +532,17 @@ int zpack_write_files(zpack_writer *w, zpack_file *files, zpack_u64 file_count) 
             ++j;
         }
         const size_t n = d.size();
-        std::vector<zpack_u8> in, out;
         std::vector<uint64_t> csz(n), dig(n);
         std::vector<int32_t> st(n);
-        try { in.resize((size_t)in_bytes + 16); out.resize((size_t)out_bytes + 16); }
-        catch (const std::exception &) { return ZPACK_ERROR_MALLOC_FAILED; }
+        zpb_ctx *g = gpu();
+        if (!g) return ZPACK_ERROR_MALLOC_FAILED;
+        // pinned staging owned by the calling thread (pageable buffers would make every copy of zpb_pack_host synchronous)
+        if (!t_ctx.ensure_pins((size_t)in_bytes + 16, (size_t)out_bytes + 16)) return ZPACK_ERROR_MALLOC_FAILED;
+        zpack_u8 *in = t_ctx.pin_in, *out = t_ctx.pin_out;
         for (size_t k = 0; k < n; ++k)
-            if (files[i + k].size) memcpy(in.data() + d[k].src_off, files[i + k].buffer, (size_t)files[i + k].size);
-        {
-            std::lock_guard<std::mutex> lk(g_gpu_lock);
-            zpb_ctx *g = gpu();
-            if (!g) return ZPACK_ERROR_MALLOC_FAILED;
-            if (zpb_pack_host(g, in.data(), in.size(), out.data(), out.size(), d.data(), n, csz.data(), dig.data(),
-                              st.data()) != ZPB_OK)
-                return ZPACK_ERROR_COMPRESS_FAILED;
-        }
+            if (files[i + k].size) memcpy(in + d[k].src_off, files[i + k].buffer, (size_t)files[i + k].size);
+        if (zpb_pack_host(g, in, in_bytes + 16, out, out_bytes + 16, d.data(), n, csz.data(), dig.data(), st.data()) != ZPB_OK)
+            return ZPACK_ERROR_COMPRESS_FAILED;
         for (size_t k = 0; k < n; ++k) {
             w->last_return = (size_t)st[k];
             if (st[k]) return st[k];                       // files before it are already in the archive, as in the reference
@@ -495,7 +554,7 @@ int zpack_write_files(zpack_writer *w, zpack_file *files, zpack_u64 file_count) 
             e->uncomp_size = files[i + k].size;
             e->hash = dig[k];                              // XXH3-64 of the input, fused into the pack kernel
             e->comp_method = (zpack_u8)files[i + k].options->method;
-            int rc = sink_append(w, out.data() + d[k].dst_off, (size_t)csz[k]);
+            int rc = sink_append(w, out + d[k].dst_off, (size_t)csz[k]);
             if (rc) return rc;
         }
         i = j;
@@ -537,7 +596,6 @@ int zpack_write_files_from_archive(zpack_writer *w, zpack_reader *r, zpack_file_
 int zpack_write_file_stream(zpack_writer *w, zpack_compress_options *opt, zpack_stream *s, void *) {
     if (!s->next_in || !s->next_out || !s->avail_out) return ZPACK_ERROR_STREAM_INVALID;
     if (!known_method(opt->method)) return ZPACK_ERROR_COMP_METHOD_INVALID;
-    if (opt->method == ZPACK_COMPRESSION_ZSTD) return ZPACK_ERROR_NOT_AVAILABLE;
     if (!w->file && !w->buffer) return ZPACK_ERROR_WRITER_NOT_OPENED;
     StreamState *st = state_of(s);
     if (!st) return ZPACK_ERROR_STREAM_INVALID;
@@ -552,7 +610,6 @@ int zpack_write_file_stream(zpack_writer *w, zpack_compress_options *opt, zpack_
 int zpack_write_file_stream_end(zpack_writer *w, char *filename, zpack_compress_options *opt, zpack_stream *s, void *) {
     if (!s->next_out || !s->avail_out) return ZPACK_ERROR_STREAM_INVALID;
     if (!known_method(opt->method)) return ZPACK_ERROR_COMP_METHOD_INVALID;
-    if (opt->method == ZPACK_COMPRESSION_ZSTD) return ZPACK_ERROR_NOT_AVAILABLE;
     StreamState *st = state_of(s);
     if (!st) return ZPACK_ERROR_STREAM_INVALID;
     if (s->total_in == 0) st->data.clear();

@@ -101,8 +101,84 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.zpb_blocks_digest.argtypes = [vp, vp, vp, u64, u64, vp, u64p, vp]
     lib.zpb_last_chain_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.zpb_unpack_entry_blocks_host.argtypes = [vp, vp, u64, vp, u64, u64, u64, C.c_uint32, i32p, u64p]
+    lib.zpb_group_create.restype = vp
+    lib.zpb_group_create.argtypes = [vp, C.c_int]
+    lib.zpb_group_destroy.argtypes = [vp]
+    lib.zpb_group_size.argtypes = [vp]
+    lib.zpb_group_last_error.restype = C.c_char_p
+    lib.zpb_group_last_error.argtypes = [vp]
+    lib.zpb_group_partition.argtypes = [vp, u64, C.c_int, vp, vp]
+    lib.zpb_group_unpack_host.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, vp]
+    lib.zpb_group_pack_host.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, vp, vp]
+    lib.zpb_group_last_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+    lib.zpb_host_alloc.restype = vp
+    lib.zpb_host_alloc.argtypes = [u64]
+    lib.zpb_host_free.argtypes = [vp]
     _lib = lib
     return lib
+
+
+def group_partition(entries: np.ndarray, world: int):
+    """zpb_group_partition: (order, cuts) — device k takes entries[order[cuts[k]:cuts[k+1]]] (host logic, no GPU needed)."""
+    lib = load_library()
+    assert entries.dtype == Entry and entries.flags.c_contiguous
+    order = np.zeros(len(entries), np.uint64)
+    cuts = np.zeros(world + 1, np.uint64)
+    rc = lib.zpb_group_partition(entries.ctypes.data, len(entries), world, order.ctypes.data, cuts.ctypes.data)
+    if rc != 0:
+        raise ZpbError(f"zpb_group_partition: {rc}")
+    return order, cuts
+
+
+class Group:
+    """Several GPUs of one box behind one call (`zpb_group`): entries cut into contiguous runs balanced by decoded bytes,
+    one run per device, each on its own host thread; no collective."""
+
+    def __init__(self, devices=None):
+        self.lib = load_library()
+        if devices is None:
+            self.h = self.lib.zpb_group_create(None, 0)
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            self.h = self.lib.zpb_group_create(arr, len(devices))
+        if not self.h:
+            raise ZpbError("zpb_group_create failed: " + self.lib.zpb_last_error(None).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.zpb_group_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    @property
+    def size(self) -> int:
+        return self.lib.zpb_group_size(self.h)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ZpbError(f"zpb error {rc}: {self.lib.zpb_group_last_error(self.h).decode()}")
+
+    def unpack_host(self, h_archive, archive_size: int, h_out, out_size: int, entries: np.ndarray):
+        assert entries.dtype == Entry and entries.flags.c_contiguous
+        n = len(entries)
+        status, digest = np.zeros(n, np.int32), np.zeros(n, np.uint64)
+        self._check(self.lib.zpb_group_unpack_host(self.h, _ptr(h_archive), archive_size, _ptr(h_out), out_size,
+                                                   entries.ctypes.data, n, status.ctypes.data, digest.ctypes.data))
+        return status, digest
+
+    def pack_host(self, h_in, in_size: int, h_out, out_size: int, files: np.ndarray):
+        assert files.dtype == File and files.flags.c_contiguous
+        n = len(files)
+        comp, digest, status = np.zeros(n, np.uint64), np.zeros(n, np.uint64), np.zeros(n, np.int32)
+        self._check(self.lib.zpb_group_pack_host(self.h, _ptr(h_in), in_size, _ptr(h_out), out_size, files.ctypes.data, n,
+                                                 comp.ctypes.data, digest.ctypes.data, status.ctypes.data))
+        return comp, digest, status
+
+    def last_ms(self):
+        a = (C.c_float * 16)()
+        self.lib.zpb_group_last_ms(self.h, a, 16)
+        return [float(a[k]) for k in range(self.size)]
 
 
 def _ptr(a) -> int:
