@@ -44,7 +44,7 @@ def _counters(ctx):
         return None
     a = (C.c_uint32 * 16)()
     ctx.lib.zpb_debug_counters(C.c_void_p(ctx.h), a)
-    return {"heavy": a[8], "medium": a[9], "light": a[10], "split_retries": a[14], "general": a[1]}
+    return {"heavy": a[8], "medium": a[9], "light": a[10], "split_second_tries": a[15], "split_retries": a[14], "general": a[1]}
 
 
 def main():

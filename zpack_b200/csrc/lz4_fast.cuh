@@ -58,7 +58,7 @@
 #define FE_GENERAL 2u   // handed to the general kernel
 #define FE_ZSTD    3u   // handed to the zstd kernel (zstd_decode.cuh)
 
-#define FAST_DESC_PER_BLOCK 460ull
+#define FAST_DESC_PER_BLOCK 2060ull
 #define K1_HEAVY   (24u << 10)   // compressed block bytes: heavy / medium / light parse work lists
 #define K1_MEDIUM  (6u << 10)
 
@@ -394,11 +394,14 @@ struct LaneStage {
 // from its first byte.  When the four lanes of a block have finished, the warp moves the valid parts of segments 1-3
 // down behind segment 0 (output positions made absolute), so that K2 sees one flat descriptor list per block.
 #ifndef K1_MERGE_MAX
-#define K1_MERGE_MAX 96u
+#define K1_MERGE_MAX 384u
 #endif
-#define K1_SEG_SLACK 112u     // descriptor slots per segment beyond (compressed bytes / 3): the overrun until the join
+#define K1_SEG_SLACK 512u     // descriptor slots per segment beyond (compressed bytes / 3): the overrun until the join (+ a shifted second start)
 
-ZPB_DEVINL u32 k1_seg_start(u32 bsz, u32 j, u32 J) { return J == 1 ? 0u : (u32)(((u64)bsz * j) / J); }
+// where segment j's walk starts (attempt 1 shifts the speculative starts: a second try after a failed join)
+ZPB_DEVINL u32 k1_seg_start(u32 bsz, u32 j, u32 J, u32 attempt = 0) {
+    return J == 1 || j == 0 ? 0u : (u32)(((u64)bsz * j) / J) + 89u * attempt * j;
+}
 ZPB_DEVINL u32 k1_seg_desc(u32 bsz, u32 j, u32 J) {   // first descriptor slot of segment j (multiple of 4)
     return J == 1 ? 0u : ((k1_seg_start(bsz, j, J) / 3u + K1_SEG_SLACK * j) + 3u) & ~3u;
 }
@@ -433,7 +436,7 @@ lz4_fast_parse_body(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, u32 
     sg.gbase = archive; sg.glo = archive; sg.ghi = archive + asz; sg.row_s = row_s; sg.nreq = sg.avail = sg.klo = sg.khi = 0;
     // all positions below are ring coordinates (block position + skew)
     u32 slot = 0, skew = 0, qend = 0, qstop = 0, q = 0, op = 0, nseq = 0, last_ms = 0, mode = K1M_DONE;
-    u32 mptr = 0, msteps = 0, jtok = 0, jop = 0, bszv = 0;
+    u32 mptr = 0, msteps = 0, jtok = 0, jop = 0, bszv = 0, attempt = 0;
     bool had_match = false;
     u32 b0 = 0, b1 = 0, b2 = 0, b3 = 0;
     u32 *dout = nullptr;     // this segment's descriptor region
@@ -474,7 +477,7 @@ lz4_fast_parse_body(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, u32 
                         qstop = sj + 1 < J ? skew + k1_seg_start(B.bsz, sj + 1, J) : qend;
                         dout = desc + B.desc_off + k1_seg_desc(B.bsz, sj, J);
                         op = 0; nseq = 0; last_ms = 0; had_match = false;
-                        mode = K1M_WALK; mptr = 0; msteps = 0; jtok = 0; jop = 0;
+                        mode = K1M_WALK; mptr = 0; msteps = 0; jtok = 0; jop = 0; attempt = 0;
                         active = true;
                         sg.need(q, q + 1);       // the first four chunks, waited for
                     }
@@ -555,32 +558,53 @@ lz4_fast_parse_body(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, u32 
                         const u32 sv = __shfl_sync(0xffffffffu, srcv, gl + kk), cv = __shfl_sync(0xffffffffu, cnt, gl + kk),
                                   bv = __shfl_sync(0xffffffffu, base, gl + kk);
                         __syncwarp();                                           // the segments' own stores, and the previous move
-                        for (u32 i0 = 0; i0 < cv; i0 += 32) {
-                            const u32 i = i0 + lane;
-                            u32 v = 0;
-                            if (i < cv) v = __ldcg(bd + sv + i);
-                            __syncwarp();                                       // every load of the chunk before any store of it
-                            if (i < cv) bd[dst + i] = (v & 0xFFFFu) | (((v >> 16) + bv) << 16);
+                        for (u32 i0 = 0; i0 < cv; i0 += 256) {                   // eight loads in flight per lane: the move is latency-bound
+                            u32 v[8];
+#pragma unroll
+                            for (u32 u = 0; u < 8; ++u) {
+                                const u32 i = i0 + 32 * u + lane;
+                                v[u] = i < cv ? __ldcg(bd + sv + i) : 0u;
+                            }
+                            __syncwarp();                                       // every load of the batch before any store of it
+#pragma unroll
+                            for (u32 u = 0; u < 8; ++u) {
+                                const u32 i = i0 + 32 * u + lane;
+                                if (i < cv) bd[dst + i] = (v[u] & 0xFFFFu) | (((v[u] >> 16) + bv) << 16);
+                            }
                         }
                         dst += cv;
                     }
                 }
                 if (gdone) {
-                    if (sj == 3) {
-                        if (!ok || out_size > 65536u) {
-                            // No join within reach (few, long sequences: a walk started inside a long literal run stays off
-                            // the true chain), or a genuinely bad block: the unsplit kernel, which runs after this one,
-                            // walks it again from its first byte and has the verdict.
-                            parse_list[2ull * plist_cap + atomicAdd(&counters[10], 1u)] = slot;
-                            atomicAdd(&counters[14], 1u);   // statistics: blocks the split walk gave back
-                        } else {
-                            fb[slot].nseq = total;
-                            fb[slot].out_size = out_size;
-                            __threadfence();   // K2 may already be running (it polls `flags`): descriptors and sizes first, verdict last
-                            *reinterpret_cast<volatile u32 *>(&fb[slot].flags) = FB_PARSED;
+                    const bool failed = !ok || out_size > 65536u;
+                    if (failed && attempt == 0) {
+                        // No join within reach (a walk started inside a long literal run, or phase-locked on periodic data,
+                        // stays off the true chain): once more, the speculative starts shifted by a few bytes.
+                        attempt = 1;
+                        cp_async_wait_all();
+                        skew = sg.open(archive, asz, fb[slot].src, row_s);
+                        q = skew + k1_seg_start(bszv, sj, J, 1);
+                        qstop = sj + 1 < J ? skew + k1_seg_start(bszv, sj + 1, J, 1) : qend;
+                        op = 0; nseq = 0; last_ms = 0; had_match = false;
+                        mode = K1M_WALK; mptr = 0; msteps = 0; jtok = 0; jop = 0;
+                        sg.need(q, q + 1);
+                        if (sj == 3) atomicAdd(&counters[15], 1u);   // statistics: second attempts
+                    } else {
+                        if (sj == 3) {
+                            if (failed) {
+                                // still no join, or a genuinely bad block: the unsplit kernel, which runs after this one,
+                                // walks it again from its first byte and has the verdict
+                                parse_list[2ull * plist_cap + atomicAdd(&counters[10], 1u)] = slot;
+                                atomicAdd(&counters[14], 1u);   // statistics: blocks the split walk gave back
+                            } else {
+                                fb[slot].nseq = total;
+                                fb[slot].out_size = out_size;
+                                __threadfence();   // K2 may already be running (it polls `flags`): descriptors and sizes first, verdict last
+                                *reinterpret_cast<volatile u32 *>(&fb[slot].flags) = FB_PARSED;
+                            }
                         }
+                        active = false;
                     }
-                    active = false;
                 }
             }
         }

@@ -433,13 +433,13 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
             CK(ctx, cudaStreamWaitEvent(sp, ctx->ev_scan, 0));
         }
         CK(ctx, cudaEventRecord(ctx->ev_p0, sp));
-        // The split walk (four lanes per heavy / medium block, a quarter of the serial floor; lz4_fast_parse_body<4>) is
-        // opt-in (ZPB_PARSE_SPLIT=1).  Measured on B200 (profiles/r2_summary.md): a batch that already fills the GPU's lanes
-        // gains nothing (131 072 blocks: 2.9 ms split vs 2.2 ms unsplit, the merge is extra work), and a small batch gains
-        // only when NO block has to be given back to the unsplit kernel — one such block (0.03 % of text blocks, 2 % of
-        // fixed-stride records, whose false walks can phase-lock) costs the whole serial floor again.
-        static const int split_env = [] { const char *e = getenv("ZPB_PARSE_SPLIT"); return e ? atoi(e) : 0; }();
-        const bool split = split_env != 0;
+        // The split walk (four lanes per heavy / medium block: a quarter of the serial floor, then a merge and an in-place
+        // compaction; lz4_fast_parse_body<4>) pays when the batch leaves most of the GPU's lanes idle — measured on B200
+        // (profiles/r2_summary.md): 8 192 mixed entries 1.83 -> 1.34 ms parse, 2 048 entries 1.76 -> 1.23 ms; from about
+        // 16 384 entries on the unsplit walks fill the GPU by themselves and the merge is only extra work (text-only:
+        // 2.23 -> 2.95 ms).  ZPB_PARSE_SPLIT=0 / 1 forces either.
+        static const int split_env = [] { const char *e = getenv("ZPB_PARSE_SPLIT"); return e ? atoi(e) : -1; }();
+        const bool split = split_env >= 0 ? split_env != 0 : slots <= 40000;
         if (split) {
             lz4_fast_parse4_kernel<<<ctx->sm_count * k1_ctas, K1_THREADS, K1_THREADS * K1_ROW, sp>>>(
                 d_archive, archive_size, (FastBlock *)ctx->d_fb.p, (u32 *)ctx->d_plist.p, (u32)(slots + 1), cnt, cnt + 2,
