@@ -94,6 +94,38 @@ def main():
         zs[f"text_200k__l{lvl}"] = O.zstd_compress_ref(inputs["text_200k"], lvl)
         zs[f"mixed_300k__l{lvl}"] = O.zstd_compress_ref(inputs["mixed_300k"], lvl)
     np.savez_compressed(os.path.join(HERE, "zstd_cases.npz"), **zs)
+
+    # zstd stress frames: zstd's own generator (externals/zstd/tests/decodecorpus.c, built by oracle/Makefile as
+    # oracle/_ref/decodecorpus), seeded, content up to 128 KiB; plus the upstream golden frame whose first block is RLE.
+    # Stored: the frame, and of the original its size and XXH3-64 (the unmodified reference decoder's output is the truth).
+    import subprocess
+    import tempfile
+    gen = os.path.join(ROOT, "oracle", "_ref", "decodecorpus")
+    zc = {}
+    with tempfile.TemporaryDirectory() as td:
+        zdir, odir = os.path.join(td, "z"), os.path.join(td, "o")
+        os.mkdir(zdir); os.mkdir(odir)
+        subprocess.run([gen, "-n240", "-s20261018", "--max-content-size-log=17", f"-p{zdir}", f"-o{odir}"], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        names = sorted(os.listdir(zdir))
+        sizes, digests = [], []
+        for k, nm in enumerate(names):
+            fr = np.fromfile(os.path.join(zdir, nm), np.uint8)
+            orig = np.fromfile(os.path.join(odir, nm.replace("z", "o", 1).replace(".zst", "")), np.uint8) if os.path.exists(
+                os.path.join(odir, nm.replace("z", "o", 1).replace(".zst", ""))) else None
+            got = O.zstd_decompress_ref(fr, 1 << 18)
+            if orig is not None:
+                assert np.array_equal(got, orig), nm
+            zc[f"f{k:03d}"] = fr
+            sizes.append(len(got)); digests.append(O.xxh3_ref(got))
+    rle = np.fromfile(os.path.join(REF, "externals/zstd/tests/golden-decompression/rle-first-block.zst"), np.uint8)
+    got = O.zstd_decompress_ref(rle, 1 << 22)
+    zc["rle_first_block"] = rle
+    sizes.append(len(got)); digests.append(O.xxh3_ref(got))
+    zc["__names"] = np.array([f"f{k:03d}" for k in range(len(sizes) - 1)] + ["rle_first_block"])
+    zc["__sizes"] = np.array(sizes, np.uint64)
+    zc["__xxh3"] = np.array(digests, np.uint64)
+    np.savez_compressed(os.path.join(HERE, "zstd_corpus.npz"), **zc)
     print("golden fixtures written:", sorted(os.listdir(HERE)))
 
 

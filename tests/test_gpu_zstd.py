@@ -146,3 +146,32 @@ def test_c4_shape_packed_by_reference(gpu_ctx, oracle):
     for i, b in enumerate(bufs):
         o = int(e["dst_off"][i])
         assert np.array_equal(out[o:o + len(b)], b), i
+
+
+def test_decodecorpus_frames_and_rle_first_block(gpu_ctx, oracle, golden_dir):
+    """zstd's own stress generator (externals/zstd/tests/decodecorpus.c: every block / literal / sequence mode, repeat
+    offsets, long offsets, odd window sizes) and tests/golden-decompression/rle-first-block.zst, wrapped as entries:
+    the GPU's status, bytes and digest must equal the oracle's (which equals the unmodified reference's, test_oracle.py)."""
+    import os
+    d = dict(np.load(os.path.join(golden_dir, "zstd_corpus.npz")))
+    names, sizes, dg = list(d["__names"]), d["__sizes"], d["__xxh3"]
+    frames = [d[nm] for nm in names]
+    arch = container.assemble([str(n) for n in names], frames, [int(s) for s in sizes], [int(x) for x in dg], [1] * len(names))
+    e = container.parse(arch).entries()
+    out_size = int((e["dst_off"] + e["dst_cap"]).max()) + 16
+    for host in (True, False):
+        if host:
+            out = np.zeros(out_size, np.uint8)
+            status, digest = gpu_ctx.unpack_host(arch, len(arch), out, out_size, e)
+        else:
+            import torch
+            d_arch = torch.from_numpy(arch).cuda()
+            d_out = torch.zeros(out_size, dtype=torch.uint8, device="cuda")
+            status, digest = gpu_ctx.unpack_device(d_arch, len(arch), d_out, out_size, e)
+            out = d_out.cpu().numpy()
+        assert (status == 0).all(), {str(names[i]): int(status[i]) for i in np.nonzero(status)[0]}
+        assert np.array_equal(digest, dg)
+        for k in range(0, len(names), 7):
+            rc, want = oracle.zstd_decode_port(frames[k], int(sizes[k]))
+            o = int(e["dst_off"][k])
+            assert rc == 0 and np.array_equal(out[o:o + len(want)], want), names[k]

@@ -220,3 +220,17 @@ def test_ref_and_port_agree_on_zstd_corpus_and_corruption(oracle):
             rd.close()
             rc_port, _, _ = oracle.read_entry_port(1, m, size, size, h)
             assert (rc_ref == 0) == (rc_port == 0), (i, trial, rc_ref, rc_port)
+
+
+def test_zstd_port_decodes_the_decodecorpus_frames(oracle, golden_dir):
+    """Frames from zstd's own generator (externals/zstd/tests/decodecorpus.c, seeded; tests/golden/make_golden.py) and the
+    upstream golden frame whose first block is RLE (tests/golden-decompression/rle-first-block.zst): sizes and XXH3-64
+    digests recorded from the unmodified reference decoder."""
+    d = dict(np.load(os.path.join(golden_dir, "zstd_corpus.npz")))
+    names, sizes, dg = list(d["__names"]), d["__sizes"], d["__xxh3"]
+    assert len(names) == 241 and "rle_first_block" in names
+    for k, nm in enumerate(names):
+        rc, got = oracle.zstd_decode_port(d[nm], int(sizes[k]))
+        assert rc == 0 and len(got) == int(sizes[k]) and oracle.xxh3_port(got) == int(dg[k]), nm
+        if oracle.have_ref() and k % 16 == 0:
+            assert np.array_equal(oracle.zstd_decompress_ref(d[nm], int(sizes[k])), got), nm
