@@ -1,0 +1,22 @@
+// pack_sim.cpp — TEST INFRASTRUCTURE: runs the block compressor of zpack_b200/csrc/pack_blocks.cuh on the CPU emulation
+// (sim_rt.h) so that tests/test_pack_sim.py can decode its output with the oracle without a GPU.
+// Built by tests/test_pack_sim.py:  g++ -O1 -g -DZPB_SIM -shared -fPIC pack_sim.cpp -o libpack_sim.so
+#include <cstring>
+#include <vector>
+
+#include "../../include/zpack_b200.h"
+#include "../../zpack_b200/csrc/pack_blocks.cuh"
+
+// blocks: (src_off, len) pairs; scratch: nblocks * 65536 bytes; csize: nblocks
+extern "C" int sim_lz4_pack_blocks(const uint8_t *in, const uint64_t *src_off, const uint32_t *len, uint32_t nblocks,
+                                   uint8_t *scratch, uint32_t *csize, int grid, uint64_t seed) {
+    std::vector<PackBlock> pb(nblocks);
+    for (u32 i = 0; i < nblocks; ++i) { pb[i].src_off = src_off[i]; pb[i].len = len[i]; pb[i].pad = 0; }
+    u32 counter = 0;
+    const PackBlock *dpb = pb.data();
+    u32 *cnt = &counter;
+    sim::launch(sim::Dim3((unsigned)grid), sim::Dim3(32 * P2_WARPS), P2_SMEM, [&] {
+        lz4_pack_blocks_body(in, dpb, nblocks, cnt, scratch, csize);
+    }, seed);
+    return 0;
+}

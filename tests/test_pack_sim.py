@@ -1,0 +1,107 @@
+"""The LZ4 block compressor (zpack_b200/csrc/pack_blocks.cuh) on the CPU emulation of tests/sim: every block it emits is
+wrapped into an LZ4 frame and decoded by the oracle; sizes are compared with the reference algorithm's (oracle port of
+LZ4F_compressFrame at level 0).  The GPU tests (tests/test_gpu_pack.py) cover the real library."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from zpack_b200 import corpus
+
+import crafted
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SIM = os.path.join(HERE, "sim")
+LIB = os.path.join(SIM, "libpack_sim.so")
+CSRC = os.path.join(os.path.dirname(HERE), "zpack_b200", "csrc")
+
+
+def _build():
+    deps = [os.path.join(SIM, f) for f in ("pack_sim.cpp", "sim_rt.h", "sim_cuda.h")]
+    deps += [os.path.join(CSRC, f) for f in ("pack_blocks.cuh", "ptx.cuh", "common.cuh")]
+    if os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
+        return
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-DZPB_SIM", "-shared", "-fPIC", "-w",
+                    os.path.join(SIM, "pack_sim.cpp"), "-o", LIB], check=True)
+
+
+@pytest.fixture(scope="module")
+def sim():
+    _build()
+    lib = C.CDLL(LIB)
+    vp = C.c_void_p
+    lib.sim_lz4_pack_blocks.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_int, C.c_uint64]
+    return lib
+
+
+def pack_blocks(sim, bufs, seed=1, grid=2, misalign=0):
+    """bufs: list of byte arrays (each <= 64 KB) -> list of (csize, payload)"""
+    offs, total = [], misalign
+    for b in bufs:
+        offs.append(total)
+        total += len(b) + (3 if misalign else 0)
+    inp = np.zeros(total + 64, np.uint8)
+    for o, b in zip(offs, bufs):
+        inp[o:o + len(b)] = b
+    n = len(bufs)
+    so = np.array(offs, np.uint64)
+    ln = np.array([len(b) for b in bufs], np.uint32)
+    scratch = np.full(n * 65536 + 64, 0xEE, np.uint8)
+    csize = np.full(n, 0xFFFFFFFF, np.uint32)
+    sim.sim_lz4_pack_blocks(inp.ctypes.data, so.ctypes.data, ln.ctypes.data, n, scratch.ctypes.data, csize.ctypes.data, grid, seed)
+    assert (scratch[n * 65536:] == 0xEE).all()
+    return [(int(csize[i]), scratch[i * 65536:i * 65536 + int(csize[i])].copy()) for i in range(n)]
+
+
+def decode_block(oracle, payload, n):
+    hdr = bytes(oracle.lz4f_encode_port(np.zeros(0, np.uint8), 0, independent=True)[:7])
+    fr = hdr + len(payload).to_bytes(4, "little") + bytes(payload) + b"\0\0\0\0"
+    return oracle.lz4f_decode_port(np.frombuffer(fr, np.uint8), n)
+
+
+def check(sim, oracle, bufs, **kw):
+    res = pack_blocks(sim, bufs, **kw)
+    ours = ref = 0
+    for i, (b, (c, payload)) in enumerate(zip(bufs, res)):
+        assert c < len(b), (i, c, len(b))                      # compressed only if smaller, else 0 = stored
+        if c:
+            rc, out = decode_block(oracle, payload, len(b))
+            assert rc == 0 and np.array_equal(out[:len(b)], b), (i, len(b), c)
+        ours += c if c else len(b)
+        ref += len(oracle.lz4f_encode_port(b, 0, independent=True)) - 15 if len(b) else 0
+    return ours, ref
+
+
+def test_corpus_blocks_decode_and_ratio(sim, oracle):
+    bufs = [corpus.entry_bytes(i, 65536) for i in range(6)] + [corpus.entry_bytes(40 + i, s) for i, s in enumerate((40000, 4097, 4096, 300))]
+    ours, ref = check(sim, oracle, bufs)
+    print(f"\nblock compressor on zpk-synth-v1: {ours} bytes vs reference algorithm {ref} ({ref / ours:.3f} of its ratio)")
+    assert ours < 1.06 * ref
+
+
+def test_edge_sizes(sim, oracle):
+    rng = np.random.default_rng(3)
+    sizes = [1, 4, 5, 11, 12, 13, 14, 17, 31, 32, 33, 64, 127, 128, 129, 140, 255, 256, 1000, 4095, 4096, 4097, 4108, 4109, 8192, 65535, 65536]
+    bufs = [np.frombuffer((b"abcdefgh" * 9000)[:s], np.uint8) for s in sizes]            # periodic: matches run to every limit
+    bufs += [np.zeros(s, np.uint8) for s in sizes]                                     # overlapping matches at distance 1
+    bufs += [rng.integers(0, 256, s, dtype=np.uint8) for s in (13, 100, 5000, 65536)]  # incompressible: stored
+    bufs += [rng.integers(0, 4, s, dtype=np.uint8) for s in (100, 5000, 65536)]        # dense short matches
+    check(sim, oracle, bufs, misalign=1)
+    check(sim, oracle, bufs[:30], seed=9, grid=1)
+
+
+def test_crafted_inputs(sim, oracle):
+    """Plain texts of the crafted decoder cases (tests/crafted.py): long matches, overlaps, far offsets."""
+    rng = np.random.default_rng(11)
+    bufs = []
+    for style in ("mixed", "overlap", "far", "long"):
+        try:
+            _fr, plain = crafted.frame(rng, [65536, 30000], style)
+        except Exception:
+            continue
+        plain = np.frombuffer(plain, np.uint8)
+        bufs += [plain[i:i + 65536] for i in range(0, len(plain), 65536)]
+    assert bufs
+    check(sim, oracle, bufs)

@@ -14,19 +14,37 @@ extern "C" uint64_t zpb_pack_bound(uint32_t method, uint64_t size) {
     return 0;
 }
 
+// Two launches per round: lz4_pack_blocks_kernel compresses every 64 KB block of the round's LZ4 files (one warp per
+// block, payload into a scratch slot per block), lz4_pack_kernel lays the frames out and hashes the inputs (one warp per
+// file).  A round takes as many files (largest first) as its blocks fit the scratch: pack_scratch_blocks slots of 64 KB.
 static int pack_device_impl(zpb_ctx *ctx, const u8 *d_in, u64 in_size, u8 *d_out, u64 out_size,
                             const zpb_file *files, u64 n, u64 *comp_size, u64 *digest, int32_t *status,
                             cudaStream_t s) {
     if (n == 0) return ZPB_OK;
     if (n > 0x7fffffffull) return fail(ctx, ZPB_E_ARG, "too many files in one batch");
-    size_t desc_b = n * sizeof(zpb_file), ord_b = n * sizeof(u32);
-    size_t res_b = n * (2 * sizeof(u64) + sizeof(int));
-    if (!ctx->d_desc.ensure(desc_b) || !ctx->d_order.ensure(ord_b) || !ctx->d_res.ensure(res_b + 64) ||
-        !ctx->d_counter.ensure(256) || !ctx->h_stage.ensure(desc_b + ord_b + res_b + 64))
+    // block list of the LZ4 files the stage-2 kernel will accept (same checks as there)
+    u64 nblk = 0;
+    for (u64 i = 0; i < n; ++i) {
+        const zpb_file &f = files[i];
+        if (f.method != ZPB_METHOD_LZ4 || f.level >= 3) continue;
+        if (f.src_off > in_size || f.size > in_size - f.src_off || f.dst_off > out_size || f.dst_cap > out_size - f.dst_off) continue;
+        if (f.dst_cap < 7 + 4 * ((f.size + 65535) >> 16) + f.size + 4) continue;
+        nblk += (f.size + 65535) >> 16;
+    }
+    if (nblk > 0x7fffffffull) return fail(ctx, ZPB_E_ARG, "too many blocks in one batch");
+    const size_t desc_b = n * sizeof(zpb_file), ord_b = (n * sizeof(u32) + 15) & ~(size_t)15;
+    const size_t res_b = n * (2 * sizeof(u64) + sizeof(int));
+    const size_t blk_b = nblk * sizeof(PackBlock), base_b = ord_b;
+    const u64 cap_blocks = std::max<u64>(ctx->pack_scratch_blocks, 1);
+    if (!ctx->d_desc.ensure(desc_b) || !ctx->d_order.ensure(ord_b + base_b) || !ctx->d_res.ensure(res_b + 64) ||
+        !ctx->d_counter.ensure(256) || !ctx->h_stage.ensure(desc_b + ord_b + base_b + blk_b + res_b + 64) ||
+        !ctx->d_pblk.ensure(blk_b + 16) || !ctx->d_csize.ensure(std::min(nblk, cap_blocks) * sizeof(u32) + 16))
         return fail(ctx, ZPB_E_NOMEM, "scratch allocation failed");
     u8 *hs = (u8 *)ctx->h_stage.p;
     memcpy(hs, files, desc_b);
     u32 *h_order = (u32 *)(hs + desc_b);
+    u32 *h_base = (u32 *)(hs + desc_b + ord_b);
+    PackBlock *h_blk = (PackBlock *)(hs + desc_b + ord_b + base_b);
     {   // largest files first (counting sort on size / 4 KiB, descending)
         auto key = [&](u64 i) -> u32 { u64 c = files[i].size >> 12; return c > 1023 ? 0u : 1023u - (u32)c; };
         std::vector<u32> head(1025, 0);
@@ -34,25 +52,65 @@ static int pack_device_impl(zpb_ctx *ctx, const u8 *d_in, u64 in_size, u8 *d_out
         for (u32 k = 0; k < 1024; ++k) head[k + 1] += head[k];
         for (u64 i = 0; i < n; ++i) h_order[head[key(i)]++] = (u32)i;
     }
+    // rounds: [first file in h_order, first block in h_blk); block indices in h_base are relative to the round's scratch
+    struct Round { u64 f0, f1, b0, b1; };
+    std::vector<Round> rounds;
+    {
+        u64 bi = 0, rb0 = 0, rf0 = 0;
+        for (u64 k = 0; k < n; ++k) {
+            const u32 i = h_order[k];
+            const zpb_file &f = files[i];
+            h_base[i] = 0;
+            if (f.method != ZPB_METHOD_LZ4 || f.level >= 3) continue;
+            if (f.src_off > in_size || f.size > in_size - f.src_off || f.dst_off > out_size || f.dst_cap > out_size - f.dst_off) continue;
+            const u64 fb = (f.size + 65535) >> 16;
+            if (f.dst_cap < 7 + 4 * fb + f.size + 4) continue;
+            if (bi - rb0 + fb > cap_blocks && bi > rb0) { rounds.push_back({rf0, k, rb0, bi}); rf0 = k; rb0 = bi; }
+            h_base[i] = (u32)(bi - rb0);
+            for (u64 b = 0; b < fb; ++b) {
+                h_blk[bi].src_off = f.src_off + (b << 16);
+                h_blk[bi].len = (u32)std::min<u64>(f.size - (b << 16), 65536);
+                h_blk[bi].pad = 0;
+                ++bi;
+            }
+        }
+        rounds.push_back({rf0, n, rb0, bi});
+    }
+    u64 max_round = 0;
+    for (const Round &r : rounds) max_round = std::max(max_round, r.b1 - r.b0);
+    if (!ctx->d_pscratch.ensure((max_round << 16) + 64) || !ctx->d_csize.ensure(max_round * sizeof(u32) + 16))
+        return fail(ctx, ZPB_E_NOMEM, "block scratch allocation failed");
     u64 *d_comp = (u64 *)ctx->d_res.p;
     u64 *d_dig = d_comp + n;
     int *d_st = (int *)(d_dig + n);
+    const u32 *d_ord = (const u32 *)ctx->d_order.p;
+    const u32 *d_base = (const u32 *)((const u8 *)ctx->d_order.p + ord_b);
     CK(ctx, cudaMemcpyAsync(ctx->d_desc.p, hs, desc_b, cudaMemcpyHostToDevice, s));
-    CK(ctx, cudaMemcpyAsync(ctx->d_order.p, h_order, ord_b, cudaMemcpyHostToDevice, s));
-    CK(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, 256, s));
+    CK(ctx, cudaMemcpyAsync(ctx->d_order.p, h_order, ord_b + base_b, cudaMemcpyHostToDevice, s));
+    if (blk_b) CK(ctx, cudaMemcpyAsync(ctx->d_pblk.p, h_blk, blk_b, cudaMemcpyHostToDevice, s));
     CK(ctx, cudaEventRecord(ctx->ev0, s));
-    int per_sm = 0;
-    CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz4_pack_kernel, 32 * PK_WARPS, 0));
-    if (per_sm < 1) per_sm = 1;
-    u64 want = (n + PK_WARPS - 1) / PK_WARPS;
-    u32 grid = (u32)std::min<u64>((u64)ctx->sm_count * per_sm, std::max<u64>(want, 1));
-    lz4_pack_kernel<<<grid, 32 * PK_WARPS, 0, s>>>(d_in, in_size, d_out, out_size, (const zpb_file *)ctx->d_desc.p,
-                                                   (const u32 *)ctx->d_order.p, (u32)n, (u32 *)ctx->d_counter.p,
-                                                   d_comp, d_dig, d_st);
-    CK(ctx, cudaGetLastError());
-    ctx->launches += 1;
+    for (const Round &r : rounds) {
+        CK(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, 256, s));
+        const u64 rb = r.b1 - r.b0, rf = r.f1 - r.f0;
+        if (rb) {
+            const u32 grid = (u32)std::min<u64>((u64)ctx->sm_count * ctx->p2_per_sm, (rb + P2_WARPS - 1) / P2_WARPS);
+            lz4_pack_blocks_kernel<<<grid, 32 * P2_WARPS, P2_SMEM, s>>>(d_in, (const PackBlock *)ctx->d_pblk.p + r.b0, (u32)rb,
+                                                                        (u32 *)ctx->d_counter.p + 32, (u8 *)ctx->d_pscratch.p,
+                                                                        (u32 *)ctx->d_csize.p);
+            CK(ctx, cudaGetLastError());
+            ctx->launches += 1;
+        }
+        if (rf) {
+            const u32 grid = (u32)std::min<u64>((u64)ctx->sm_count * ctx->pk_per_sm, (rf + PK_WARPS - 1) / PK_WARPS);
+            lz4_pack_kernel<<<grid, 32 * PK_WARPS, 0, s>>>(d_in, in_size, d_out, out_size, (const zpb_file *)ctx->d_desc.p,
+                                                           d_ord + r.f0, (u32)rf, (u32 *)ctx->d_counter.p, d_comp, d_dig, d_st,
+                                                           d_base, (const u8 *)ctx->d_pscratch.p, (const u32 *)ctx->d_csize.p);
+            CK(ctx, cudaGetLastError());
+            ctx->launches += 1;
+        }
+    }
     CK(ctx, cudaEventRecord(ctx->ev1, s));
-    u8 *h_res = hs + desc_b + ord_b;
+    u8 *h_res = hs + desc_b + ord_b + base_b + blk_b;
     CK(ctx, cudaMemcpyAsync(h_res, ctx->d_res.p, res_b, cudaMemcpyDeviceToHost, s));
     CK(ctx, cudaStreamSynchronize(s));
     CK(ctx, cudaEventElapsedTime(&ctx->pack_ms, ctx->ev0, ctx->ev1));

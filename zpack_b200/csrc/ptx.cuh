@@ -91,6 +91,7 @@ ZPB_DEVINL void mbar_wait(u32 bar, u32 parity) {
                  "@p bra ZPB_MBD_%=;\n\tbra ZPB_MBW_%=;\n\tZPB_MBD_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
 #define ZPB_DYN_SMEM(name) extern __shared__ uint4 name[]
+ZPB_DEVINL void spin_pause() { __nanosleep(32); }     // inside a wait on a flag another warp of the CTA sets
 ZPB_DEVINL u32 smem_window(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 // where the dynamic shared window of a kernel without static shared memory starts on sm_100 (1 KiB is reserved in
 // front of it); kernels that build addresses from it check it at entry and trap on a mismatch
@@ -155,6 +156,7 @@ ZPB_DEVINL void mbar_arrive_expect_tx(u32 bar, u32 bytes) { sim::mbar_arrive_exp
 ZPB_DEVINL void bulk_g2s(u32 dst, const void *src, u32 bytes, u32 bar) { sim::bulk_g2s(dst, src, bytes, bar); }
 ZPB_DEVINL void mbar_wait(u32 bar, u32 parity) { while (!sim::mbar_test_wait(bar, parity)) sim::park(); }
 #define ZPB_DYN_SMEM(name) uint4 *name = reinterpret_cast<uint4 *>(sim::S().smem.data())
+ZPB_DEVINL void spin_pause() { sim::park(); }
 ZPB_DEVINL u32 smem_window(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 #define ZPB_DYN_SMEM_BASE (sim::SMEM_BASE)
 static inline void __trap() { fprintf(stderr, "sim: __trap()\n"); abort(); }

@@ -79,6 +79,9 @@ struct zpb_ctx {
     DevBuf d_in, d_out;
     DevBuf d_gather, d_goff;   // pack: compacted frames + their sizes / offsets
     PinBuf h_bounce;           // pack: landing zone of the one D2H per chunk
+    DevBuf d_pblk, d_pscratch, d_csize;    // pack: block list, one 64 KB payload slot per block of a round, block sizes
+    u64 pack_scratch_blocks = 16384;       // slots per round (ZPB_PACK_SCRATCH_MB, default 1 GiB)
+    int p2_per_sm = 1, pk_per_sm = 1;      // resident CTAs of the two pack kernels
     // pipelined host path: private sub-contexts (own stream + scratch), one per worker thread
     std::vector<zpb_ctx *> workers;
     // block-sharded path (one large block-independent LZ4 entry): per-KiB XXH3 stripe sums of the last shard
@@ -177,6 +180,14 @@ extern "C" zpb_ctx *zpb_create(int device) {
         }
         ctx->zs_grid = ctx->sm_count * per_sm;
     }
+    if (cudaFuncSetAttribute(lz4_pack_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2_SMEM) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->p2_per_sm, lz4_pack_blocks_kernel, 32 * P2_WARPS, P2_SMEM) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->pk_per_sm, lz4_pack_kernel, 32 * PK_WARPS, 0) != cudaSuccess ||
+        ctx->p2_per_sm < 1 || ctx->pk_per_sm < 1) {
+        g_last_error = std::string("pack kernel setup failed: ") + cudaGetErrorString(cudaGetLastError());
+        delete ctx; return nullptr;
+    }
+    if (const char *e = getenv("ZPB_PACK_SCRATCH_MB")) ctx->pack_scratch_blocks = std::max<u64>((u64)atoll(e) * 16, 1);
     return ctx;
 }
 
@@ -190,6 +201,7 @@ extern "C" void zpb_destroy(zpb_ctx *ctx) {
     ctx->d_aux.release(); ctx->d_fe.release(); ctx->d_fb.release(); ctx->d_plist.release();
     ctx->d_glist.release(); ctx->d_fdesc.release(); ctx->d_zlist.release(); ctx->d_zlit.release();
     ctx->d_gather.release(); ctx->d_goff.release(); ctx->h_bounce.release();
+    ctx->d_pblk.release(); ctx->d_pscratch.release(); ctx->d_csize.release();
     ctx->d_partials.release(); ctx->d_acc.release();
     for (auto &ev : ctx->evs) if (ev) cudaEventDestroy(ev);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
