@@ -184,6 +184,9 @@ int zpb_pack_host(zpb_ctx *ctx, const uint8_t *h_in, uint64_t in_size, uint8_t *
 
 /* last kernel timing (CUDA events on the launching stream), for bench.py's roofline block */
 int zpb_last_kernel_ms(const zpb_ctx *ctx, float *unpack_ms, float *pack_ms);
+/* The last zpb_pack_device call by stage, summed over its rounds: the block compressor (lz4_pack_blocks_kernel, the
+ * role of LZ4_compress_fast_extState under lz4frame.c:735-760) and the framing + XXH3 kernel (lz4_pack_kernel). */
+int zpb_last_pack_stage_ms(const zpb_ctx *ctx, float *blocks_ms, float *frames_ms);
 
 /* per-stage device time of the last unpack (ms): scan, parse, exec, general-fallback.  With the overlap on (the
  * default, zpb_set_overlap) parse and exec run concurrently, so the two intervals overlap and exec's includes the time

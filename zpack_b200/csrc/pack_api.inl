@@ -89,8 +89,15 @@ static int pack_device_impl(zpb_ctx *ctx, const u8 *d_in, u64 in_size, u8 *d_out
     CK(ctx, cudaMemcpyAsync(ctx->d_order.p, h_order, ord_b + base_b, cudaMemcpyHostToDevice, s));
     if (blk_b) CK(ctx, cudaMemcpyAsync(ctx->d_pblk.p, h_blk, blk_b, cudaMemcpyHostToDevice, s));
     CK(ctx, cudaEventRecord(ctx->ev0, s));
+    while (ctx->pack_evs.size() < 3 * rounds.size()) {
+        cudaEvent_t e = nullptr;
+        CK(ctx, cudaEventCreate(&e));
+        ctx->pack_evs.push_back(e);
+    }
+    size_t ri = 0;
     for (const Round &r : rounds) {
         CK(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, 256, s));
+        CK(ctx, cudaEventRecord(ctx->pack_evs[3 * ri], s));
         const u64 rb = r.b1 - r.b0, rf = r.f1 - r.f0;
         if (rb) {
             const u32 grid = (u32)std::min<u64>((u64)ctx->sm_count * ctx->p2_per_sm, (rb + P2_WARPS - 1) / P2_WARPS);
@@ -100,6 +107,7 @@ static int pack_device_impl(zpb_ctx *ctx, const u8 *d_in, u64 in_size, u8 *d_out
             CK(ctx, cudaGetLastError());
             ctx->launches += 1;
         }
+        CK(ctx, cudaEventRecord(ctx->pack_evs[3 * ri + 1], s));
         if (rf) {
             const u32 grid = (u32)std::min<u64>((u64)ctx->sm_count * ctx->pk_per_sm, (rf + PK_WARPS - 1) / PK_WARPS);
             lz4_pack_kernel<<<grid, 32 * PK_WARPS, 0, s>>>(d_in, in_size, d_out, out_size, (const zpb_file *)ctx->d_desc.p,
@@ -108,15 +116,32 @@ static int pack_device_impl(zpb_ctx *ctx, const u8 *d_in, u64 in_size, u8 *d_out
             CK(ctx, cudaGetLastError());
             ctx->launches += 1;
         }
+        CK(ctx, cudaEventRecord(ctx->pack_evs[3 * ri + 2], s));
+        ++ri;
     }
     CK(ctx, cudaEventRecord(ctx->ev1, s));
     u8 *h_res = hs + desc_b + ord_b + base_b + blk_b;
     CK(ctx, cudaMemcpyAsync(h_res, ctx->d_res.p, res_b, cudaMemcpyDeviceToHost, s));
     CK(ctx, cudaStreamSynchronize(s));
     CK(ctx, cudaEventElapsedTime(&ctx->pack_ms, ctx->ev0, ctx->ev1));
+    ctx->pack_blocks_ms = ctx->pack_frames_ms = 0.f;
+    for (size_t k = 0; k < rounds.size(); ++k) {
+        float a = 0.f, b = 0.f;
+        CK(ctx, cudaEventElapsedTime(&a, ctx->pack_evs[3 * k], ctx->pack_evs[3 * k + 1]));
+        CK(ctx, cudaEventElapsedTime(&b, ctx->pack_evs[3 * k + 1], ctx->pack_evs[3 * k + 2]));
+        ctx->pack_blocks_ms += a;
+        ctx->pack_frames_ms += b;
+    }
     if (comp_size) memcpy(comp_size, h_res, n * sizeof(u64));
     if (digest) memcpy(digest, h_res + n * sizeof(u64), n * sizeof(u64));
     if (status) memcpy(status, h_res + 2 * n * sizeof(u64), n * sizeof(int));
+    return ZPB_OK;
+}
+
+extern "C" int zpb_last_pack_stage_ms(const zpb_ctx *ctx, float *blocks_ms, float *frames_ms) {
+    if (!ctx) return ZPB_E_ARG;
+    if (blocks_ms) *blocks_ms = ctx->pack_blocks_ms;
+    if (frames_ms) *frames_ms = ctx->pack_frames_ms;
     return ZPB_OK;
 }
 

@@ -9,23 +9,27 @@
 //   The block is brought into shared memory by one bulk asynchronous copy (cp.async.bulk + mbarrier): every later read
 //   of the input — probing, verifying, extending, copying literals — is a shared-memory access.  It is then processed
 //   in windows of P2_WIN = 4096 positions, window w by warp w mod 4:
-//   (1a) PROBE, all positions in order, 32 per step: 4-byte word, multiplicative hash into the table, candidate = the
-//        table's previous position (or a lower lane of the same step holding the same word, for distances below 32).
-//        Positions enter the table in ascending order, as in the reference, so windows are probed strictly one after
-//        the other: a token in shared memory goes from the warp of window w to the warp of window w + 1.
-//   (1b) VERIFY: candidate -> match distance of every position (0 = none), independent loads.
+//   (1a) HASH of every position, 32 per step (no order needed).
+//   (1b) PROBE, the only part that has to see the positions in ascending order, as the reference does: hash -> the
+//        table's previous position, the table takes the new one.  Windows are probed strictly one after the other: a
+//        token in shared memory goes from the warp of window w to the warp of window w + 1.
+//   (1c) VERIFY: candidate (or a lower lane of the same step holding the same word, for distances below 32) -> match
+//        distance of every position (0 = none), independent loads.
 //   (2)  WALK, one lane per 128-byte sub-chunk: the greedy walk (first position with a candidate, extend both ways,
 //        emit, skip) runs in all 32 sub-chunks at once; a match stops at its sub-chunk's end.  A lane stages its
 //        sequences in shared memory (over the part of the distance array it has already consumed) — except its FIRST
 //        one, whose literal run starts in an earlier sub-chunk, and a LAST one that was cut by the sub-chunk's end.
-//   (3)  JOIN, window after window (a second token): the held-back sequences are completed in lane order — a cut match
-//        is continued by the next sub-chunk's first match when that starts where it ended with the same offset — and
-//        emitted by the whole warp, the staged bytes appended, into the block's scratch slot in HBM.
-//   While one warp probes window w, the others verify / walk / join the windows before it.
+//   (3)  JOIN: the held-back sequences are completed in lane order — a cut match is continued by the next sub-chunk's
+//        first match when that starts where it ended with the same offset — and emitted by the whole warp, the staged
+//        bytes appended, into the block's scratch slot in HBM.  The window's size is counted first; a second token
+//        carries the output position and the start of the pending literal run from window to window and is held for a
+//        few instructions only, so the windows of a block are written concurrently.
+//   While one warp probes window w, the others hash / verify / walk / join the windows around it.
 //
 // A block that does not shrink is reported as stored (size 0): the framing stage copies it, as LZ4F_makeBlock does
 // (lz4frame.c:750-754).  The compressed bytes are valid LZ4 but not the reference's bytes (every position is probed: no
-// skip acceleration, negative levels compress like level 0; matches are cut at 128-byte sub-chunk ends unless rejoined);
+// skip acceleration — a block whose first 16 KB or more save less than 1/64 is stored instead —, negative levels compress
+// like level 0; matches are cut at 128-byte sub-chunk ends unless rejoined, and at window ends);
 // the ratio is reported next to the reference's by the tests and the bench.
 #pragma once
 #include "common.cuh"
@@ -102,6 +106,46 @@ ZPB_DEVINL bool p2_wait(volatile u32 *token, u32 want, volatile u32 *stop) {
     }
     __threadfence_block();
     return true;
+}
+
+// One window's sequences in lane order, at dst + op (WRITE) or only counted (!WRITE): the first literal run starts at
+// block position `anchor`.  One sequence is always held back (pv, p_*): the next lane's first match continues it when it
+// starts where that one ended with the same offset (a match cut at a sub-chunk end).  Returns the new output position.
+template <bool WRITE>
+ZPB_DEVINL u32 p2_join(u8 *dst, u32 op, u32 anchor, const u8 *sm, u32 D, u32 dso, u32 lane, bool has, u32 f_pos, u32 f_off,
+                       u32 f_len, u32 so, u32 l_pos, u32 l_off, u32 l_len, u32 l_ls, u32 la) {
+    bool pv = false;
+    u32 p_ls = 0, p_pos = 0, p_off = 0, p_len = 0;
+    u32 m = __ballot_sync(0xffffffffu, has);
+    while (m) {
+        const int k = __ffs(m) - 1;
+        m &= m - 1;
+        const u32 P = __shfl_sync(0xffffffffu, f_pos, k), O = __shfl_sync(0xffffffffu, f_off, k),
+                  L = __shfl_sync(0xffffffffu, f_len, k), SO = __shfl_sync(0xffffffffu, so, k),
+                  LL = __shfl_sync(0xffffffffu, l_len, k);
+        if (pv && P == anchor && O == p_off) p_len += L;
+        else {
+            if (pv) op = WRITE ? p2_emit_coop(dst, op, sm, D + p_ls, p_pos - p_ls, p_off, p_len, lane) : op + p2_seq_bytes(p_pos - p_ls, p_len);
+            pv = true; p_ls = anchor; p_pos = P; p_off = O; p_len = L;
+        }
+        anchor = P + L;
+        if (SO || LL) {
+            op = WRITE ? p2_emit_coop(dst, op, sm, D + p_ls, p_pos - p_ls, p_off, p_len, lane) : op + p2_seq_bytes(p_pos - p_ls, p_len);
+            if (WRITE) {
+                const u32 sk = dso + (u32)k * P2_LANE_B;
+                for (u32 i = lane; i < SO; i += 32) dst[op + i] = sm[sk + i];
+            }
+            op += SO;
+            pv = LL != 0;
+            if (pv) {
+                p_ls = __shfl_sync(0xffffffffu, l_ls, k); p_pos = __shfl_sync(0xffffffffu, l_pos, k);
+                p_off = __shfl_sync(0xffffffffu, l_off, k); p_len = LL;
+            }
+            anchor = __shfl_sync(0xffffffffu, la, k);
+        }
+    }
+    if (pv) op = WRITE ? p2_emit_coop(dst, op, sm, D + p_ls, p_pos - p_ls, p_off, p_len, lane) : op + p2_seq_bytes(p_pos - p_ls, p_len);
+    return op;
 }
 
 // Compressed size of every block -> csize[b] (0: store it), payload -> scratch + b * 65536 (at most len - 1 bytes).
@@ -265,63 +309,39 @@ lz4_pack_blocks_body(const u8 *__restrict__ in, const PackBlock *__restrict__ bl
                 la = p;
             }
             __syncwarp();
-            // ---- (3) join, in window and lane order.  One sequence is always held back (pv, p_*): the next lane's first
-            // match continues it when it starts where that one ended with the same offset (a match cut at a sub-chunk end).
+            // ---- (3) join.  What the window emits is counted first (its first literal run taken as empty); the output
+            // position and the start of that literal run then come from the window before — a token again, held for a few
+            // instructions only — and the warp writes its sequences while the next windows do the same.
+            const u32 hm = __ballot_sync(0xffffffffu, has);
+            const u32 P0 = __shfl_sync(0xffffffffu, f_pos, hm ? __ffs(hm) - 1 : 0);
+            const u32 bytes0 = hm ? p2_join<false>(dst, 0u, P0, sm, D, dso, lane, has, f_pos, f_off, f_len, so, l_pos, l_off, l_len, l_ls, la) : 0u;
+            const u32 a_last = __shfl_sync(0xffffffffu, la, hm ? 31 - __clz(hm) : 0);
             if (!p2_wait(ctl + 3, w, ctl + 5)) break;
-            u32 op = ctl[8], anchor = ctl[9], p_ls = ctl[11], p_pos = ctl[12], p_off = ctl[13], p_len = ctl[14];
-            bool pv = ctl[10] != 0, fits = ctl[15] != 0;
-            u32 m = fits ? __ballot_sync(0xffffffffu, has) : 0u;
-            while (m) {
-                const int k = __ffs(m) - 1;
-                m &= m - 1;
-                const u32 P = __shfl_sync(0xffffffffu, f_pos, k), O = __shfl_sync(0xffffffffu, f_off, k),
-                          L = __shfl_sync(0xffffffffu, f_len, k), SO = __shfl_sync(0xffffffffu, so, k),
-                          LL = __shfl_sync(0xffffffffu, l_len, k), LA = __shfl_sync(0xffffffffu, la, k);
-                if (pv && P == anchor && O == p_off) p_len += L;
-                else {
-                    if (pv) {
-                        if (op + p2_seq_bytes(p_pos - p_ls, p_len) + 16u > cap) { fits = false; break; }
-                        op = p2_emit_coop(dst, op, sm, D + p_ls, p_pos - p_ls, p_off, p_len, lane);
-                    }
-                    pv = true; p_ls = anchor; p_pos = P; p_off = O; p_len = L;
-                }
-                anchor = P + L;
-                if (SO || LL) {
-                    if (op + p2_seq_bytes(p_pos - p_ls, p_len) + SO + 16u > cap) { fits = false; break; }
-                    op = p2_emit_coop(dst, op, sm, D + p_ls, p_pos - p_ls, p_off, p_len, lane);
-                    const u32 sk = dso + (u32)k * P2_LANE_B;
-                    for (u32 i = lane; i < SO; i += 32) dst[op + i] = sm[sk + i];
-                    op += SO;
-                    pv = LL != 0;
-                    if (pv) {
-                        p_ls = __shfl_sync(0xffffffffu, l_ls, k); p_pos = __shfl_sync(0xffffffffu, l_pos, k);
-                        p_off = __shfl_sync(0xffffffffu, l_off, k); p_len = LL;
-                    }
-                    anchor = LA;
-                }
-            }
-            __syncwarp();
+            const u32 op = ctl[8], anchor = ctl[9];
+            const u32 lit0 = P0 - anchor;                                     // the literals in front of the window's first match
+            const u32 bytes = hm ? bytes0 + lit0 + (lit0 >= 15u ? (lit0 - 15u) / 255u + 1u : 0u) : 0u;
+            const u32 a_out = hm ? a_last : anchor;
+            bool fits = op + bytes + 16u <= cap;
             // the reference's answer to incompressible input is its growing search step (lz4.c:634,957); here: a block whose
             // first 16 KB or more saved less than 1/64 so far is stored
             const u32 seen = w0 + P2_WIN;
-            if (fits && seen >= 16384u && seen < n && op + (seen - (pv ? p_ls : anchor)) + (seen >> 6) > seen) fits = false;
+            if (seen >= 16384u && seen < n && op + bytes + (seen - a_out) + (seen >> 6) > seen) fits = false;
+            __syncwarp();
             if (lane == 0) {
-                if (!fits) ctl[5] = 1;
-                ctl[8] = op; ctl[9] = anchor; ctl[10] = pv; ctl[11] = p_ls; ctl[12] = p_pos; ctl[13] = p_off; ctl[14] = p_len; ctl[15] = fits;
+                if (!fits) { ctl[5] = 1; ctl[15] = 0; }
+                ctl[8] = op + bytes; ctl[9] = a_out;
                 __threadfence_block();
                 ctl[3] = w + 1u;
             }
+            if (!fits) break;
+            if (hm) p2_join<true>(dst, op, anchor, sm, D, dso, lane, has, f_pos, f_off, f_len, so, l_pos, l_off, l_len, l_ls, la);
         }
         __syncthreads();
-        // ---- the held-back sequence and the last literals (lz4.c:1224-1240): everything behind the last match
+        // ---- the last literals (lz4.c:1224-1240): everything behind the last match
         if (warp == 0) {
             u32 op = ctl[8];
-            const u32 anchor = ctl[9], p_ls = ctl[11], p_pos = ctl[12], p_off = ctl[13], p_len = ctl[14];
-            bool fits = ctl[15] != 0;
-            if (fits && ctl[10]) {
-                if (op + p2_seq_bytes(p_pos - p_ls, p_len) + 16u > cap) fits = false;
-                else op = p2_emit_coop(dst, op, sm, D + p_ls, p_pos - p_ls, p_off, p_len, lane);
-            }
+            const u32 anchor = ctl[9];
+            bool fits = ctl[15] != 0 && ctl[5] == 0;
             if (fits) {
                 const u32 lit = n - anchor;
                 if (op + p2_seq_bytes(lit, 0) > cap) fits = false;

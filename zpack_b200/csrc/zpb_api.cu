@@ -82,6 +82,8 @@ struct zpb_ctx {
     DevBuf d_pblk, d_pscratch, d_csize;    // pack: block list, one 64 KB payload slot per block of a round, block sizes
     u64 pack_scratch_blocks = 16384;       // slots per round (ZPB_PACK_SCRATCH_MB, default 1 GiB)
     int p2_per_sm = 1, pk_per_sm = 1;      // resident CTAs of the two pack kernels
+    std::vector<cudaEvent_t> pack_evs;     // three per round: before the block compressor, between, after the framing kernel
+    float pack_blocks_ms = 0.f, pack_frames_ms = 0.f;
     // pipelined host path: private sub-contexts (own stream + scratch), one per worker thread
     std::vector<zpb_ctx *> workers;
     // block-sharded path (one large block-independent LZ4 entry): per-KiB XXH3 stripe sums of the last shard
@@ -202,6 +204,7 @@ extern "C" void zpb_destroy(zpb_ctx *ctx) {
     ctx->d_glist.release(); ctx->d_fdesc.release(); ctx->d_zlist.release(); ctx->d_zlit.release();
     ctx->d_gather.release(); ctx->d_goff.release(); ctx->h_bounce.release();
     ctx->d_pblk.release(); ctx->d_pscratch.release(); ctx->d_csize.release();
+    for (cudaEvent_t e : ctx->pack_evs) cudaEventDestroy(e);
     ctx->d_partials.release(); ctx->d_acc.release();
     for (auto &ev : ctx->evs) if (ev) cudaEventDestroy(ev);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

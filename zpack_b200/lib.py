@@ -50,7 +50,7 @@ assert Entry.itemsize == 64 and File.itemsize == 64 and Block.itemsize == 16
 EXPORTS = [
     "zpb_abi_version", "zpb_create", "zpb_destroy", "zpb_last_error", "zpb_device_info",
     "zpb_launch_count", "zpb_unpack_device", "zpb_unpack_host", "zpb_xxh3_device", "zpb_xxh3_host",
-    "zpb_pack_bound", "zpb_pack_device", "zpb_pack_host", "zpb_last_kernel_ms", "zpb_set_tuning",
+    "zpb_pack_bound", "zpb_pack_device", "zpb_pack_host", "zpb_last_kernel_ms", "zpb_last_pack_stage_ms", "zpb_set_tuning",
     "zpb_last_stage_ms", "zpb_set_fast_path", "zpb_set_overlap", "zpb_last_zstd_ms",
     "zpb_lz4_frame_index", "zpb_unpack_blocks_device", "zpb_blocks_digest", "zpb_last_chain_ms",
     "zpb_unpack_entry_blocks_host",
@@ -92,6 +92,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.zpb_pack_device.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, vp, vp, vp]
     lib.zpb_pack_host.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, vp, vp]
     lib.zpb_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.zpb_last_pack_stage_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.zpb_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.zpb_set_fast_path.argtypes = [vp, C.c_int]
     lib.zpb_set_overlap.argtypes = [vp, C.c_int]
@@ -263,7 +264,9 @@ class Context:
     def last_kernel_ms(self):
         a, b = C.c_float(), C.c_float()
         self.lib.zpb_last_kernel_ms(self.h, C.byref(a), C.byref(b))
-        return {"unpack_ms": a.value, "pack_ms": b.value}
+        c, d = C.c_float(), C.c_float()
+        self.lib.zpb_last_pack_stage_ms(self.h, C.byref(c), C.byref(d))
+        return {"unpack_ms": a.value, "pack_ms": b.value, "pack_blocks_ms": c.value, "pack_frames_ms": d.value}
 
     # ---- unpack + verify -------------------------------------------------------------------
     def unpack_device(self, d_archive, archive_size: int, d_out, out_size: int, entries: np.ndarray,
