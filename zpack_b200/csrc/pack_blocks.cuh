@@ -13,8 +13,9 @@
 //   (1b) PROBE, the only part that has to see the positions in ascending order, as the reference does: hash -> the
 //        table's previous position, the table takes the new one.  Windows are probed strictly one after the other: a
 //        token in shared memory goes from the warp of window w to the warp of window w + 1.
-//   (1c) VERIFY: candidate (or a lower lane of the same step holding the same word, for distances below 32) -> match
-//        distance of every position (0 = none), independent loads.
+//   (1c) VERIFY: candidate -> match distance of every position (0 = none), independent loads.  The table cannot hold
+//        distances below 32 when a step reads it; the one short distance that matters — 1, inside a byte run — is
+//        recognised from the word itself (four equal bytes).
 //   (2)  WALK, one lane per 128-byte sub-chunk: the greedy walk (first position with a candidate, extend both ways,
 //        emit, skip) runs in all 32 sub-chunks at once; a match stops at its sub-chunk's end.  A lane stages its
 //        sequences in shared memory (over the part of the distance array it has already consumed) — except its FIRST
@@ -239,8 +240,7 @@ lz4_pack_blocks_body(const u8 *__restrict__ in, const PackBlock *__restrict__ bl
             }
             __syncwarp();
             if (lane == 0) { __threadfence_block(); ctl[2] = w + 1u; }
-            // ---- (1c) verify: candidate -> match distance (0 = none).  A lower lane of the same step holding the same
-            // word is the nearer candidate (distances below 32 are not in the table yet when the step reads it).
+            // ---- (1c) verify: candidate -> match distance (0 = none)
             u32 nmatch = 0;
             for (u32 s = 0; s < P2_WIN; s += 128) {
                 const u32 e = dso + 2u * (s + 2u * (s >> 7) + lane);
@@ -255,8 +255,7 @@ lz4_pack_blocks_body(const u8 *__restrict__ in, const PackBlock *__restrict__ bl
 #pragma unroll
                 for (u32 k = 0; k < 4; ++k) {
                     const u32 p = w0 + s + 32 * k + lane;
-                    const u32 peers = __match_any_sync(0xffffffffu, x[k]) & ((1u << lane) - 1u);   // lanes past the last probe are the highest: nobody's lower peer
-                    if (peers) c[k] = p - lane + (31u - (u32)__clz(peers));
+                    if (x[k] == __funnelshift_r(x[k], x[k], 8) && p) c[k] = p - 1u;   // four equal bytes: inside a byte run the byte before is the candidate
                     if (p > mflimit) c[k] = 0;
                     y[k] = p2_load32(sm, D + c[k]);
                 }
