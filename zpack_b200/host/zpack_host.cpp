@@ -70,6 +70,14 @@ zpb_ctx *gpu() {
             }
             t_ctx.c = zpb_create(k % n);
         }
+        if (!t_ctx.c) {
+            // No CPU fallback exists.  Callers get ZPACK_ERROR_* codes, but the reference CLI drops some of them
+            // (programs/commands.c:155 ignores zpack_write_file_stream_end), so say it once where a user will see it.
+            static std::atomic<bool> told{false};
+            if (!told.exchange(true))
+                fprintf(stderr, "zpack-b200: no usable CUDA device (%s); every (de)compression call fails, there is no CPU path\n",
+                        zpb_last_error(nullptr));
+        }
     }
     return t_ctx.c;
 }
