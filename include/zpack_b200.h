@@ -210,6 +210,7 @@ int zpb_set_overlap(zpb_ctx *ctx, int enabled);
  * decoded bytes, one run per device, each driven from its own host thread through zpb_unpack_host / zpb_pack_host.
  * No collective, no peer traffic (there is nothing to reduce); every device copies only the archive range it needs. */
 typedef struct zpb_group zpb_group;
+int         zpb_device_count(void);                            /* visible CUDA devices (0: none, or no driver) */
 zpb_group  *zpb_group_create(const int *devices, int n);        /* devices == NULL or n <= 0: every visible device */
 void        zpb_group_destroy(zpb_group *g);
 int         zpb_group_size(const zpb_group *g);

@@ -395,3 +395,59 @@ def test_large_entry_takes_the_block_parallel_path_and_round_trips(oracle):
         rc, ref_out = rd.read(0)
         assert rc == 0 and np.array_equal(ref_out[:total], data)
         rd.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["memory", "file"])
+def test_sequential_reads_are_served_by_the_read_ahead(tmp_path, oracle, mode):
+    """The CLI's `t` / `x` pattern (programs/commands.c): zpack_read_file on reader.file_entries[0], [1], [2] ... in
+    order.  From the second consecutive call on, the drop-in decodes the entries behind the one asked for in the same GPU
+    call and serves the next calls from that cache; bytes, return codes and last_return must be what one call per entry
+    gives: a corrupted entry in the middle still reports FILE_HASH_MISMATCH (15) on its own call only, stored / zstd /
+    lz4 entries mix, an entry whose fields the caller changed after the fill is decoded again, out-of-order reads work."""
+    lib = _lib()
+    from zpack_b200 import container, corpus
+    n = 40
+    sizes = [0 if i == 7 else 1000 + 3001 * i for i in range(n)]
+    bufs = [corpus.entry_bytes(i, s) for i, s in enumerate(sizes)]
+    methods = [(0, 2, 1)[i % 3] if oracle.have_ref() else (0, 2)[i % 2] for i in range(n)]
+    frames = []
+    for b, m in zip(bufs, methods):
+        frames.append(b if m == 0 else oracle.lz4f_encode_port(b, 0, False) if m == 2 else oracle.zstd_compress_ref(b, 3))
+    hashes = [oracle.xxh3_port(b) for b in bufs]
+    arch = container.assemble([f"f{i}" for i in range(n)], frames, sizes, hashes, methods)
+    d = container.parse(arch)
+    bad = next(i for i in range(10, n) if methods[i] == 2)   # an LZ4 entry: flip a literal byte inside its payload
+    arch[int(d.offset[bad]) + int(d.comp_size[bad]) - 9] ^= 0x01
+    r = Reader()
+    if mode == "memory":
+        assert lib.zpack_init_reader_memory_shared(C.byref(r), arch.ctypes.data_as(C.c_void_p), C.c_size_t(len(arch))) == 0
+    else:
+        p = tmp_path / "ra.zpk"
+        arch.tofile(p)
+        assert lib.zpack_init_reader(C.byref(r), str(p).encode()) == 0
+    lib.zpack_read_file.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    esz = C.sizeof(FileEntry)
+    base = C.cast(r.file_entries, C.c_void_p).value
+
+    def read(i):
+        out = np.full(max(sizes[i], 1), 0xCD, np.uint8)
+        rc = lib.zpack_read_file(C.byref(r), base + i * esz, out.ctypes.data, C.c_size_t(len(out)), None)
+        return rc, out[:sizes[i]]
+
+    for order in (range(n), [5, 6, 7, 8, 9, 3, 4, 30, 31, 32, 33, 9, 10, 11, 12, 13], reversed(range(n))):
+        for i in order:
+            rc, out = read(i)
+            if i == bad:
+                assert rc in (15, 10), (i, rc)            # digest mismatch (or a decode error, if the flip broke a sequence)
+            else:
+                assert rc == 0 and np.array_equal(out, bufs[i]), (i, rc, mode)
+    # the caller edits an entry the cache holds: the cached result must not be used for it
+    for i in (20, 21, 22):
+        assert read(i)[0] == 0
+    r.file_entries[23].hash ^= 1
+    assert read(23)[0] == 15
+    r.file_entries[23].hash ^= 1
+    rc, out = read(23)
+    assert rc == 0 and np.array_equal(out, bufs[23])
+    lib.zpack_close_reader(C.byref(r))

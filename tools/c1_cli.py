@@ -64,6 +64,21 @@ def main():
                 r = subprocess.run([os.path.join(REFDIR, "zpack_ref"), "t", arch], cwd=wd, env=env, capture_output=True, text=True)
                 print(json.dumps({"cli": "zpack_ref", "op": f"t on the drop-in's {method} archive", "rc": r.returncode,
                                   "tail": r.stdout[-80:].replace("\n", " | ")}), flush=True)
+    # fixed cost of a drop-in process (CUDA context + kernel setup): `t` on a one-file archive
+    one = os.path.join(wd, "one")
+    os.makedirs(one)
+    corpus.entry_bytes(0, size).tofile(os.path.join(one, "f.bin"))
+    for cli in ("zpack_ref", "dropin_zpack"):
+        exe = os.path.join(REFDIR, cli)
+        arch = os.path.join(wd, f"{cli}_one.zpk")
+        subprocess.run([exe, "c", "-m", "lz4", arch, one], cwd=wd, env=env, capture_output=True)
+        best = None
+        for rep in range(3):
+            t0 = time.perf_counter()
+            r = subprocess.run([exe, "t", arch], cwd=wd, env=env, capture_output=True)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        print(json.dumps({"cli": cli, "op": "t on a one-file archive (process start-up)", "rc": r.returncode, "best_of_3_s": round(best, 4)}), flush=True)
     shutil.rmtree(wd, ignore_errors=True)
 
 

@@ -13,6 +13,11 @@ struct zpb_group {
     std::vector<float> last_ms;     // wall time of each device's share in the last call
 };
 
+extern "C" int zpb_device_count(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
 extern "C" zpb_group *zpb_group_create(const int *devices, int n) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { g_last_error = "no CUDA device"; return nullptr; }

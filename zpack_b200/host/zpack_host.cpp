@@ -61,10 +61,8 @@ zpb_ctx *gpu() {
             const int k = g_next_device.fetch_add(1);
             static std::atomic<int> ndev{0};
             int n = ndev.load();
-            if (n == 0) {            // first caller counts the devices by creating the group once
-                zpb_group *g = zpb_group_create(nullptr, 0);
-                n = g ? zpb_group_size(g) : 1;
-                zpb_group_destroy(g);
+            if (n == 0) {
+                n = zpb_device_count();
                 ndev.store(n > 0 ? n : 1);
                 n = ndev.load();
             }
@@ -92,6 +90,7 @@ zpb_group *gpu_group() {      // call with g_group_lock held
     return g_group;
 }
 int g_ctx_token;  // zpack_create_cctx / _dctx hand out its address: contexts are opaque to callers
+std::atomic<uint64_t> g_reader_gen{1};   // bumped whenever a reader is opened or closed: every read-ahead cache is stale
 
 bool read_at(FILE *fp, zpack_u64 off, void *dst, size_t n, int *err) {
     if (fseeko(fp, (off_t)off, SEEK_SET) != 0) { *err = ZPACK_ERROR_SEEK_FAILED; return false; }
@@ -291,6 +290,7 @@ int zpack_read_cdr(FILE *fp, zpack_u64 cdr_offset, zpack_file_entry **entries, z
 // ------------------------------------------------------------------------------------------------
 // reader
 int zpack_read_archive_memory(zpack_reader *r) {
+    g_reader_gen.fetch_add(1);
     if (!r->buffer) return ZPACK_ERROR_ARCHIVE_NOT_LOADED;
     if (r->file_size < ZPK_MIN_ARCHIVE_BYTES) return ZPACK_ERROR_FILE_TOO_SMALL;
     int rc;
@@ -303,6 +303,7 @@ int zpack_read_archive_memory(zpack_reader *r) {
                                  &r->file_count, &r->comp_size, &r->uncomp_size);
 }
 int zpack_read_archive(zpack_reader *r) {
+    g_reader_gen.fetch_add(1);
     if (!r->file) return ZPACK_ERROR_ARCHIVE_NOT_LOADED;
     if (fseeko(r->file, 0, SEEK_END) != 0) return ZPACK_ERROR_SEEK_FAILED;
     if (!r->file_size) r->file_size = (size_t)ftello(r->file);
@@ -328,6 +329,98 @@ int zpack_read_raw_file(zpack_reader *r, zpack_file_entry *e, zpack_u8 *buffer, 
     return ZPACK_OK;
 }
 
+// ---- read-ahead.  The reference's API hands out one entry per call (its CLI's `t` and `x` walk reader->file_entries
+// in order, programs/commands.c), and a GPU call costs about the same for one entry as for a thousand.  When a thread
+// asks for entry i of a reader's own CDR array right after entry i-1, the entries behind it — up to
+// ZPACK_GPU_READAHEAD_MB of decoded bytes (default 128, 0 = off) — are decoded by the same call into a per-thread
+// cache, and the following calls are served from it.  What a call returns (bytes, status, last_return) is what the
+// individual call would have returned: same kernels, same entry fields (a cached result is only used while the
+// entry's fields are what they were when it was decoded).
+struct ReadAhead {
+    const zpack_reader *owner = nullptr;
+    uint64_t gen = 0;
+    zpack_u64 last_idx = ~0ull;                 // entry index of this thread's previous zpack_read_file on `owner`
+    zpack_u64 first = 0, count = 0;             // cached entries [first, first + count)
+    zpack_u8 *out = nullptr;                    // pinned
+    size_t out_cap = 0;
+    std::vector<zpack_u64> off;
+    std::vector<int32_t> st;
+    std::vector<zpack_file_entry> seen;         // the entries' fields at decode time (filename unused)
+    std::vector<zpb_entry> d;
+    std::vector<zpack_u8> staged;
+    ~ReadAhead() { zpb_host_free(out); }
+};
+thread_local ReadAhead t_ra;
+size_t readahead_bytes() {
+    static const size_t v = [] {
+        const char *e = getenv("ZPACK_GPU_READAHEAD_MB");
+        return (size_t)(e ? atoll(e) : 128) << 20;
+    }();
+    return v;
+}
+bool same_fields(const zpack_file_entry &a, const zpack_file_entry &b) {
+    return a.offset == b.offset && a.comp_size == b.comp_size && a.uncomp_size == b.uncomp_size && a.hash == b.hash &&
+           a.comp_method == b.comp_method;
+}
+bool plain_entry(const zpack_reader *r, const zpack_file_entry &e) {      // what zpack_read_file would hand to the GPU as one chain
+    return e.comp_size && e.offset < r->file_size && e.comp_size < r->file_size - e.offset && known_method(e.comp_method) &&
+           !(e.comp_method == ZPACK_COMPRESSION_LZ4 && e.comp_size >= (4u << 20));
+}
+// Decodes entries [idx, idx + k) into the cache; false = nothing cached (the caller takes the one-entry path).
+bool readahead_fill(zpack_reader *r, zpack_u64 idx) {
+    ReadAhead &c = t_ra;
+    const size_t budget = readahead_bytes();
+    zpack_u64 k = 0, bytes = 0;
+    while (idx + k < r->file_count && k < 65536) {
+        const zpack_file_entry &e = r->file_entries[idx + k];
+        if (!plain_entry(r, e)) break;
+        const zpack_u64 slot = (e.uncomp_size + 15) & ~15ull;
+        if (bytes + slot > budget) break;
+        bytes += slot;
+        ++k;
+    }
+    c.count = 0;
+    if (k < 2) return false;
+    zpb_ctx *g = gpu();
+    if (!g) return false;
+    if (c.out_cap < bytes + 16) {
+        zpb_host_free(c.out);
+        c.out = (zpack_u8 *)zpb_host_alloc(budget + 16);
+        c.out_cap = c.out ? budget + 16 : 0;
+        if (!c.out) return false;
+    }
+    try {
+        c.off.resize((size_t)k); c.st.assign((size_t)k, 0); c.seen.assign(r->file_entries + idx, r->file_entries + idx + k);
+        c.d.resize((size_t)k);
+        if (!r->buffer) {
+            zpack_u64 total = 0;
+            for (zpack_u64 i = 0; i < k; ++i) total += (c.seen[i].comp_size + 15) & ~15ull;
+            c.staged.resize((size_t)total + 16);
+        }
+    } catch (const std::exception &) { return false; }
+    zpack_u64 pos = 0, spos = 0;
+    for (zpack_u64 i = 0; i < k; ++i) {
+        const zpack_file_entry &e = c.seen[i];
+        zpb_entry &d = c.d[i];
+        memset(&d, 0, sizeof d);
+        d.src_off = e.offset; d.comp_size = e.comp_size; d.dst_off = pos; d.dst_cap = e.uncomp_size;
+        d.uncomp_size = e.uncomp_size; d.hash = e.hash; d.method = e.comp_method;
+        if (!r->buffer) {
+            int err;
+            if (!read_at(r->file, e.offset, c.staged.data() + spos, (size_t)e.comp_size, &err)) return false;
+            d.src_off = spos;
+            spos += (e.comp_size + 15) & ~15ull;
+        }
+        c.off[i] = pos;
+        pos += (e.uncomp_size + 15) & ~15ull;
+    }
+    const zpack_u8 *arch = r->buffer ? r->buffer : c.staged.data();
+    const zpack_u64 asz = r->buffer ? r->file_size : c.staged.size();
+    if (zpb_unpack_host(g, arch, asz, c.out, c.out_cap, c.d.data(), k, c.st.data(), nullptr) != ZPB_OK) return false;
+    c.owner = r; c.gen = g_reader_gen.load(); c.first = idx; c.count = k;
+    return true;
+}
+
 // zpack_read_file (lib/zpack_read.c:326-471) = a GPU batch of one
 int zpack_read_file(zpack_reader *r, zpack_file_entry *e, zpack_u8 *buffer, size_t max_size, void *) {
     if (e->comp_size == 0) return ZPACK_OK;                                          // :328
@@ -335,6 +428,23 @@ int zpack_read_file(zpack_reader *r, zpack_file_entry *e, zpack_u8 *buffer, size
     // :331 (strict: offset + comp_size < file_size), written so that it cannot wrap
     if (e->offset >= r->file_size || e->comp_size >= r->file_size - e->offset) return ZPACK_ERROR_FILE_OFFSET_INVALID;
     if (!known_method(e->comp_method)) return ZPACK_ERROR_COMP_METHOD_INVALID;       // :459-461
+    if (!r->file && !r->buffer) return ZPACK_ERROR_ARCHIVE_NOT_LOADED;
+    if (readahead_bytes() && r->file_entries && e >= r->file_entries && e < r->file_entries + r->file_count) {
+        ReadAhead &c = t_ra;
+        const zpack_u64 idx = (zpack_u64)(e - r->file_entries);
+        const bool mine = c.owner == r && c.gen == g_reader_gen.load();
+        const bool sequential = mine && c.last_idx + 1 == idx;
+        if (!mine) { c.owner = r; c.gen = g_reader_gen.load(); c.count = 0; }
+        c.last_idx = idx;
+        bool hit = mine && idx >= c.first && idx < c.first + c.count && same_fields(*e, c.seen[(size_t)(idx - c.first)]);
+        if (!hit && sequential && plain_entry(r, *e)) hit = readahead_fill(r, idx);
+        if (hit) {
+            const size_t k = (size_t)(idx - c.first);
+            memcpy(buffer, c.out + c.off[k], (size_t)e->uncomp_size);
+            r->last_return = (size_t)c.st[k];
+            return c.st[k];
+        }
+    }
     if (r->file) {                                                                   // :336-344
         std::vector<zpack_u8> comp;
         try { comp.resize((size_t)e->comp_size); } catch (const std::exception &) { return ZPACK_ERROR_MALLOC_FAILED; }
@@ -478,6 +588,7 @@ int zpack_init_reader_memory_shared(zpack_reader *r, zpack_u8 *buffer, size_t si
 }
 void zpack_reset_reader_dctx(zpack_reader *) {}   // GPU decodes are one-shot: nothing carries over between calls
 void zpack_close_reader(zpack_reader *r) {
+    g_reader_gen.fetch_add(1);
     if (r->file) fclose(r->file);
     if (!r->buffer_shared) free(r->buffer);
     if (r->file_entries) {

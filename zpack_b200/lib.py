@@ -53,7 +53,7 @@ EXPORTS = [
     "zpb_pack_bound", "zpb_pack_device", "zpb_pack_host", "zpb_last_kernel_ms", "zpb_last_pack_stage_ms", "zpb_set_tuning",
     "zpb_last_stage_ms", "zpb_set_fast_path", "zpb_set_overlap", "zpb_last_zstd_ms",
     "zpb_lz4_frame_index", "zpb_unpack_blocks_device", "zpb_blocks_digest", "zpb_last_chain_ms",
-    "zpb_unpack_entry_blocks_host",
+    "zpb_unpack_entry_blocks_host", "zpb_device_count",
 ]
 
 
