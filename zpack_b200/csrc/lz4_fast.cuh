@@ -421,10 +421,15 @@ ZPB_DEVINL void
 lz4_fast_parse_body(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, u32 *parse_list,
                     u32 plist_cap, u32 *counters, u32 *work_counter, u32 *desc, u32 all_lists) {
     // J = 4 walks the heavy list, then the medium one; J = 1 the light one — or, when the batch is so large that even
-    // unsplit walks fill the GPU (all_lists: the host decides), all three, heavy first (K0 sorts blocks by compressed size)
-    const u32 n_heavy = (J == 4 || all_lists) ? counters[8] : 0u;
-    const u32 n_medium = (J == 4 || all_lists) ? counters[9] : 0u;
-    const u32 nitems = J == 4 ? n_heavy + n_medium : n_heavy + n_medium + counters[10];
+    // unsplit walks fill the GPU (all_lists bit 0: the host decides), all three, heavy first (K0 sorts blocks by compressed
+    // size).  With the split walk the light list is parsed FIRST (bit 2: remember its length in counters[17]) so that the
+    // execute kernel has entries to start on, and the blocks the split walk gives back, which it appends to the light
+    // list, are walked by a last launch (bit 1: only the items from counters[17] on).
+    const u32 n_heavy = (J == 4 || (all_lists & 1u)) ? counters[8] : 0u;
+    const u32 n_medium = (J == 4 || (all_lists & 1u)) ? counters[9] : 0u;
+    const u32 light_skip = (J == 1 && (all_lists & 2u)) ? counters[17] : 0u;
+    const u32 nitems = J == 4 ? n_heavy + n_medium : n_heavy + n_medium + counters[10] - light_skip;
+    if (J == 1 && (all_lists & 4u) && blockIdx.x == 0 && threadIdx.x == 0) counters[17] = counters[10];
     ZPB_DYN_SMEM(k1_smem);
     const u32 lane = threadIdx.x & 31u;
     const u32 sj = lane & (J - 1);                 // this lane's segment
@@ -468,7 +473,7 @@ lz4_fast_parse_body(const u8 *__restrict__ archive, u64 asz, FastBlock *fb, u32 
                     if (w < nitems) {
                         slot = w < n_heavy ? parse_list[w]
                              : w < n_heavy + n_medium ? parse_list[(u64)plist_cap + (w - n_heavy)]
-                                                      : parse_list[2ull * plist_cap + (w - n_heavy - n_medium)];
+                                                      : parse_list[2ull * plist_cap + (w - n_heavy - n_medium + light_skip)];
                         const FastBlock B = fb[slot];
                         bszv = B.bsz;
                         skew = sg.open(archive, asz, B.src, row_s);

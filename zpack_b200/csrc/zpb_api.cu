@@ -456,15 +456,31 @@ static int unpack_device_impl(zpb_ctx *ctx, const u8 *d_archive, u64 archive_siz
         static const int split_env = [] { const char *e = getenv("ZPB_PARSE_SPLIT"); return e ? atoi(e) : -1; }();
         const bool split = split_env >= 0 ? split_env != 0 : slots <= 40000;
         if (split) {
-            lz4_fast_parse4_kernel<<<ctx->sm_count * k1_ctas, K1_THREADS, K1_THREADS * K1_ROW, sp>>>(
+            // The light list first (stored blocks, runs: parsed within microseconds), so that the execute kernel, which
+            // starts with the parse kernels, finds entries it can work on while text and record blocks are being walked;
+            // then the split walk; then the blocks the split walk gave back (appended to the light list).
+            lz4_fast_parse_kernel<<<ctx->sm_count, K1_THREADS, K1_THREADS * K1_ROW, sp>>>(
+                d_archive, archive_size, (FastBlock *)ctx->d_fb.p, (u32 *)ctx->d_plist.p, (u32)(slots + 1), cnt, cnt + 13,
+                (u32 *)ctx->d_fdesc.p, 4u);
+            CK(ctx, cudaGetLastError());
+            // Split walks of one batch end at about the same time, so three resident parse CTAs per SM (209 KB of shared
+            // memory) would keep every execute CTA out until then.  When two per SM hold all the lanes the batch needs,
+            // launch two: the third slot goes to an execute CTA.
+            static const int p4_env = [] { const char *e = getenv("ZPB_PARSE4_CTAS"); return e ? atoi(e) : 0; }();
+            const int p4_ctas = p4_env > 0 ? p4_env : (overlap && 4ull * slots <= (u64)ctx->sm_count * 2 * K1_THREADS ? 2 : k1_ctas);
+            lz4_fast_parse4_kernel<<<ctx->sm_count * p4_ctas, K1_THREADS, K1_THREADS * K1_ROW, sp>>>(
                 d_archive, archive_size, (FastBlock *)ctx->d_fb.p, (u32 *)ctx->d_plist.p, (u32)(slots + 1), cnt, cnt + 2,
                 (u32 *)ctx->d_fdesc.p);
             CK(ctx, cudaGetLastError());
-            ctx->launches += 1;
+            lz4_fast_parse_kernel<<<ctx->sm_count, K1_THREADS, K1_THREADS * K1_ROW, sp>>>(
+                d_archive, archive_size, (FastBlock *)ctx->d_fb.p, (u32 *)ctx->d_plist.p, (u32)(slots + 1), cnt, cnt + 18,
+                (u32 *)ctx->d_fdesc.p, 2u);
+            ctx->launches += 2;
+        } else {
+            lz4_fast_parse_kernel<<<ctx->sm_count * k1_ctas, K1_THREADS, K1_THREADS * K1_ROW, sp>>>(
+                d_archive, archive_size, (FastBlock *)ctx->d_fb.p, (u32 *)ctx->d_plist.p, (u32)(slots + 1), cnt, cnt + 13,
+                (u32 *)ctx->d_fdesc.p, 1u);
         }
-        lz4_fast_parse_kernel<<<ctx->sm_count * k1_ctas, K1_THREADS, K1_THREADS * K1_ROW, sp>>>(
-            d_archive, archive_size, (FastBlock *)ctx->d_fb.p, (u32 *)ctx->d_plist.p, (u32)(slots + 1), cnt, cnt + 13,
-            (u32 *)ctx->d_fdesc.p, split ? 0u : 1u);
         CK(ctx, cudaGetLastError());
         CK(ctx, cudaEventRecord(ctx->ev_p1, sp));
         CK(ctx, cudaEventRecord(ctx->ev_x0, s));
