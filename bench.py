@@ -622,6 +622,23 @@ def run_ours(args):
             b.record()
             torch.cuda.synchronize()
             pcie[name] = 3 * nb / (a.elapsed_time(b) * 1e-3) / 1e9
+        # the same D2H while an H2D stream is busy in the other direction — the condition of the e2e pipeline, which
+        # uploads the next chunk's compressed bytes while decoded bytes go down
+        side = torch.cuda.Stream()
+        h_src2 = h_arch[:min(len(arch), nb)]
+        d_dst2 = torch.empty(len(h_src2), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(side):
+            for _ in range(6):
+                d_dst2.copy_(h_src2, non_blocking=True)
+        a.record()
+        for _ in range(3):
+            h_out[:nb].copy_(d_out[:nb], non_blocking=True)
+        b.record()
+        torch.cuda.synchronize()
+        pcie["d2h_GBps_while_h2d"] = 3 * nb / (a.elapsed_time(b) * 1e-3) / 1e9
+        del d_dst2
     clocks = sampler.stop() if rank == 0 else None
 
     stages = {k: float(np.mean([s[k] for s in stage_ms])) for k in stage_ms[0]}

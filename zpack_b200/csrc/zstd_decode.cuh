@@ -98,13 +98,16 @@ struct ZWarp {
 #define ZS_ERR (-1)
 #define ZS_LIT_SCRATCH (ZS_BLOCK_MAX + 64u)  // per-warp literal buffer in global memory
 
-struct ZsCell { u32 x, y; };
+// One 4-byte cell per FSE state: next-state base [0,10) | state bits [10,14) | symbol code [14,20) | extra bits [20,25).
+// The code's base value comes from the constant tables below (OF: 1 << code).
+typedef u32 ZsCell;
+#define ZS_CELL(base, nb, code, eb) ((base) | ((nb) << 10) | ((code) << 14) | ((eb) << 20))
 
 // Per-warp decoder state in shared memory.
 struct ZstdShared {
-    // LL [0,512) | OF [512,768) | ML [768,1280).  One 8-byte cell carries everything a sequence needs from a
-    // state (the layout idea of ZSTD_seqSymbol, zstd_decompress_block.h): x = next-state base | nbits << 16 |
-    // extra bits << 24, y = base value (OF: 1 << code, so that value = y + extra bits in all three cases).
+    // LL [0,512) | OF [512,768) | ML [768,1280).  One 4-byte cell per state (ZsCell above; the layout idea of
+    // ZSTD_seqSymbol, zstd_decompress_block.h, with the base value looked up from the code): 5 KB instead of 10 KB per
+    // warp, which is what bounds the number of frames resident on an SM.
     ZsCell fse[1280];
     u32 wfse[64];    // FSE table of the Huffman weights (tableLog <= 6)
     u16 huf[4096];   // sym | nbits << 8, indexed by the next huf_log bits
@@ -336,13 +339,12 @@ ZPB_DEVINL void zs_code_info(u32 which, u32 sym, u32 *eb, u32 *bv) {
     else { *eb = ZS_ML_BITS[sym]; *bv = ZS_ML_BASE[sym]; }
 }
 
-// Sequence decode table from normalized counts, 8-byte cells; serial.  The symbol spread goes to a u32
-// staging area in the upper half of the table's own storage and is converted in place, ascending
-// (cell u is written at words 2u, 2u+1 < size + u', the staging word of any cell u' > u not yet read).
+// Sequence decode table from normalized counts; serial.  The symbol spread is staged in the table's own words and
+// converted in place.
 template <typename NormT>
 ZPB_DEVINL int zs_fse_build_seq(ZsCell *cell, u16 *next, const NormT *norm, int max_sym, int log, u32 which) {
     int size = 1 << log, high = size - 1;
-    u32 *stage = reinterpret_cast<u32 *>(cell) + size;
+    u32 *stage = cell;
     for (int s = 0; s <= max_sym; ++s) {
         if (norm[s] == -1) { stage[high--] = (u32)s; next[s] = 1; }
         else next[s] = (u16)norm[s];
@@ -360,10 +362,7 @@ ZPB_DEVINL int zs_fse_build_seq(ZsCell *cell, u16 *next, const NormT *norm, int 
         u32 nb = (u32)log - (u32)zs_highbit(n);
         u32 eb, bv;
         zs_code_info(which, s, &eb, &bv);
-        ZsCell c;
-        c.x = (((n << nb) - (u32)size) & 0xFFFFu) | (nb << 16) | (eb << 24);
-        c.y = bv;
-        cell[u] = c;
+        cell[u] = ZS_CELL(((n << nb) - (u32)size) & 0x3FFu, nb, s, eb);
     }
     return 0;
 }
@@ -380,10 +379,7 @@ ZPB_DEVINL int zs_seq_table(ZstdShared &S, u32 base, u32 which, int mode, const 
         if (len == 0 || (int)src[0] > max_sym) return ZS_ERR;
         u32 eb, bv;
         zs_code_info(which, src[0], &eb, &bv);
-        ZsCell c;
-        c.x = eb << 24;
-        c.y = bv;
-        S.fse[base] = c;
+        S.fse[base] = ZS_CELL(0u, 0u, (u32)src[0], eb);
         S.log[which] = 0;
         return 1;
     }
@@ -705,9 +701,11 @@ ZPB_DEVINL int zs_block(const ZWarp &w, ZstdShared &S, const u8 *src, u32 len, u
                     // read order (zstd_decompress_block.c:937-1039): OF, ML, LL extra bits, then the LL, ML, OF
                     // state updates (skipped after the last sequence).  All widths are known from the cells,
                     // so the six fields are cut from one 64-bit window at independent offsets.
-                    const u32 e_of = co.x >> 24, e_ml = cm.x >> 24, e_ll = cl.x >> 24;
-                    const u32 n_ll = more ? (cl.x >> 16) & 0xFFu : 0u, n_ml = more ? (cm.x >> 16) & 0xFFu : 0u,
-                              n_of = more ? (co.x >> 16) & 0xFFu : 0u;
+                    const u32 e_of = co >> 20, e_ml = cm >> 20, e_ll = cl >> 20;
+                    const u32 n_ll = more ? (cl >> 10) & 0xFu : 0u, n_ml = more ? (cm >> 10) & 0xFu : 0u,
+                              n_of = more ? (co >> 10) & 0xFu : 0u;
+                    const u32 v_of = 1u << ((co >> 14) & 0x3Fu), v_ml = ZS_ML_BASE[(cm >> 14) & 0x3Fu],
+                              v_ll = ZS_LL_BASE[(cl >> 14) & 0x3Fu];
                     const u32 c1 = e_of, c2 = c1 + e_ml, c3 = c2 + e_ll, c4 = c3 + n_ll, c5 = c4 + n_ml,
                               total = c5 + n_of;
                     u32 ofv, ml, ll;
@@ -716,23 +714,23 @@ ZPB_DEVINL int zs_block(const ZWarp &w, ZstdShared &S, const u8 *src, u32 len, u
                         const u32 avail = (u32)(b.left - b.wpos);        // 1..64 unread bits at the top of the window
                         const u64 v = b.win << (64u - avail);             // top-aligned (avail >= total >= ... > 0 or unused)
                         const u32 hi = (u32)(v >> 32), lo = (u32)v;
-                        ofv = co.y + zs_field(hi, lo, 0, e_of);
-                        ml = cm.y + zs_field(hi, lo, c1, e_ml);
-                        ll = cl.y + zs_field(hi, lo, c2, e_ll);
+                        ofv = v_of + zs_field(hi, lo, 0, e_of);
+                        ml = v_ml + zs_field(hi, lo, c1, e_ml);
+                        ll = v_ll + zs_field(hi, lo, c2, e_ll);
                         if (more) {
-                            sl = (cl.x & 0xFFFFu) + zs_field(hi, lo, c3, n_ll);
-                            sm = (cm.x & 0xFFFFu) + zs_field(hi, lo, c4, n_ml);
-                            so = (co.x & 0xFFFFu) + zs_field(hi, lo, c5, n_of);
+                            sl = (cl & 0x3FFu) + zs_field(hi, lo, c3, n_ll);
+                            sm = (cm & 0x3FFu) + zs_field(hi, lo, c4, n_ml);
+                            so = (co & 0x3FFu) + zs_field(hi, lo, c5, n_of);
                         }
                         b.left -= (int)total;
                     } else {  // > 64 bits in one sequence (huge offset codes): field by field
-                        ofv = co.y + zs_rb_read(b, e_of);
-                        ml = cm.y + zs_rb_read(b, e_ml);
-                        ll = cl.y + zs_rb_read(b, e_ll);
+                        ofv = v_of + zs_rb_read(b, e_of);
+                        ml = v_ml + zs_rb_read(b, e_ml);
+                        ll = v_ll + zs_rb_read(b, e_ll);
                         if (more) {
-                            sl = (cl.x & 0xFFFFu) + zs_rb_read(b, n_ll);
-                            sm = (cm.x & 0xFFFFu) + zs_rb_read(b, n_ml);
-                            so = (co.x & 0xFFFFu) + zs_rb_read(b, n_of);
+                            sl = (cl & 0x3FFu) + zs_rb_read(b, n_ll);
+                            sm = (cm & 0x3FFu) + zs_rb_read(b, n_ml);
+                            so = (co & 0x3FFu) + zs_rb_read(b, n_of);
                         }
                     }
                     u32 off;
@@ -751,7 +749,7 @@ ZPB_DEVINL int zs_block(const ZWarp &w, ZstdShared &S, const u8 *src, u32 len, u
                     S.seq_ll[j] = ll; S.seq_ml[j] = ml; S.seq_off[j] = off;
                     if (!more) {
                         // the library updates the states once more, then wants every bit consumed (:1195)
-                        int tail = (int)(((cl.x >> 16) & 0xFFu) + ((cm.x >> 16) & 0xFFu) + ((co.x >> 16) & 0xFFu));
+                        int tail = (int)(((cl >> 10) & 0xFu) + ((cm >> 10) & 0xFu) + ((co >> 10) & 0xFu));
                         if (b.left > tail) err = 1;
                     }
                 }
@@ -942,7 +940,7 @@ struct ZsHasher {
     ZPB_DEVINL void advance(u64 front, const ZWarp &w) { s.advance(front, w.g); }
 };
 
-__global__ void __launch_bounds__(ZS_WARPS * 32)
+__global__ void __launch_bounds__(ZS_WARPS * 32, 7)
 zstd_unpack_kernel(const u8 *__restrict__ archive, u8 *__restrict__ out, const zpb_entry *__restrict__ entries,
                    const u32 *__restrict__ list, const u32 *__restrict__ n_ptr, u32 *counter, u8 *scratch,
                    int *status, u64 *digest) {
