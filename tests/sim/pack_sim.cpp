@@ -20,3 +20,13 @@ extern "C" int sim_lz4_pack_blocks(const uint8_t *in, const uint64_t *src_off, c
     }, seed);
     return 0;
 }
+
+// ---- the zstd block encoder (zpack_b200/csrc/zstd_encode.cuh) is plain serial code per block: called directly
+#include "../../zpack_b200/csrc/zstd_encode.cuh"
+extern "C" uint32_t sim_zstd_encode_block(const uint8_t *lz, uint32_t csize, uint32_t raw_len, uint8_t *out) {
+    static ZeTables T;
+    static bool built = false;
+    if (!built) { ze_build_tables(T); built = true; }
+    std::vector<u64> seq(ZE_SEQ_MAX);
+    return ze_encode_block(lz, csize, raw_len, out, seq.data(), T);
+}

@@ -95,6 +95,27 @@ def test_ratio_against_the_reference_level0(gpu_ctx, oracle):
     assert ratio_ours > 0.85 * ratio_ref
 
 
+def test_zstd_ratio_against_the_reference_level3(gpu_ctx, oracle):
+    """Every class of the corpus through the zstd writer: frames decode in the oracle's port (and in ZSTD_decompress),
+    ratio printed next to ZSTD_compress level 3 (the match finder is the LZ4 block compressor's, literals are raw)."""
+    n, size = 64, 131072
+    bufs, frames, comp, digest, status = _pack(gpu_ctx, [size] * n, host=False, method=1)
+    assert (status == 0).all()
+    for i in range(0, n, 5):
+        rc, got = oracle.zstd_decode_port(frames[i], size)
+        assert rc == 0 and np.array_equal(got[:size], bufs[i]), i
+        if oracle.have_ref():
+            assert np.array_equal(oracle.zstd_decompress_ref(frames[i], size), bufs[i])
+    ours = n * size / float(comp.sum())
+    lz4 = n * size / float(_pack(gpu_ctx, [size] * n, host=False)[2].sum())
+    msg = f"\nzstd writer ratio on zpk-synth-v1: GPU {ours:.3f} (its LZ4 frames: {lz4:.3f})"
+    if oracle.have_ref():
+        ref = n * size / float(sum(len(oracle.zstd_compress_ref(b, 3)) for b in bufs))
+        msg += f" vs ZSTD_compress level 3 {ref:.3f}"
+    print(msg)
+    assert ours > lz4
+
+
 def test_pack_then_unpack_on_gpu(gpu_ctx):
     sizes = [131072] * 64 + SIZES
     bufs, frames, comp, digest, status = _pack(gpu_ctx, sizes, host=False, first=100)
@@ -115,11 +136,14 @@ def test_none_method_and_error_statuses(gpu_ctx, oracle):
     assert (status == 0).all()
     for b, fr, dg in zip(bufs, frames, digest):
         assert np.array_equal(fr, b) and int(dg) == oracle.xxh3_port(b)
-    # zstd: valid frames of Raw_Blocks (the entropy-coding compressor is SURVEY §8(f) row 3); the unmodified reference
-    # decoder and our GPU decoder must both read them back
+    # zstd: frames of 64 KB Compressed_Blocks built from the block compressor's matches (raw literals + predefined-mode
+    # FSE sequences, zstd_encode.cuh), Raw_Blocks where that does not pay; the oracle's port, the unmodified reference
+    # decoder and our GPU decoder must all read them back
     sizes = [0, 1, 1000, 131072, 131073, 400000]
     bufs, frames, comp, digest, status = _pack(gpu_ctx, sizes, method=1)
     assert (status == 0).all(), status
+    assert all(len(fr) <= gpu_ctx.pack_bound(1, len(b)) for fr, b in zip(frames, bufs))
+    assert comp[3] < 0.8 * sizes[3] and comp[5] < 0.8 * sizes[5]                  # it does compress (records / text classes)
     for b, fr, dg in zip(bufs, frames, digest):
         assert int(dg) == oracle.xxh3_port(b)
         rc, got = oracle.zstd_decode_port(fr, len(b))

@@ -105,3 +105,56 @@ def test_crafted_inputs(sim, oracle):
         bufs += [plain[i:i + 65536] for i in range(0, len(plain), 65536)]
     assert bufs
     check(sim, oracle, bufs)
+
+
+def zstd_frame(bodies, blocks):
+    """A zstd frame around per-block bodies (None = Raw_Block), laid out as pack_kernel.cuh does: magic, FHD 0xC0
+    (8-byte content size), window descriptor 0x38 (128 KB), 3-byte block headers."""
+    total = sum(len(b) for b in blocks)
+    fr = bytearray([0x28, 0xB5, 0x2F, 0xFD, 0xC0, 0x38]) + total.to_bytes(8, "little")
+    for k, (body, raw) in enumerate(zip(bodies, blocks)):
+        last = 1 if k + 1 == len(blocks) else 0
+        if body is None:
+            fr += (last | (len(raw) << 3)).to_bytes(3, "little") + bytes(raw)
+        else:
+            fr += (last | (2 << 1) | (len(body) << 3)).to_bytes(3, "little") + bytes(body)
+    return np.frombuffer(bytes(fr), np.uint8)
+
+
+def test_zstd_blocks_from_the_lz4_matches_decode_with_the_oracle_and_the_reference(sim, oracle):
+    """zstd_encode.cuh: the block compressor's LZ4 payload -> a zstd Compressed_Block (raw literals + predefined-mode FSE
+    sequences).  Frames must decode in the oracle's zstd port and in the UNMODIFIED reference's ZSTD_decompress."""
+    sim.sim_zstd_encode_block.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    sim.sim_zstd_encode_block.restype = C.c_uint32
+    rng = np.random.default_rng(5)
+    blocks = [corpus.entry_bytes(i, 65536) for i in range(8)]
+    blocks += [corpus.entry_bytes(20 + i, s) for i, s in enumerate((70, 300, 4097, 40000))]
+    blocks += [np.zeros(65536, np.uint8), np.frombuffer((b"abcdefgh" * 9000)[:65536], np.uint8),
+               rng.integers(0, 4, 65536, dtype=np.uint8), rng.integers(0, 256, 5000, dtype=np.uint8)]
+    packed = pack_blocks(sim, blocks)
+    bodies, lz_total, z_total = [], 0, 0
+    for b, (c, payload) in zip(blocks, packed):
+        body = None
+        if c:
+            out = np.zeros(65536 + 64, np.uint8)
+            n = sim.sim_zstd_encode_block(payload.ctypes.data, c, len(b), out.ctypes.data)
+            assert n < len(b)
+            assert (out[65536:] == 0).all()
+            if n:
+                body = out[:n].copy()
+        bodies.append(body)
+        lz_total += c if c else len(b)
+        z_total += len(body) if body is not None else len(b)
+    assert sum(x is not None for x in bodies) >= len(blocks) - 4          # the random blocks stay raw
+    for k in range(len(blocks)):                       # one frame per block, and all of them in one frame
+        fr = zstd_frame([bodies[k]], [blocks[k]])
+        rc, got = oracle.zstd_decode_port(fr, len(blocks[k]))
+        assert rc == 0 and np.array_equal(got[:len(blocks[k])], blocks[k]), k
+    fr = zstd_frame(bodies, blocks)
+    plain = np.concatenate(blocks)
+    rc, got = oracle.zstd_decode_port(fr, len(plain))
+    assert rc == 0 and np.array_equal(got[:len(plain)], plain)
+    if oracle.have_ref():
+        assert np.array_equal(oracle.zstd_decompress_ref(fr, len(plain)), plain)
+        ref = sum(len(oracle.zstd_compress_ref(b, 3)) for b in blocks)
+        print(f"\nzstd blocks: {z_total} bytes (LZ4 payloads {lz_total}) vs ZSTD_compress level 3: {ref}")

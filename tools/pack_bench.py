@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--size", type=int, default=131072)
     ap.add_argument("--classes", default="-1")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--method", type=int, default=2, help="2 = LZ4 (default), 1 = zstd")
     a = ap.parse_args()
     import multiprocessing as mp
     import torch
@@ -47,13 +48,13 @@ def main():
         ref_comp = sum(r[1] for r in res)
         n = a.entries
         f = np.zeros(n, zlib.File)
-        cap = ctx.pack_bound(2, a.size)
+        cap = ctx.pack_bound(a.method, a.size)
         slot = (cap + 15) & ~15
         f["src_off"] = np.arange(n, dtype=np.uint64) * a.size
         f["size"] = a.size
         f["dst_off"] = np.arange(n, dtype=np.uint64) * slot
         f["dst_cap"] = cap
-        f["method"] = 2
+        f["method"] = a.method
         d_in = torch.from_numpy(data.reshape(-1)).cuda()
         d_out = torch.empty(n * slot, dtype=torch.uint8, device="cuda")
         ms = []
@@ -64,7 +65,7 @@ def main():
         assert (st == 0).all()
         t = float(np.median(ms))
         unc = n * a.size
-        print(json.dumps({"class": names[cls], "entries": n, "pack_kernel_ms": round(t, 3),
+        print(json.dumps({"method": a.method, "class": names[cls], "entries": n, "pack_kernel_ms": round(t, 3),
                           "uncomp_GBps": round(unc / t / 1e6, 1), "traffic_GBps": round((unc + int(comp.sum())) / t / 1e6, 1),
                           "ratio_gpu": round(unc / float(comp.sum()), 3), "ratio_reference_level0_sampled": round(unc / ref_comp, 3)}),
               flush=True)

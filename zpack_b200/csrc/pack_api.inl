@@ -9,9 +9,18 @@ extern "C" uint64_t zpb_pack_bound(uint32_t method, uint64_t size) {
     // (same role as LZ4F_compressBound at lib/zpack_write.c:141; an empty file is 11 bytes, as in the reference)
     if (method == ZPB_METHOD_LZ4) return 7 + 4 * ((size + 65535) / 65536) + size + 4;
     if (method == ZPB_METHOD_NONE) return size;
-    // zstd: frame header 14 + per 128 KB block a 3-byte header + raw payload (pack_kernel.cuh writes Raw_Blocks)
-    if (method == ZPB_METHOD_ZSTD) return 14 + 3 * (size ? (size + 131071) / 131072 : 1) + size;
+    // zstd: frame header 14 + per 64 KB block a 3-byte header + at most the raw payload
+    if (method == ZPB_METHOD_ZSTD) return 14 + 3 * (size ? (size + 65535) / 65536 : 1) + size;
     return 0;
+}
+
+// which files have blocks in the stage-1 list: LZ4 below the HC levels and zstd, in bounds, with a slot that holds the worst case
+static bool pack_file_has_blocks(const zpb_file &f, u64 in_size, u64 out_size) {
+    if (f.src_off > in_size || f.size > in_size - f.src_off || f.dst_off > out_size || f.dst_cap > out_size - f.dst_off) return false;
+    const u64 fb = (f.size + 65535) >> 16;
+    if (f.method == ZPB_METHOD_LZ4) return f.level < 3 && f.dst_cap >= 7 + 4 * fb + f.size + 4;
+    if (f.method == ZPB_METHOD_ZSTD) return f.dst_cap >= 14 + 3 * (f.size ? fb : 1) + f.size;
+    return false;
 }
 
 // Two launches per round: lz4_pack_blocks_kernel compresses every 64 KB block of the round's LZ4 files (one warp per
@@ -24,18 +33,19 @@ static int pack_device_impl(zpb_ctx *ctx, const u8 *d_in, u64 in_size, u8 *d_out
     if (n > 0x7fffffffull) return fail(ctx, ZPB_E_ARG, "too many files in one batch");
     // block list of the LZ4 files the stage-2 kernel will accept (same checks as there)
     u64 nblk = 0;
+    bool any_zstd = false;
     for (u64 i = 0; i < n; ++i) {
         const zpb_file &f = files[i];
-        if (f.method != ZPB_METHOD_LZ4 || f.level >= 3) continue;
-        if (f.src_off > in_size || f.size > in_size - f.src_off || f.dst_off > out_size || f.dst_cap > out_size - f.dst_off) continue;
-        if (f.dst_cap < 7 + 4 * ((f.size + 65535) >> 16) + f.size + 4) continue;
+        if (!pack_file_has_blocks(f, in_size, out_size)) continue;
         nblk += (f.size + 65535) >> 16;
+        any_zstd |= f.method == ZPB_METHOD_ZSTD;
     }
     if (nblk > 0x7fffffffull) return fail(ctx, ZPB_E_ARG, "too many blocks in one batch");
     const size_t desc_b = n * sizeof(zpb_file), ord_b = (n * sizeof(u32) + 15) & ~(size_t)15;
     const size_t res_b = n * (2 * sizeof(u64) + sizeof(int));
     const size_t blk_b = nblk * sizeof(PackBlock), base_b = ord_b;
-    const u64 cap_blocks = std::max<u64>(ctx->pack_scratch_blocks, 1);
+    // zstd blocks need two more slots each (the block body and 128 KB of sequence records): smaller rounds
+    const u64 cap_blocks = std::max<u64>(any_zstd ? std::min<u64>(ctx->pack_scratch_blocks, 4096) : ctx->pack_scratch_blocks, 1);
     if (!ctx->d_desc.ensure(desc_b) || !ctx->d_order.ensure(ord_b + base_b) || !ctx->d_res.ensure(res_b + 64) ||
         !ctx->d_counter.ensure(256) || !ctx->h_stage.ensure(desc_b + ord_b + base_b + blk_b + res_b + 64) ||
         !ctx->d_pblk.ensure(blk_b + 16) || !ctx->d_csize.ensure(std::min(nblk, cap_blocks) * sizeof(u32) + 16))
@@ -61,16 +71,14 @@ static int pack_device_impl(zpb_ctx *ctx, const u8 *d_in, u64 in_size, u8 *d_out
             const u32 i = h_order[k];
             const zpb_file &f = files[i];
             h_base[i] = 0;
-            if (f.method != ZPB_METHOD_LZ4 || f.level >= 3) continue;
-            if (f.src_off > in_size || f.size > in_size - f.src_off || f.dst_off > out_size || f.dst_cap > out_size - f.dst_off) continue;
+            if (!pack_file_has_blocks(f, in_size, out_size)) continue;
             const u64 fb = (f.size + 65535) >> 16;
-            if (f.dst_cap < 7 + 4 * fb + f.size + 4) continue;
             if (bi - rb0 + fb > cap_blocks && bi > rb0) { rounds.push_back({rf0, k, rb0, bi}); rf0 = k; rb0 = bi; }
             h_base[i] = (u32)(bi - rb0);
             for (u64 b = 0; b < fb; ++b) {
                 h_blk[bi].src_off = f.src_off + (b << 16);
                 h_blk[bi].len = (u32)std::min<u64>(f.size - (b << 16), 65536);
-                h_blk[bi].pad = 0;
+                h_blk[bi].pad = f.method == ZPB_METHOD_ZSTD ? 1u : 0u;
                 ++bi;
             }
         }
@@ -78,8 +86,11 @@ static int pack_device_impl(zpb_ctx *ctx, const u8 *d_in, u64 in_size, u8 *d_out
     }
     u64 max_round = 0;
     for (const Round &r : rounds) max_round = std::max(max_round, r.b1 - r.b0);
-    if (!ctx->d_pscratch.ensure((max_round << 16) + 64) || !ctx->d_csize.ensure(max_round * sizeof(u32) + 16))
+    if (!ctx->d_pscratch.ensure((max_round << 16) + 64) || !ctx->d_csize.ensure(2 * max_round * sizeof(u32) + 16))
         return fail(ctx, ZPB_E_NOMEM, "block scratch allocation failed");
+    if (any_zstd && (!ctx->d_zslot.ensure((max_round << 16) + 64) || !ctx->d_zseq.ensure(max_round * ZE_SEQ_MAX * sizeof(u64) + 64)))
+        return fail(ctx, ZPB_E_NOMEM, "zstd block scratch allocation failed");
+    u32 *d_zbody = (u32 *)ctx->d_csize.p + max_round;
     u64 *d_comp = (u64 *)ctx->d_res.p;
     u64 *d_dig = d_comp + n;
     int *d_st = (int *)(d_dig + n);
@@ -107,12 +118,20 @@ static int pack_device_impl(zpb_ctx *ctx, const u8 *d_in, u64 in_size, u8 *d_out
             CK(ctx, cudaGetLastError());
             ctx->launches += 1;
         }
+        if (rb && any_zstd) {
+            zstd_encode_blocks_kernel<<<(u32)std::min<u64>((rb + 127) / 128, (u64)ctx->sm_count * 8), 128, 0, s>>>(
+                (const u8 *)ctx->d_pscratch.p, (const u32 *)ctx->d_csize.p, (const PackBlock *)ctx->d_pblk.p + r.b0, (u32)rb,
+                (u8 *)ctx->d_zslot.p, (u64 *)ctx->d_zseq.p, d_zbody);
+            CK(ctx, cudaGetLastError());
+            ctx->launches += 1;
+        }
         CK(ctx, cudaEventRecord(ctx->pack_evs[3 * ri + 1], s));
         if (rf) {
             const u32 grid = (u32)std::min<u64>((u64)ctx->sm_count * ctx->pk_per_sm, (rf + PK_WARPS - 1) / PK_WARPS);
             lz4_pack_kernel<<<grid, 32 * PK_WARPS, 0, s>>>(d_in, in_size, d_out, out_size, (const zpb_file *)ctx->d_desc.p,
                                                            d_ord + r.f0, (u32)rf, (u32 *)ctx->d_counter.p, d_comp, d_dig, d_st,
-                                                           d_base, (const u8 *)ctx->d_pscratch.p, (const u32 *)ctx->d_csize.p);
+                                                           d_base, (const u8 *)ctx->d_pscratch.p, (const u32 *)ctx->d_csize.p,
+                                                           (const u8 *)ctx->d_zslot.p, d_zbody);
             CK(ctx, cudaGetLastError());
             ctx->launches += 1;
         }

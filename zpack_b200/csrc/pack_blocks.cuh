@@ -50,7 +50,7 @@
 struct PackBlock {      // host -> device, one per 64 KB block of an LZ4 file
     u64 src_off;        // where the block's bytes are in the input buffer
     u32 len;            // 1 .. 65536
-    u32 pad;
+    u32 pad;            // != 0: the block belongs to a zstd file (zstd_encode.cuh turns its matches into a zstd block)
 };
 
 // Shared memory is addressed by byte offsets from the start of the dynamic window (`sm`): 32-bit address arithmetic,

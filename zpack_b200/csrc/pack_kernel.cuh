@@ -17,6 +17,7 @@
 #include "xxh3.cuh"
 #include "lz4_decode.cuh"
 #include "pack_blocks.cuh"
+#include "zstd_encode.cuh"
 #include "../../include/zpack_b200.h"
 
 #define PK_WARPS 4
@@ -24,7 +25,8 @@
 __global__ void __launch_bounds__(32 * PK_WARPS)
 lz4_pack_kernel(const u8 *__restrict__ in, u64 in_size, u8 *out, u64 out_size, const zpb_file *__restrict__ files,
                 const u32 *__restrict__ order, u32 n, u32 *counter, u64 *comp_size, u64 *digest, int *status,
-                const u32 *__restrict__ blk_base, const u8 *__restrict__ scratch, const u32 *__restrict__ csize) {
+                const u32 *__restrict__ blk_base, const u8 *__restrict__ scratch, const u32 *__restrict__ csize,
+                const u8 *__restrict__ zslot, const u32 *__restrict__ zbody) {
     const int lane = threadIdx.x & 31;
     Group<32> g;
     for (;;) {
@@ -97,15 +99,15 @@ lz4_pack_kernel(const u8 *__restrict__ in, u64 in_size, u8 *out, u64 out_size, c
                 csz = op;
             }
         } else if (f.method == ZPB_METHOD_ZSTD) {
-            // A VALID zstd frame without entropy coding: Raw_Blocks of up to 128 KB (zstd_compression_format.md:320-404;
-            // what ZSTD_compress itself emits for incompressible input, zstd_compress.c ZSTD_noCompressBlock).  It keeps the
-            // writer usable for ZPACK_COMPRESSION_ZSTD (the reference reader and CLI accept the archives) until the dfast +
-            // FSE / Huffman encoder of SURVEY §8(f) row 3 exists; the ratio is 1.0 and is reported as such.
-            const u64 nblocks = f.size ? (f.size + 131071) >> 17 : 1;
+            // A zstd frame of 64 KB blocks (zstd_compression_format.md:320-404): Compressed_Blocks whose bodies
+            // zstd_encode_blocks_kernel built from the block compressor's matches (raw literals + predefined-mode FSE
+            // sequences), Raw_Blocks where that did not shrink the block.
+            const u64 nblocks = f.size ? (f.size + 65535) >> 16 : 1;
             if (f.dst_cap < 14 + 3 * nblocks + f.size) st = ZPB_ST_COMPRESS_FAILED;
             else {
                 const u8 *src = in + f.src_off;
                 u8 *dst = out + f.dst_off;
+                const u32 b0 = blk_base[idx];
                 if (lane == 0) {
                     // magic; FHD: 8-byte frame content size, no single-segment, no checksum, no dictionary; window 128 KB
                     dst[0] = 0x28; dst[1] = 0xB5; dst[2] = 0x2F; dst[3] = 0xFD; dst[4] = 0xC0; dst[5] = 0x38;
@@ -115,12 +117,15 @@ lz4_pack_kernel(const u8 *__restrict__ in, u64 in_size, u8 *out, u64 out_size, c
                 Xxh3Stream<32> hs;
                 hs.init(src, f.size, g);
                 for (u64 b = 0; b < nblocks; ++b) {
-                    const u32 blen = (u32)(f.size - (b << 17) < 131072 ? f.size - (b << 17) : 131072);
-                    const u32 hdr = (b + 1 == nblocks ? 1u : 0u) | (blen << 3);      // last | Raw_Block | size
+                    const u32 blen = (u32)(f.size - (b << 16) < 65536 ? f.size - (b << 16) : 65536);
+                    const u32 z = f.size ? zbody[b0 + b] : 0u;
+                    const u32 last = b + 1 == nblocks ? 1u : 0u;
+                    const u32 hdr = z ? (last | (2u << 1) | (z << 3)) : (last | (blen << 3));      // Compressed_Block / Raw_Block
                     if (lane == 0) { dst[op] = (u8)hdr; dst[op + 1] = (u8)(hdr >> 8); dst[op + 2] = (u8)(hdr >> 16); }
-                    group_copy<32>(g, dst + op + 3, src + (b << 17), blen);
-                    op += 3 + blen;
-                    hs.advance((b << 17) + blen, g);
+                    if (z) group_copy<32>(g, dst + op + 3, zslot + ((u64)(b0 + b) << 16), z);
+                    else group_copy<32>(g, dst + op + 3, src + (b << 16), blen);
+                    op += 3 + (z ? z : blen);
+                    hs.advance((b << 16) + blen, g);
                 }
                 dg = hs.finish(g);
                 csz = op;
