@@ -32,12 +32,12 @@ def sim():
     _build()
     lib = C.CDLL(LIB)
     vp = C.c_void_p
-    lib.sim_lz4_pack_blocks.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_int, C.c_uint64]
+    lib.sim_lz4_pack_blocks.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_int, C.c_uint64, vp]
     return lib
 
 
-def pack_blocks(sim, bufs, seed=1, grid=2, misalign=0):
-    """bufs: list of byte arrays (each <= 64 KB) -> list of (csize, payload)"""
+def pack_blocks(sim, bufs, seed=1, grid=2, misalign=0, want_winop=False):
+    """bufs: list of byte arrays (each <= 64 KB) -> list of (csize, payload[, window offsets])"""
     offs, total = [], misalign
     for b in bufs:
         offs.append(total)
@@ -50,9 +50,12 @@ def pack_blocks(sim, bufs, seed=1, grid=2, misalign=0):
     ln = np.array([len(b) for b in bufs], np.uint32)
     scratch = np.full(n * 65536 + 64, 0xEE, np.uint8)
     csize = np.full(n, 0xFFFFFFFF, np.uint32)
-    sim.sim_lz4_pack_blocks(inp.ctypes.data, so.ctypes.data, ln.ctypes.data, n, scratch.ctypes.data, csize.ctypes.data, grid, seed)
+    winop = np.zeros(n * 17, np.uint32)
+    sim.sim_lz4_pack_blocks(inp.ctypes.data, so.ctypes.data, ln.ctypes.data, n, scratch.ctypes.data, csize.ctypes.data, grid, seed,
+                            winop.ctypes.data if want_winop else None)
     assert (scratch[n * 65536:] == 0xEE).all()
-    return [(int(csize[i]), scratch[i * 65536:i * 65536 + int(csize[i])].copy()) for i in range(n)]
+    res = [(int(csize[i]), scratch[i * 65536:i * 65536 + int(csize[i])].copy()) for i in range(n)]
+    return [r + (winop[17 * i:17 * i + 17].copy(),) for i, r in enumerate(res)] if want_winop else res
 
 
 def decode_block(oracle, payload, n):
@@ -108,44 +111,61 @@ def test_crafted_inputs(sim, oracle):
 
 
 def zstd_frame(bodies, blocks):
-    """A zstd frame around per-block bodies (None = Raw_Block), laid out as pack_kernel.cuh does: magic, FHD 0xC0
-    (8-byte content size), window descriptor 0x38 (128 KB), 3-byte block headers."""
+    """A zstd frame laid out as pack_kernel.cuh does: magic, FHD 0xC0 (8-byte content size), window descriptor 0x38
+    (128 KB), 3-byte block headers.  bodies[k]: the list of Compressed_Block bodies of block k, or None = Raw_Block."""
     total = sum(len(b) for b in blocks)
     fr = bytearray([0x28, 0xB5, 0x2F, 0xFD, 0xC0, 0x38]) + total.to_bytes(8, "little")
-    for k, (body, raw) in enumerate(zip(bodies, blocks)):
-        last = 1 if k + 1 == len(blocks) else 0
-        if body is None:
-            fr += (last | (len(raw) << 3)).to_bytes(3, "little") + bytes(raw)
+    for k, (subs, raw) in enumerate(zip(bodies, blocks)):
+        last_block = k + 1 == len(blocks)
+        if subs is None:
+            fr += ((1 if last_block else 0) | (len(raw) << 3)).to_bytes(3, "little") + bytes(raw)
         else:
-            fr += (last | (2 << 1) | (len(body) << 3)).to_bytes(3, "little") + bytes(body)
+            for j, body in enumerate(subs):
+                last = 1 if last_block and j + 1 == len(subs) else 0
+                fr += (last | (2 << 1) | (len(body) << 3)).to_bytes(3, "little") + bytes(body)
     return np.frombuffer(bytes(fr), np.uint8)
 
 
 def test_zstd_blocks_from_the_lz4_matches_decode_with_the_oracle_and_the_reference(sim, oracle):
-    """zstd_encode.cuh: the block compressor's LZ4 payload -> a zstd Compressed_Block (raw literals + predefined-mode FSE
-    sequences).  Frames must decode in the oracle's zstd port and in the UNMODIFIED reference's ZSTD_decompress."""
-    sim.sim_zstd_encode_block.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
-    sim.sim_zstd_encode_block.restype = C.c_uint32
+    """zstd_encode.cuh: every 4 KB window of the block compressor's LZ4 payload -> one zstd Compressed_Block (raw literals
+    + predefined-mode FSE sequences).  Frames must decode in the oracle's zstd port and in the UNMODIFIED reference's
+    ZSTD_decompress."""
+    sim.sim_zstd_encode_range.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
+    sim.sim_zstd_encode_range.restype = C.c_uint32
     rng = np.random.default_rng(5)
     blocks = [corpus.entry_bytes(i, 65536) for i in range(8)]
     blocks += [corpus.entry_bytes(20 + i, s) for i, s in enumerate((70, 300, 4097, 40000))]
+    far = rng.integers(0, 256, 65536, dtype=np.uint8)            # short matches at far offsets: zstd bodies larger than the LZ4 bytes
+    for k in range(300):
+        p, q = int(rng.integers(40000, 65000)), int(rng.integers(0, 20000))
+        far[p:p + 6] = far[q:q + 6]
     blocks += [np.zeros(65536, np.uint8), np.frombuffer((b"abcdefgh" * 9000)[:65536], np.uint8),
-               rng.integers(0, 4, 65536, dtype=np.uint8), rng.integers(0, 256, 5000, dtype=np.uint8)]
-    packed = pack_blocks(sim, blocks)
+               rng.integers(0, 4, 65536, dtype=np.uint8), rng.integers(0, 256, 5000, dtype=np.uint8), far]
+    packed = pack_blocks(sim, blocks, want_winop=True)
     bodies, lz_total, z_total = [], 0, 0
-    for b, (c, payload) in zip(blocks, packed):
-        body = None
+    for b, (c, payload, winop) in zip(blocks, packed):
+        subs = None
         if c:
-            out = np.zeros(65536 + 64, np.uint8)
-            n = sim.sim_zstd_encode_block(payload.ctypes.data, c, len(b), out.ctypes.data)
-            assert n < len(b)
-            assert (out[65536:] == 0).all()
-            if n:
-                body = out[:n].copy()
-        bodies.append(body)
+            nwin = (len(b) - 12) // 4096 + 1
+            subs, failed = [], False
+            for w in range(nwin):
+                begin, end = int(winop[w]), int(winop[w + 1])
+                tail_end = c if w + 1 == nwin else end
+                cap = (tail_end - begin) + ((tail_end - begin) >> 2) + 20
+                out = np.zeros(cap + 64, np.uint8)
+                n = sim.sim_zstd_encode_range(payload.ctypes.data, begin, end, tail_end, out.ctypes.data, cap)
+                assert (out[cap:] == 0).all()
+                if n == 0xFFFFFFFF:
+                    failed = True
+                    break
+                if n:
+                    subs.append(out[:n].copy())
+            if failed or sum(len(x) + 3 for x in subs) >= len(b):
+                subs = None
+        bodies.append(subs)
         lz_total += c if c else len(b)
-        z_total += len(body) if body is not None else len(b)
-    assert sum(x is not None for x in bodies) >= len(blocks) - 4          # the random blocks stay raw
+        z_total += sum(len(x) + 3 for x in subs) if subs is not None else len(b)
+    assert sum(x is not None for x in bodies) >= len(blocks) - 5          # the random blocks stay raw
     for k in range(len(blocks)):                       # one frame per block, and all of them in one frame
         fr = zstd_frame([bodies[k]], [blocks[k]])
         rc, got = oracle.zstd_decode_port(fr, len(blocks[k]))

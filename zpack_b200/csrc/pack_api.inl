@@ -86,11 +86,13 @@ static int pack_device_impl(zpb_ctx *ctx, const u8 *d_in, u64 in_size, u8 *d_out
     }
     u64 max_round = 0;
     for (const Round &r : rounds) max_round = std::max(max_round, r.b1 - r.b0);
-    if (!ctx->d_pscratch.ensure((max_round << 16) + 64) || !ctx->d_csize.ensure(2 * max_round * sizeof(u32) + 16))
+    if (!ctx->d_pscratch.ensure((max_round << 16) + 64) || !ctx->d_csize.ensure(max_round * sizeof(u32) + 16))
         return fail(ctx, ZPB_E_NOMEM, "block scratch allocation failed");
-    if (any_zstd && (!ctx->d_zslot.ensure((max_round << 16) + 64) || !ctx->d_zseq.ensure(max_round * ZE_SEQ_MAX * sizeof(u64) + 64)))
+    if (any_zstd && (!ctx->d_zslot.ensure(max_round * (u64)ZE_SLOT + 64) || !ctx->d_zseq.ensure(max_round * 16 * (u64)ZE_WIN_SEQ * sizeof(u64) + 64) ||
+                     !ctx->d_zmeta.ensure(max_round * (17 + ZE_ZBODY) * sizeof(u32) + 64)))
         return fail(ctx, ZPB_E_NOMEM, "zstd block scratch allocation failed");
-    u32 *d_zbody = (u32 *)ctx->d_csize.p + max_round;
+    u32 *d_winop = any_zstd ? (u32 *)ctx->d_zmeta.p : nullptr;
+    u32 *d_zbody = any_zstd ? d_winop + max_round * 17 : nullptr;
     u64 *d_comp = (u64 *)ctx->d_res.p;
     u64 *d_dig = d_comp + n;
     int *d_st = (int *)(d_dig + n);
@@ -114,13 +116,13 @@ static int pack_device_impl(zpb_ctx *ctx, const u8 *d_in, u64 in_size, u8 *d_out
             const u32 grid = (u32)std::min<u64>((u64)ctx->sm_count * ctx->p2_per_sm, (rb + P2_WARPS - 1) / P2_WARPS);
             lz4_pack_blocks_kernel<<<grid, 32 * P2_WARPS, P2_SMEM, s>>>(d_in, (const PackBlock *)ctx->d_pblk.p + r.b0, (u32)rb,
                                                                         (u32 *)ctx->d_counter.p + 32, (u8 *)ctx->d_pscratch.p,
-                                                                        (u32 *)ctx->d_csize.p);
+                                                                        (u32 *)ctx->d_csize.p, d_winop);
             CK(ctx, cudaGetLastError());
             ctx->launches += 1;
         }
         if (rb && any_zstd) {
-            zstd_encode_blocks_kernel<<<(u32)std::min<u64>((rb + 127) / 128, (u64)ctx->sm_count * 8), 128, 0, s>>>(
-                (const u8 *)ctx->d_pscratch.p, (const u32 *)ctx->d_csize.p, (const PackBlock *)ctx->d_pblk.p + r.b0, (u32)rb,
+            zstd_encode_blocks_kernel<<<(u32)std::min<u64>((rb * 16 + 127) / 128, (u64)ctx->sm_count * 16), 128, 0, s>>>(
+                (const u8 *)ctx->d_pscratch.p, (const u32 *)ctx->d_csize.p, (const PackBlock *)ctx->d_pblk.p + r.b0, d_winop, (u32)rb,
                 (u8 *)ctx->d_zslot.p, (u64 *)ctx->d_zseq.p, d_zbody);
             CK(ctx, cudaGetLastError());
             ctx->launches += 1;
@@ -131,7 +133,7 @@ static int pack_device_impl(zpb_ctx *ctx, const u8 *d_in, u64 in_size, u8 *d_out
             lz4_pack_kernel<<<grid, 32 * PK_WARPS, 0, s>>>(d_in, in_size, d_out, out_size, (const zpb_file *)ctx->d_desc.p,
                                                            d_ord + r.f0, (u32)rf, (u32 *)ctx->d_counter.p, d_comp, d_dig, d_st,
                                                            d_base, (const u8 *)ctx->d_pscratch.p, (const u32 *)ctx->d_csize.p,
-                                                           (const u8 *)ctx->d_zslot.p, d_zbody);
+                                                           (const u8 *)ctx->d_zslot.p, d_zbody, d_winop);
             CK(ctx, cudaGetLastError());
             ctx->launches += 1;
         }

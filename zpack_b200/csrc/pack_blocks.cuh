@@ -150,8 +150,12 @@ ZPB_DEVINL u32 p2_join(u8 *dst, u32 op, u32 anchor, const u8 *sm, u32 D, u32 dso
 }
 
 // Compressed size of every block -> csize[b] (0: store it), payload -> scratch + b * 65536 (at most len - 1 bytes).
+// winop (optional, P2_WINOPS entries per block): the payload offset at which each window's sequences start, and behind the
+// last window the offset of the closing literals-only sequence — the zstd encoder reads the payload window by window.
+#define P2_WINOPS 17u
 ZPB_DEVINL void
-lz4_pack_blocks_body(const u8 *__restrict__ in, const PackBlock *__restrict__ blocks, u32 nblocks, u32 *counter, u8 *scratch, u32 *csize) {
+lz4_pack_blocks_body(const u8 *__restrict__ in, const PackBlock *__restrict__ blocks, u32 nblocks, u32 *counter, u8 *scratch, u32 *csize,
+                     u32 *winop) {
     ZPB_DYN_SMEM(p2_smem);
     u8 *sm = reinterpret_cast<u8 *>(p2_smem);
     volatile u32 *ctl = reinterpret_cast<volatile u32 *>(sm);     // [0,1] mbarrier  [2] probe token  [3] join token  [4] block  [5] given up  [8..15] join state
@@ -329,6 +333,7 @@ lz4_pack_blocks_body(const u8 *__restrict__ in, const PackBlock *__restrict__ bl
             if (lane == 0) {
                 if (!fits) { ctl[5] = 1; ctl[15] = 0; }
                 ctl[8] = op + bytes; ctl[9] = a_out;
+                if (winop) winop[(u64)b * P2_WINOPS + w] = op;
                 __threadfence_block();
                 ctl[3] = w + 1u;
             }
@@ -341,6 +346,7 @@ lz4_pack_blocks_body(const u8 *__restrict__ in, const PackBlock *__restrict__ bl
             u32 op = ctl[8];
             const u32 anchor = ctl[9];
             bool fits = ctl[15] != 0 && ctl[5] == 0;
+            if (winop && lane == 0) winop[(u64)b * P2_WINOPS + nwin] = op;
             if (fits) {
                 const u32 lit = n - anchor;
                 if (op + p2_seq_bytes(lit, 0) > cap) fits = false;
@@ -353,6 +359,7 @@ lz4_pack_blocks_body(const u8 *__restrict__ in, const PackBlock *__restrict__ bl
 }
 
 __global__ void __launch_bounds__(32 * P2_WARPS)
-lz4_pack_blocks_kernel(const u8 *__restrict__ in, const PackBlock *__restrict__ blocks, u32 nblocks, u32 *counter, u8 *scratch, u32 *csize) {
-    lz4_pack_blocks_body(in, blocks, nblocks, counter, scratch, csize);
+lz4_pack_blocks_kernel(const u8 *__restrict__ in, const PackBlock *__restrict__ blocks, u32 nblocks, u32 *counter, u8 *scratch, u32 *csize,
+                       u32 *winop) {
+    lz4_pack_blocks_body(in, blocks, nblocks, counter, scratch, csize, winop);
 }

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(32 * PK_WARPS)
 lz4_pack_kernel(const u8 *__restrict__ in, u64 in_size, u8 *out, u64 out_size, const zpb_file *__restrict__ files,
                 const u32 *__restrict__ order, u32 n, u32 *counter, u64 *comp_size, u64 *digest, int *status,
                 const u32 *__restrict__ blk_base, const u8 *__restrict__ scratch, const u32 *__restrict__ csize,
-                const u8 *__restrict__ zslot, const u32 *__restrict__ zbody) {
+                const u8 *__restrict__ zslot, const u32 *__restrict__ zbody, const u32 *__restrict__ winop) {
     const int lane = threadIdx.x & 31;
     Group<32> g;
     for (;;) {
@@ -118,13 +118,32 @@ lz4_pack_kernel(const u8 *__restrict__ in, u64 in_size, u8 *out, u64 out_size, c
                 hs.init(src, f.size, g);
                 for (u64 b = 0; b < nblocks; ++b) {
                     const u32 blen = (u32)(f.size - (b << 16) < 65536 ? f.size - (b << 16) : 65536);
-                    const u32 z = f.size ? zbody[b0 + b] : 0u;
-                    const u32 last = b + 1 == nblocks ? 1u : 0u;
-                    const u32 hdr = z ? (last | (2u << 1) | (z << 3)) : (last | (blen << 3));      // Compressed_Block / Raw_Block
-                    if (lane == 0) { dst[op] = (u8)hdr; dst[op + 1] = (u8)(hdr >> 8); dst[op + 2] = (u8)(hdr >> 16); }
-                    if (z) group_copy<32>(g, dst + op + 3, zslot + ((u64)(b0 + b) << 16), z);
-                    else group_copy<32>(g, dst + op + 3, src + (b << 16), blen);
-                    op += 3 + (z ? z : blen);
+                    const u64 bb = b0 + b;
+                    const bool last_block = b + 1 == nblocks;
+                    // the block's windows: lanes 0-15 look at one body size each; any failure, or bodies that are not
+                    // smaller than the block, and it is stored raw
+                    u32 zw = f.size && lane < 16 ? zbody[bb * ZE_ZBODY + lane] : 0u;
+                    const bool zfail = !f.size || __any_sync(0xffffffffu, zw == ZE_FAIL);
+                    u32 ztotal = zw && zw != ZE_FAIL ? zw + 3u : 0u;
+                    for (int d = 16; d; d >>= 1) ztotal += __shfl_xor_sync(0xffffffffu, ztotal, d);
+                    if (!zfail && ztotal && ztotal < blen) {
+                        // one Compressed_Block per window of the block compressor that emitted something; the last
+                        // window always does (it carries the block's closing literals)
+                        const u32 nwin = (blen - 12u) / 4096u + 1u;
+                        for (u32 w = 0; w < nwin; ++w) {
+                            const u32 z = __shfl_sync(0xffffffffu, zw, (int)w);
+                            if (!z) continue;
+                            const u32 hdr = ((last_block && w + 1 == nwin) ? 1u : 0u) | (2u << 1) | (z << 3);
+                            if (lane == 0) { dst[op] = (u8)hdr; dst[op + 1] = (u8)(hdr >> 8); dst[op + 2] = (u8)(hdr >> 16); }
+                            group_copy<32>(g, dst + op + 3, zslot + bb * ZE_SLOT + ZE_OFF(winop[bb * 17u + w], w), z);
+                            op += 3 + z;
+                        }
+                    } else {
+                        const u32 hdr = (last_block ? 1u : 0u) | (blen << 3);                      // Raw_Block
+                        if (lane == 0) { dst[op] = (u8)hdr; dst[op + 1] = (u8)(hdr >> 8); dst[op + 2] = (u8)(hdr >> 16); }
+                        group_copy<32>(g, dst + op + 3, src + (b << 16), blen);
+                        op += 3 + blen;
+                    }
                     hs.advance((b << 16) + blen, g);
                 }
                 dg = hs.finish(g);

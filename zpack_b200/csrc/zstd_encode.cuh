@@ -43,7 +43,11 @@ struct ZeTables {
     int dfs_ll[36], dfs_of[29], dfs_ml[53];
 };
 
+#ifdef ZPB_SIM
 ZPB_DEVINL int ze_highbit(u32 v) { int r = 0; while (v >>= 1) ++r; return r; }
+#else
+ZPB_DEVINL int ze_highbit(u32 v) { return 31 - __clz((int)v); }
+#endif
 
 ZPB_DEVINL void ze_build(u16 *st, u32 *dnb, int *dfs, const short *norm, int nsym, int log) {
     const int size = 1 << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
@@ -122,47 +126,59 @@ ZPB_DEVINL u32 ze_encode(ZeBits &b, const u16 *st, const u32 *dnb, const int *df
     return st[(int)(state >> nbo) + dfs[sym]];
 }
 
-// One block: the LZ4 payload `lz` (csize bytes, a complete LZ4 block) -> a zstd Compressed_Block body at `out`.
-// `seq` is scratch for ZE_SEQ_MAX records.  Returns the body size, or 0 when it would not be smaller than `raw_len`
-// (or the payload is not what pack_blocks.cuh writes): the caller stores the block as a Raw_Block.
-ZPB_DEVINL u32 ze_encode_block(const u8 *lz, u32 csize, u32 raw_len, u8 *out, u64 *seq, const ZeTables &T) {
-    const u32 cap = raw_len < 65536u ? raw_len : 65536u;
-    if (csize == 0 || cap < 16) return 0;
+#define ZE_FAIL 0xFFFFFFFFu
+#define ZE_WIN_SEQ 1040u       // records per window: at most 1024 matches start inside 4096 positions
+// a block's bodies: window w's at 1.25 x the payload offset of its first sequence + 24 * w (a zstd body can be somewhat
+// larger than the LZ4 bytes it restates: 16-bit offsets cost 2 bytes there, code + extra bits here)
+#define ZE_SLOT (65536u + 16384u + 512u)
+#define ZE_OFF(begin, w) ((begin) + ((begin) >> 2) + 24u * (w))
+#define ZE_ZBODY 16u           // per block: the body size of every window's sub-block (0: nothing to emit, ZE_FAIL: store the block raw)
+
+// One sub-block: the LZ4 sequences in lz[begin, end) — whole sequences, each with a match — and, for the last
+// sub-block of a block, the closing literals-only sequence lz[end, tail_end) -> a zstd Compressed_Block body at `out`.
+// `seq`: scratch for `seq_cap` records.  Returns the body size; 0 when the range is empty; ZE_FAIL when the body does
+// not fit `cap` or the payload is not what pack_blocks.cuh writes (the caller then stores the whole block raw).
+ZPB_DEVINL u32 ze_encode_range(const u8 *lz, u32 begin, u32 end, u32 tail_end, u8 *out, u32 cap, u64 *seq, u32 seq_cap,
+                               const ZeTables &T) {
+    if (begin == end && tail_end == end) return 0;
+    if (cap < 16) return ZE_FAIL;
     // ---- forward: literals to the literals section (3-byte Raw_Literals_Block header, filled in below), sequences to `seq`
-    u32 ip = 0, lit = 0, nseq = 0;
+    u32 ip = begin, lit = 0, nseq = 0;
     u8 *lit_out = out + 3;
-    for (;;) {
-        if (ip >= csize) return 0;
+    while (ip < tail_end) {
         const u32 token = lz[ip++];
         u32 ll = token >> 4;
         if (ll == 15) {
             u32 x;
-            do { if (ip >= csize) return 0; x = lz[ip++]; ll += x; } while (x == 255);
+            do { if (ip >= tail_end) return ZE_FAIL; x = lz[ip++]; ll += x; } while (x == 255);
         }
-        if (ip + ll > csize || 3 + lit + ll >= cap) return 0;
+        if (ip + ll > tail_end || 3 + lit + ll + 8 >= cap) return ZE_FAIL;
         for (u32 i = 0; i < ll; ++i) lit_out[lit + i] = lz[ip + i];
         lit += ll;
         ip += ll;
-        if (ip == csize) break;                       // the last sequence of an LZ4 block has literals only
-        if (ip + 2 > csize) return 0;
+        if (ip > end) {                               // the closing sequence of the block: literals only
+            if (ip != tail_end) return ZE_FAIL;
+            break;
+        }
+        if (ip + 2 > end) return ZE_FAIL;
         const u32 off = (u32)lz[ip] | ((u32)lz[ip + 1] << 8);
         ip += 2;
         u32 ml = token & 15u;
         if (ml == 15) {
             u32 x;
-            do { if (ip >= csize) return 0; x = lz[ip++]; ml += x; } while (x == 255);
+            do { if (ip >= end) return ZE_FAIL; x = lz[ip++]; ml += x; } while (x == 255);
         }
         ml += 4;
-        if (off == 0 || nseq >= ZE_SEQ_MAX || ll > 65535u || ml > 65535u) return 0;
+        if (off == 0 || nseq >= seq_cap || ll > 65535u || ml > 65535u) return ZE_FAIL;
         seq[nseq++] = (u64)ll | ((u64)ml << 16) | ((u64)off << 32);
+        if (ip == end && tail_end == end) break;
     }
     out[0] = (u8)(0x0Cu | ((lit & 0xFu) << 4));       // Raw_Literals_Block, size format 11: 20-bit size
     out[1] = (u8)(lit >> 4);
     out[2] = (u8)(lit >> 12);
     u32 op = 3 + lit;
-    if (op + 4 >= cap) return 0;
     // ---- sequences section header: count, then symbol compression modes = 0 (all predefined)
-    if (nseq == 0) { out[op++] = 0; return op < cap ? op : 0; }
+    if (nseq == 0) { out[op++] = 0; return op <= cap ? op : ZE_FAIL; }
     if (nseq < 128) out[op++] = (u8)nseq;
     else if (nseq < 0x7F00) { out[op++] = (u8)((nseq >> 8) + 0x80); out[op++] = (u8)nseq; }
     else { out[op++] = 0xFF; out[op++] = (u8)(nseq - 0x7F00); out[op++] = (u8)((nseq - 0x7F00) >> 8); }
@@ -204,25 +220,39 @@ ZPB_DEVINL u32 ze_encode_block(const u8 *lz, u32 csize, u32 raw_len, u8 *out, u6
     ze_add(b, 1u, 1);                                // BIT_closeCStream: the end mark
     ze_flush(b);
     if (b.n) { if (b.p < b.end) *b.p++ = (u8)b.acc; else b.ovf = true; }
-    if (b.ovf) return 0;
-    op = (u32)(b.p - out);
-    return op < cap ? op : 0;
+    if (b.ovf) return ZE_FAIL;
+    return (u32)(b.p - out);
 }
 
 #ifndef ZPB_SIM
-// zbody[b] = size of block b's Compressed_Block body at zslot + b * 65536 (0: store the block raw).  Only the blocks the
-// host marked (PackBlock::pad != 0: they belong to a ZPACK_COMPRESSION_ZSTD file) are encoded.
+// One THREAD per 4 KB window of the block compressor: the window's sequences become one zstd sub-block (the windows'
+// payload offsets come from lz4_pack_blocks_kernel: winop).  Each walk is serial and latency-bound, so the kernel relies
+// on the number of windows in flight (16 per block, every block of the round at once), not on staging.
+// zbody[b * 16 + w] = body size of window w (0: none, ZE_FAIL: the block is stored raw).  Only the blocks the host marked
+// (PackBlock::pad != 0: they belong to a ZPACK_COMPRESSION_ZSTD file) are encoded.
 __global__ void __launch_bounds__(128)
 zstd_encode_blocks_kernel(const u8 *__restrict__ lz_slots, const u32 *__restrict__ csize, const PackBlock *__restrict__ blocks,
-                          u32 nblocks, u8 *zslot, u64 *zseq, u32 *zbody) {
+                          const u32 *__restrict__ winop, u32 nblocks, u8 *zslot, u64 *zseq, u32 *zbody) {
     __shared__ ZeTables T;
     if (threadIdx.x == 0) ze_build_tables(T);
     __syncthreads();
-    for (u32 b = blockIdx.x * blockDim.x + threadIdx.x; b < nblocks; b += gridDim.x * blockDim.x) {
+    const u64 nwork = (u64)nblocks * 16u;
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < nwork; t += (u64)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(t >> 4), w = (u32)(t & 15u);
+        const u32 cs = csize[b], len = blocks[b].len;
         u32 z = 0;
-        if (blocks[b].pad) z = ze_encode_block(lz_slots + ((u64)b << 16), csize[b], blocks[b].len, zslot + ((u64)b << 16),
-                                               zseq + (u64)b * ZE_SEQ_MAX, T);
-        zbody[b] = z;
+        if (blocks[b].pad && cs) {
+            const u32 nwin = (len - 12u) / 4096u + 1u;           // as in pack_blocks.cuh (cs != 0 implies len >= 13)
+            if (w < nwin) {
+                const u32 begin = winop[(u64)b * 17u + w], end = winop[(u64)b * 17u + w + 1u];
+                const u32 tail_end = w + 1u == nwin ? cs : end;
+                z = begin <= end && tail_end <= cs && end <= tail_end
+                        ? ze_encode_range(lz_slots + ((u64)b << 16), begin, end, tail_end, zslot + (u64)b * ZE_SLOT + ZE_OFF(begin, w),
+                                          (tail_end - begin) + ((tail_end - begin) >> 2) + 20u, zseq + t * ZE_WIN_SEQ, ZE_WIN_SEQ, T)
+                        : ZE_FAIL;
+            }
+        } else if (w == 0) z = ZE_FAIL;
+        zbody[t] = z;
     }
 }
 #endif
