@@ -108,12 +108,49 @@ struct ZeBits {                 // forward little-endian bit writer (bitstream.h
     bool ovf;
 };
 ZPB_DEVINL void ze_add(ZeBits &b, u32 v, u32 nb) { b.acc |= (u64)v << b.n; b.n += nb; }
-ZPB_DEVINL void ze_flush(ZeBits &b) {
+// The writer only ever stores aligned 32-bit words (one predicated store per flush: lanes of a warp stay converged).
+// A stream that starts at an unaligned byte starts at the word below it, the bytes in front taken as `fill` (what is
+// already there, or zeros where nothing is yet).
+ZPB_DEVINL void ze_open(ZeBits &b, u8 *at, u8 *end, bool keep) {
+    const u32 k = (u32)(uintptr_t)at & 3u;
+    b.p = at - k;
+    b.end = end;
+    b.ovf = false;
+    b.n = 8u * k;
+    b.acc = keep && k ? (u64)(*reinterpret_cast<const u32 *>(b.p) & ((1u << (8u * k)) - 1u)) : 0ull;
+}
+ZPB_DEVINL void ze_flush(ZeBits &b) {                 // leaves at most 31 bits pending
+    if (b.n >= 32) {
+        if (b.p + 4 <= b.end) { *reinterpret_cast<u32 *>(b.p) = (u32)b.acc; b.p += 4; } else b.ovf = true;
+        b.acc >>= 32;
+        b.n -= 32;
+    }
+}
+ZPB_DEVINL void ze_flush_all(ZeBits &b) {             // every whole byte, then the partial one
     while (b.n >= 8) {
         if (b.p < b.end) *b.p++ = (u8)b.acc; else b.ovf = true;
         b.acc >>= 8;
         b.n -= 8;
     }
+    if (b.n) { if (b.p < b.end) *b.p++ = (u8)b.acc; else b.ovf = true; b.n = 0; }
+}
+// sequential reader of the LZ4 payload: eight aligned bytes per load
+struct ZeIn {
+    const u8 *base;
+    u64 w;
+    u32 pos;            // next byte to hand out
+};
+ZPB_DEVINL void ze_in_seek(ZeIn &r, u32 pos) {
+    r.pos = pos;
+    const u8 *a = r.base + pos;
+    r.w = *reinterpret_cast<const u64 *>((uintptr_t)a & ~(uintptr_t)7) >> (8u * ((u32)(uintptr_t)a & 7u));
+}
+ZPB_DEVINL u32 ze_in_byte(ZeIn &r) {
+    const u32 v = (u32)r.w & 0xFFu;
+    ++r.pos;
+    if ((((uintptr_t)r.base + r.pos) & 7u) == 0) r.w = *reinterpret_cast<const u64 *>(r.base + r.pos);
+    else r.w >>= 8;
+    return v;
 }
 ZPB_DEVINL u32 ze_init_state(const u16 *st, const u32 *dnb, const int *dfs, u32 sym) {      // FSE_initCState2
     const u32 nbo = (dnb[sym] + (1u << 15)) >> 16;
@@ -142,37 +179,45 @@ ZPB_DEVINL u32 ze_encode_range(const u8 *lz, u32 begin, u32 end, u32 tail_end, u
                                const ZeTables &T) {
     if (begin == end && tail_end == end) return 0;
     if (cap < 16) return ZE_FAIL;
-    // ---- forward: literals to the literals section (3-byte Raw_Literals_Block header, filled in below), sequences to `seq`
-    u32 ip = begin, lit = 0, nseq = 0;
-    u8 *lit_out = out + 3;
-    while (ip < tail_end) {
-        const u32 token = lz[ip++];
+    // ---- forward: literals to the literals section (3-byte Raw_Literals_Block header, filled in below), sequences to
+    // `seq`.  The payload is read eight bytes at a time; literal bytes are gathered in a bit writer and leave as words.
+    u32 lit = 0, nseq = 0;
+    ZeIn in;
+    in.base = lz;
+    ze_in_seek(in, begin);
+    ZeBits lw;
+    ze_open(lw, out + 3, out + cap, false);          // the bytes in front: the header (written below), up to 3 bytes of slack of the window before
+    bool bad = false;                                 // single-exit loops: the lanes of a warp (one window each) reconverge every iteration
+    while (in.pos < tail_end && !bad) {
+        const u32 token = ze_in_byte(in);
         u32 ll = token >> 4;
         if (ll == 15) {
             u32 x;
-            do { if (ip >= tail_end) return ZE_FAIL; x = lz[ip++]; ll += x; } while (x == 255);
+            do { x = in.pos < tail_end ? ze_in_byte(in) : 0u; ll += x; } while (x == 255);
         }
-        if (ip + ll > tail_end || 3 + lit + ll + 8 >= cap) return ZE_FAIL;
-        for (u32 i = 0; i < ll; ++i) lit_out[lit + i] = lz[ip + i];
+        if (in.pos + ll > tail_end || 3 + lit + ll + 8 >= cap) { bad = true; ll = 0; }
+        for (u32 i = 0; i < ll; ++i) { ze_add(lw, ze_in_byte(in), 8); ze_flush(lw); }
         lit += ll;
-        ip += ll;
-        if (ip > end) {                               // the closing sequence of the block: literals only
-            if (ip != tail_end) return ZE_FAIL;
-            break;
+        if (in.pos > end) {                           // the closing sequence of the block: literals only
+            bad |= in.pos != tail_end;
+        } else if (in.pos + 2 > end) {
+            bad = true;
+        } else {
+            u32 off = ze_in_byte(in);
+            off |= ze_in_byte(in) << 8;
+            u32 ml = token & 15u;
+            if (ml == 15) {
+                u32 x;
+                do { x = in.pos < end ? ze_in_byte(in) : 0u; ml += x; } while (x == 255);
+            }
+            ml += 4;
+            if (off == 0 || nseq >= seq_cap || ll > 65535u || ml > 65535u) bad = true;
+            else seq[nseq++] = (u64)ll | ((u64)ml << 16) | ((u64)off << 32);
         }
-        if (ip + 2 > end) return ZE_FAIL;
-        const u32 off = (u32)lz[ip] | ((u32)lz[ip + 1] << 8);
-        ip += 2;
-        u32 ml = token & 15u;
-        if (ml == 15) {
-            u32 x;
-            do { if (ip >= end) return ZE_FAIL; x = lz[ip++]; ml += x; } while (x == 255);
-        }
-        ml += 4;
-        if (off == 0 || nseq >= seq_cap || ll > 65535u || ml > 65535u) return ZE_FAIL;
-        seq[nseq++] = (u64)ll | ((u64)ml << 16) | ((u64)off << 32);
-        if (ip == end && tail_end == end) break;
     }
+    if (bad) return ZE_FAIL;
+    ze_flush_all(lw);
+    if (lw.ovf) return ZE_FAIL;
     out[0] = (u8)(0x0Cu | ((lit & 0xFu) << 4));       // Raw_Literals_Block, size format 11: 20-bit size
     out[1] = (u8)(lit >> 4);
     out[2] = (u8)(lit >> 12);
@@ -185,7 +230,7 @@ ZPB_DEVINL u32 ze_encode_range(const u8 *lz, u32 begin, u32 end, u32 tail_end, u
     out[op++] = 0;
     // ---- the bitstream, from the last sequence to the first (zstd_compress_sequences.c:ZSTD_encodeSequences_body)
     ZeBits b;
-    b.acc = 0; b.n = 0; b.p = out + op; b.end = out + cap; b.ovf = false;
+    ze_open(b, out + op, out + cap, true);
     u32 st_ll, st_of, st_ml;
     {
         const u64 r = seq[nseq - 1];
@@ -200,8 +245,10 @@ ZPB_DEVINL u32 ze_encode_range(const u8 *lz, u32 begin, u32 end, u32 tail_end, u
         ze_add(b, ob - (1u << co), co);
         ze_flush(b);
     }
+    u64 r_next = nseq > 1 ? seq[nseq - 2] : 0ull;
     for (u32 k = nseq - 1; k-- > 0;) {
-        const u64 r = seq[k];
+        const u64 r = r_next;
+        if (k) r_next = seq[k - 1];                  // the record after this one is on its way while this one is encoded
         const u32 ll = (u32)(r & 0xFFFF), ml = (u32)((r >> 16) & 0xFFFF), ob = (u32)(r >> 32) + 3u;
         const u32 cl = ze_ll_code(ll), cm = ze_ml_code(ml), co = (u32)ze_highbit(ob);
         st_of = ze_encode(b, T.st_of, T.dnb_of, T.dfs_of, st_of, co);
@@ -218,8 +265,7 @@ ZPB_DEVINL u32 ze_encode_range(const u8 *lz, u32 begin, u32 end, u32 tail_end, u
     ze_add(b, st_of & 31u, 5);
     ze_add(b, st_ll & 63u, 6);
     ze_add(b, 1u, 1);                                // BIT_closeCStream: the end mark
-    ze_flush(b);
-    if (b.n) { if (b.p < b.end) *b.p++ = (u8)b.acc; else b.ovf = true; }
+    ze_flush_all(b);
     if (b.ovf) return ZE_FAIL;
     return (u32)(b.p - out);
 }
