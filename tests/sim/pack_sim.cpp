@@ -21,12 +21,44 @@ extern "C" int sim_lz4_pack_blocks(const uint8_t *in, const uint64_t *src_off, c
     return 0;
 }
 
-// ---- the zstd encoder (zpack_b200/csrc/zstd_encode.cuh) is plain serial code per window of a block: called directly
+// ---- the zstd encoder (zpack_b200/csrc/zstd_encode.cuh) is plain serial code per window / per block: called directly,
+// in the order of the three kernels.  lz: one block's LZ4 payload (csize bytes), winop: its window offsets, raw_len: the
+// block's size.  bodies: ZE_SLOT bytes, window w's body at ZE_OFF(winop[w], w); zbody[16]: sizes (0: none).
+// Returns 1 when the block is encoded, 0 when it has to be stored raw.
 #include "../../zpack_b200/csrc/zstd_encode.cuh"
-extern "C" uint32_t sim_zstd_encode_range(const uint8_t *lz, uint32_t begin, uint32_t end, uint32_t tail_end, uint8_t *out, uint32_t cap) {
+extern "C" int sim_zstd_encode_block(const uint8_t *lz, uint32_t csize, uint32_t raw_len, const uint32_t *winop, uint8_t *bodies,
+                                     uint32_t *zbody, int use_huffman, uint32_t *modes) {
     static ZeTables T;
     static bool built = false;
     if (!built) { ze_build_tables(T); built = true; }
-    std::vector<u64> seq(ZE_WIN_SEQ);
-    return ze_encode_range(lz, begin, end, tail_end, out, cap, seq.data(), ZE_WIN_SEQ, T);
+    const u32 nwin = (raw_len - 12u) / 4096u + 1u;
+    std::vector<u8> zlit(ZE_LITSLOT + 64, 0);
+    std::vector<u64> zseq(16 * ZE_WIN_SEQ);
+    u32 lit_n[16] = {0}, seq_n[16] = {0};
+    std::vector<u32> hist(256, 0);
+    u32 total = 0;
+    for (u32 w = 0; w < nwin; ++w) {                                                            // stage A
+        const u32 begin = winop[w], end = winop[w + 1], tail_end = w + 1 == nwin ? csize : end;
+        if (!(begin <= end && tail_end <= csize && end <= tail_end)) return 0;
+        if (!ze_parse_range(lz, begin, end, tail_end, zlit.data() + ZE_LOFF(begin, w), zseq.data() + w * ZE_WIN_SEQ, ZE_WIN_SEQ, &lit_n[w], &seq_n[w]))
+            return 0;
+        for (u32 i = 0; i < lit_n[w]; ++i) ++hist[zlit[ZE_LOFF(begin, w) + i]];
+        total += lit_n[w];
+    }
+    ZeHuf H;                                                                                    // stage B
+    H.desc_len = 0;
+    if (use_huffman && total >= 256) ze_huf_build(hist.data(), H);
+    u32 sum = 0;
+    for (u32 w = 0; w < 16; ++w) zbody[w] = 0;
+    for (u32 w = 0; w < nwin; ++w) {                                                            // stage C
+        const u32 begin = winop[w], end = winop[w + 1], tail_end = w + 1 == nwin ? csize : end;
+        const u32 mode = ze_lit_mode(w, lit_n, nwin, H.desc_len != 0);
+        if (modes) modes[w] = mode;
+        const u32 z = ze_emit_range(zlit.data() + ZE_LOFF(begin, w), lit_n[w], zseq.data() + w * ZE_WIN_SEQ, seq_n[w], mode, H,
+                                    bodies + ZE_OFF(begin, w), (tail_end - begin) + ((tail_end - begin) >> 2) + 20u, T);
+        if (z == ZE_FAIL) return 0;
+        zbody[w] = z;
+        if (z) sum += z + 3;
+    }
+    return sum && sum < raw_len;
 }

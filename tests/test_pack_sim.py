@@ -126,12 +126,13 @@ def zstd_frame(bodies, blocks):
     return np.frombuffer(bytes(fr), np.uint8)
 
 
-def test_zstd_blocks_from_the_lz4_matches_decode_with_the_oracle_and_the_reference(sim, oracle):
-    """zstd_encode.cuh: every 4 KB window of the block compressor's LZ4 payload -> one zstd Compressed_Block (raw literals
-    + predefined-mode FSE sequences).  Frames must decode in the oracle's zstd port and in the UNMODIFIED reference's
-    ZSTD_decompress."""
-    sim.sim_zstd_encode_range.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
-    sim.sim_zstd_encode_range.restype = C.c_uint32
+@pytest.mark.parametrize("huffman", [0, 1])
+def test_zstd_blocks_from_the_lz4_matches_decode_with_the_oracle_and_the_reference(sim, oracle, huffman):
+    """zstd_encode.cuh: every 4 KB window of the block compressor's LZ4 payload -> one zstd Compressed_Block (Huffman or
+    raw literals + predefined-mode FSE sequences).  Frames must decode in the oracle's zstd port and in the UNMODIFIED
+    reference's ZSTD_decompress."""
+    sim.sim_zstd_encode_block.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    sim.sim_zstd_encode_block.restype = C.c_int
     rng = np.random.default_rng(5)
     blocks = [corpus.entry_bytes(i, 65536) for i in range(8)]
     blocks += [corpus.entry_bytes(20 + i, s) for i, s in enumerate((70, 300, 4097, 40000))]
@@ -139,33 +140,37 @@ def test_zstd_blocks_from_the_lz4_matches_decode_with_the_oracle_and_the_referen
     for k in range(300):
         p, q = int(rng.integers(40000, 65000)), int(rng.integers(0, 20000))
         far[p:p + 6] = far[q:q + 6]
+    skew = (rng.geometric(0.35, 65536) % 100).astype(np.uint8)    # very skewed literals: codes that need the 11-bit limit
+    skew[::97] = 120
+    for q in range(4096, 65536, 256):
+        skew[q:q + 96] = skew[q - 4096:q - 4000]                   # and enough matches for the block compressor to keep going
     blocks += [np.zeros(65536, np.uint8), np.frombuffer((b"abcdefgh" * 9000)[:65536], np.uint8),
-               rng.integers(0, 4, 65536, dtype=np.uint8), rng.integers(0, 256, 5000, dtype=np.uint8), far]
+               rng.integers(0, 4, 65536, dtype=np.uint8), rng.integers(0, 256, 5000, dtype=np.uint8), far, skew,
+               np.frombuffer(b"x" * 20000 + bytes(rng.integers(97, 123, 30000, dtype=np.uint8)), np.uint8)]
     packed = pack_blocks(sim, blocks, want_winop=True)
-    bodies, lz_total, z_total = [], 0, 0
+    bodies, lz_total, z_total, used = [], 0, 0, set()
     for b, (c, payload, winop) in zip(blocks, packed):
         subs = None
         if c:
-            nwin = (len(b) - 12) // 4096 + 1
-            subs, failed = [], False
-            for w in range(nwin):
-                begin, end = int(winop[w]), int(winop[w + 1])
-                tail_end = c if w + 1 == nwin else end
-                cap = (tail_end - begin) + ((tail_end - begin) >> 2) + 20
-                out = np.zeros(cap + 64, np.uint8)
-                n = sim.sim_zstd_encode_range(payload.ctypes.data, begin, end, tail_end, out.ctypes.data, cap)
-                assert (out[cap:] == 0).all()
-                if n == 0xFFFFFFFF:
-                    failed = True
-                    break
-                if n:
-                    subs.append(out[:n].copy())
-            if failed or sum(len(x) + 3 for x in subs) >= len(b):
-                subs = None
+            slot = np.zeros(65536 + 16384 + 512 + 64, np.uint8)
+            zbody = np.zeros(16, np.uint32)
+            modes = np.zeros(16, np.uint32)
+            pay = np.zeros(65536 + 16, np.uint8)
+            pay[:c] = payload
+            if sim.sim_zstd_encode_block(pay.ctypes.data, c, len(b), winop.ctypes.data, slot.ctypes.data, zbody.ctypes.data, huffman,
+                                         modes.ctypes.data):
+                nwin = (len(b) - 12) // 4096 + 1
+                subs = []
+                for w in range(nwin):
+                    if zbody[w]:
+                        o = int(winop[w]) + (int(winop[w]) >> 2) + 24 * w
+                        subs.append(slot[o:o + int(zbody[w])].copy())
+                        used.add(int(modes[w]))
         bodies.append(subs)
         lz_total += c if c else len(b)
         z_total += sum(len(x) + 3 for x in subs) if subs is not None else len(b)
-    assert sum(x is not None for x in bodies) >= len(blocks) - 5          # the random blocks stay raw
+    assert sum(x is not None for x in bodies) >= len(blocks) - 6          # the random blocks stay raw
+    assert used == ({0, 2, 3} if huffman else {0})
     for k in range(len(blocks)):                       # one frame per block, and all of them in one frame
         fr = zstd_frame([bodies[k]], [blocks[k]])
         rc, got = oracle.zstd_decode_port(fr, len(blocks[k]))
@@ -177,4 +182,4 @@ def test_zstd_blocks_from_the_lz4_matches_decode_with_the_oracle_and_the_referen
     if oracle.have_ref():
         assert np.array_equal(oracle.zstd_decompress_ref(fr, len(plain)), plain)
         ref = sum(len(oracle.zstd_compress_ref(b, 3)) for b in blocks)
-        print(f"\nzstd blocks: {z_total} bytes (LZ4 payloads {lz_total}) vs ZSTD_compress level 3: {ref}")
+        print(f"\nzstd blocks (huffman={huffman}): {z_total} bytes (LZ4 payloads {lz_total}) vs ZSTD_compress level 3: {ref}")

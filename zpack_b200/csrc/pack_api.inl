@@ -89,10 +89,11 @@ static int pack_device_impl(zpb_ctx *ctx, const u8 *d_in, u64 in_size, u8 *d_out
     if (!ctx->d_pscratch.ensure((max_round << 16) + 64) || !ctx->d_csize.ensure(max_round * sizeof(u32) + 16))
         return fail(ctx, ZPB_E_NOMEM, "block scratch allocation failed");
     if (any_zstd && (!ctx->d_zslot.ensure(max_round * (u64)ZE_SLOT + 64) || !ctx->d_zseq.ensure(max_round * 16 * (u64)ZE_WIN_SEQ * sizeof(u64) + 64) ||
-                     !ctx->d_zmeta.ensure(max_round * (17 + ZE_ZBODY) * sizeof(u32) + 64)))
+                     !ctx->d_zmeta.ensure(max_round * (17 + ZE_META) * sizeof(u32) + 64) || !ctx->d_zelit.ensure(max_round * (u64)ZE_LITSLOT + 64) ||
+                     !ctx->d_zhuf.ensure(max_round * sizeof(ZeHuf) + 64)))
         return fail(ctx, ZPB_E_NOMEM, "zstd block scratch allocation failed");
     u32 *d_winop = any_zstd ? (u32 *)ctx->d_zmeta.p : nullptr;
-    u32 *d_zbody = any_zstd ? d_winop + max_round * 17 : nullptr;
+    u32 *d_zbody = any_zstd ? d_winop + max_round * 17 : nullptr;      // ZE_META words per block, the body sizes first
     u64 *d_comp = (u64 *)ctx->d_res.p;
     u64 *d_dig = d_comp + n;
     int *d_st = (int *)(d_dig + n);
@@ -121,9 +122,15 @@ static int pack_device_impl(zpb_ctx *ctx, const u8 *d_in, u64 in_size, u8 *d_out
             ctx->launches += 1;
         }
         if (rb && any_zstd) {
-            zstd_encode_blocks_kernel<<<(u32)std::min<u64>((rb * 16 + 127) / 128, (u64)ctx->sm_count * 16), 128, 0, s>>>(
-                (const u8 *)ctx->d_pscratch.p, (const u32 *)ctx->d_csize.p, (const PackBlock *)ctx->d_pblk.p + r.b0, d_winop, (u32)rb,
-                (u8 *)ctx->d_zslot.p, (u64 *)ctx->d_zseq.p, d_zbody);
+            const u32 zgrid = (u32)std::min<u64>((rb * 16 + 127) / 128, (u64)ctx->sm_count * 16);
+            const PackBlock *zb = (const PackBlock *)ctx->d_pblk.p + r.b0;
+            zstd_parse_windows_kernel<<<zgrid, 128, 0, s>>>((const u8 *)ctx->d_pscratch.p, (const u32 *)ctx->d_csize.p, zb, d_winop, (u32)rb,
+                                                            d_zbody, (u8 *)ctx->d_zelit.p, (u64 *)ctx->d_zseq.p);
+            zstd_huf_tables_kernel<<<(u32)std::min<u64>((rb + 3) / 4, (u64)ctx->sm_count * 8), 128, 0, s>>>(
+                zb, (const u32 *)ctx->d_csize.p, d_winop, (u32)rb, d_zbody, (const u8 *)ctx->d_zelit.p, (ZeHuf *)ctx->d_zhuf.p);
+            zstd_encode_windows_kernel<<<zgrid, 128, 0, s>>>((const u32 *)ctx->d_csize.p, zb, d_winop, (u32)rb, d_zbody, (const u8 *)ctx->d_zelit.p,
+                                                             (const u64 *)ctx->d_zseq.p, (const ZeHuf *)ctx->d_zhuf.p, (u8 *)ctx->d_zslot.p);
+            ctx->launches += 2;
             CK(ctx, cudaGetLastError());
             ctx->launches += 1;
         }

@@ -1,15 +1,21 @@
 // zstd_encode.cuh — zstd Compressed_Blocks from the LZ4 block compressor's matches: one thread per 64 KB block.
 //
 // The role of ZSTD_compressBlock_internal's back end (/root/reference/externals/zstd/lib/compress/zstd_compress.c,
-// zstd_compress_sequences.c:ZSTD_encodeSequences, fse_compress.c) for the writer's ZPACK_COMPRESSION_ZSTD arm
-// (lib/zpack_write.c:179).  Match finding is NOT zstd's: the sequences are the ones lz4_pack_blocks_kernel found for the
-// block (pack_blocks.cuh; greedy, 64 KB window, 4-byte minimum match), read back from its LZ4 payload.  They are written
-// as a valid zstd block (zstd_compression_format.md): Raw_Literals_Block + a sequences section in Predefined_Mode — the
-// three default FSE distributions, encoded backwards exactly as ZSTD_encodeSequences does (states initialised from the
-// last sequence, extra bits LL / ML / OF, per earlier sequence the OF, ML, LL state transitions, final states ML, OF,
-// LL, end mark).  No repeat-offset codes are emitted (offset value = offset + 3 always), no Huffman literals: the ratio
-// is the LZ4 compressor's plus what FSE saves on the length codes, and is reported next to ZSTD_compress level 3 by the
-// tests and the bench.  A block that does not shrink stays a Raw_Block.
+// zstd_compress_sequences.c:ZSTD_encodeSequences, huf_compress.c, fse_compress.c) for the writer's
+// ZPACK_COMPRESSION_ZSTD arm (lib/zpack_write.c:179).  Match finding is NOT zstd's: the sequences are the ones
+// lz4_pack_blocks_kernel found for the block (pack_blocks.cuh; greedy, 64 KB window, 4-byte minimum match), read back
+// from its LZ4 payload window by window.  Every 4 KB window becomes one zstd Compressed_Block
+// (zstd_compression_format.md):
+//   * literals: Huffman-coded in four streams with ONE code per 64 KB block, built from the histogram of all the block's
+//     literals (lengths limited to 11 bits, direct 4-bit weight description); the block's first window with enough
+//     literals carries the tree (Compressed_Literals_Block), the later ones reuse it (Treeless_Literals_Block).  Blocks
+//     whose literals use byte values above 128, short sections and sections that would not shrink stay Raw_Literals.
+//   * sequences: Predefined_Mode — the three default FSE distributions, encoded backwards exactly as
+//     ZSTD_encodeSequences does (states initialised from the last sequence, extra bits LL / ML / OF, per earlier sequence
+//     the OF, ML, LL state transitions, final states ML, OF, LL, end mark).  No repeat-offset codes (offset value =
+//     offset + 3 always).
+// The ratio is reported next to ZSTD_compress level 3 by the tests and the bench.  A block that does not shrink stays a
+// Raw_Block.
 #pragma once
 #include "common.cuh"
 
@@ -169,24 +175,21 @@ ZPB_DEVINL u32 ze_encode(ZeBits &b, const u16 *st, const u32 *dnb, const int *df
 // larger than the LZ4 bytes it restates: 16-bit offsets cost 2 bytes there, code + extra bits here)
 #define ZE_SLOT (65536u + 16384u + 512u)
 #define ZE_OFF(begin, w) ((begin) + ((begin) >> 2) + 24u * (w))
-#define ZE_ZBODY 16u           // per block: the body size of every window's sub-block (0: nothing to emit, ZE_FAIL: store the block raw)
+#define ZE_ZBODY ZE_META       // stride of the per-block words; the first 16: body size of every window's sub-block (0: nothing to emit, ZE_FAIL: store the block raw)
+#define ZE_HUF_MIN 64u         // literal sections shorter than this stay raw
+#define ZE_HUF_SYMS 129u       // direct (4-bit) weight description: symbols 0..128 (huf_compress.c:HUF_writeCTable, header >= 128)
 
-// One sub-block: the LZ4 sequences in lz[begin, end) — whole sequences, each with a match — and, for the last
-// sub-block of a block, the closing literals-only sequence lz[end, tail_end) -> a zstd Compressed_Block body at `out`.
-// `seq`: scratch for `seq_cap` records.  Returns the body size; 0 when the range is empty; ZE_FAIL when the body does
-// not fit `cap` or the payload is not what pack_blocks.cuh writes (the caller then stores the whole block raw).
-ZPB_DEVINL u32 ze_encode_range(const u8 *lz, u32 begin, u32 end, u32 tail_end, u8 *out, u32 cap, u64 *seq, u32 seq_cap,
-                               const ZeTables &T) {
-    if (begin == end && tail_end == end) return 0;
-    if (cap < 16) return ZE_FAIL;
-    // ---- forward: literals to the literals section (3-byte Raw_Literals_Block header, filled in below), sequences to
-    // `seq`.  The payload is read eight bytes at a time; literal bytes are gathered in a bit writer and leave as words.
+// ---- stage A: one window's LZ4 sequences lz[begin, end) (+ the block's closing literals-only sequence lz[end, tail_end)
+// for its last window) -> literal bytes at `lit_dst` (capacity tail_end - begin), records in `seq`.  false: not what
+// pack_blocks.cuh writes.
+ZPB_DEVINL bool ze_parse_range(const u8 *lz, u32 begin, u32 end, u32 tail_end, u8 *lit_dst, u64 *seq, u32 seq_cap, u32 *lit_n,
+                               u32 *seq_n) {
     u32 lit = 0, nseq = 0;
     ZeIn in;
     in.base = lz;
     ze_in_seek(in, begin);
     ZeBits lw;
-    ze_open(lw, out + 3, out + cap, false);          // the bytes in front: the header (written below), up to 3 bytes of slack of the window before
+    ze_open(lw, lit_dst, lit_dst + (tail_end - begin) + 8u, false);
     bool bad = false;                                 // single-exit loops: the lanes of a warp (one window each) reconverge every iteration
     while (in.pos < tail_end && !bad) {
         const u32 token = ze_in_byte(in);
@@ -195,7 +198,7 @@ ZPB_DEVINL u32 ze_encode_range(const u8 *lz, u32 begin, u32 end, u32 tail_end, u
             u32 x;
             do { x = in.pos < tail_end ? ze_in_byte(in) : 0u; ll += x; } while (x == 255);
         }
-        if (in.pos + ll > tail_end || 3 + lit + ll + 8 >= cap) { bad = true; ll = 0; }
+        if (in.pos + ll > tail_end) { bad = true; ll = 0; }
         for (u32 i = 0; i < ll; ++i) { ze_add(lw, ze_in_byte(in), 8); ze_flush(lw); }
         lit += ll;
         if (in.pos > end) {                           // the closing sequence of the block: literals only
@@ -215,15 +218,178 @@ ZPB_DEVINL u32 ze_encode_range(const u8 *lz, u32 begin, u32 end, u32 tail_end, u
             else seq[nseq++] = (u64)ll | ((u64)ml << 16) | ((u64)off << 32);
         }
     }
-    if (bad) return ZE_FAIL;
     ze_flush_all(lw);
-    if (lw.ovf) return ZE_FAIL;
-    out[0] = (u8)(0x0Cu | ((lit & 0xFu) << 4));       // Raw_Literals_Block, size format 11: 20-bit size
-    out[1] = (u8)(lit >> 4);
-    out[2] = (u8)(lit >> 12);
-    u32 op = 3 + lit;
+    *lit_n = lit;
+    *seq_n = nseq;
+    return !bad && !lw.ovf;
+}
+
+// ---- stage B: one Huffman code per 64 KB block, from the histogram of all its literals (huf_compress.c:HUF_buildCTable,
+// HUF_writeCTable).  Lengths are limited to 11 bits by the overflow rule of deflate's gen_bitlen; the description is
+// the direct one (4-bit weights), so only blocks whose literals are bytes 0..128 get a table — text does, binary data
+// keeps raw literals.
+struct ZeHuf {
+    u16 code[ZE_HUF_SYMS + 3];
+    u8 len[ZE_HUF_SYMS + 3];
+    u8 desc[68];          // header byte + weights of symbols 0 .. last-1, two per byte
+    u32 desc_len;         // 0: no table for this block
+};
+ZPB_DEVINL void ze_huf_build(const u32 *hist, ZeHuf &H) {
+    H.desc_len = 0;
+    int last = -1, n = 0;
+    for (int s = 0; s < 256; ++s) if (hist[s]) { last = s; ++n; }
+    if (n < 2 || last >= (int)ZE_HUF_SYMS) return;
+    // leaves by ascending count (insertion sort), then the two-queue construction
+    short order[ZE_HUF_SYMS];
+    u32 cnt[2 * ZE_HUF_SYMS];
+    short parent[2 * ZE_HUF_SYMS];
+    int m = 0;
+    for (int s = 0; s <= last; ++s) {
+        if (!hist[s]) continue;
+        int k = m++;
+        while (k > 0 && hist[order[k - 1]] > hist[s]) { order[k] = order[k - 1]; --k; }
+        order[k] = (short)s;
+    }
+    for (int i = 0; i < n; ++i) cnt[i] = hist[order[i]];
+    int lf = 0, in0 = n, in1 = n;                       // next leaf, first unused internal node, next free node
+    for (int k = 0; k < n - 1; ++k) {
+        int a, b;
+        if (lf < n && (in0 >= in1 || cnt[lf] <= cnt[in0])) a = lf++; else a = in0++;
+        if (lf < n && (in0 >= in1 || cnt[lf] <= cnt[in0])) b = lf++; else b = in0++;
+        cnt[in1] = cnt[a] + cnt[b];
+        parent[a] = parent[b] = (short)in1;
+        ++in1;
+    }
+    const int root = in1 - 1;
+    u8 depth[2 * ZE_HUF_SYMS];
+    depth[root] = 0;
+    for (int i = root - 1; i >= 0; --i) depth[i] = (u8)(depth[parent[i]] + 1);     // parents have larger indices
+    // length limit 11: leaves deeper than that are lifted, and for every two of them one shallower leaf goes down a level
+    int bl[32];
+    for (int i = 0; i < 32; ++i) bl[i] = 0;
+    int overflow = 0;
+    for (int i = 0; i < n; ++i) {
+        int d = depth[i];
+        if (d > 11) { d = 11; ++overflow; }
+        ++bl[d];
+    }
+    while (overflow > 0) {
+        int bits = 10;
+        while (bl[bits] == 0) --bits;
+        --bl[bits];
+        bl[bits + 1] += 2;
+        --bl[11];
+        overflow -= 2;
+    }
+    int maxbits = 11;
+    while (bl[maxbits] == 0) --maxbits;
+    // lengths back to the symbols: the rarest get the longest codes
+    for (int s = 0; s < (int)ZE_HUF_SYMS + 3; ++s) { H.len[s] = 0; H.code[s] = 0; }
+    {
+        int i = 0;
+        for (int bits = maxbits; bits >= 1; --bits)
+            for (int c = 0; c < bl[bits]; ++c) H.len[order[i++]] = (u8)bits;
+    }
+    // codes as a decoder derives them from the weights (huf_decompress.c:HUF_readDTableX1): weight w = maxbits + 1 - len,
+    // table cells of 2^(w-1) in ascending weight, symbols of one weight in ascending order
+    u32 start[16], rank[16];
+    for (int r = 0; r < 16; ++r) rank[r] = 0;
+    for (int s = 0; s <= last; ++s) if (H.len[s]) ++rank[maxbits + 1 - H.len[s]];
+    u32 acc = 0;
+    for (int r = 1; r <= maxbits; ++r) { start[r] = acc; acc += rank[r] << (r - 1); }
+    if (acc != (1u << maxbits)) return;               // not a complete code: cannot happen, but then no table
+    for (int s = 0; s <= last; ++s) {
+        if (!H.len[s]) continue;
+        const int w = maxbits + 1 - H.len[s];
+        H.code[s] = (u16)(start[w] >> (w - 1));
+        start[w] += 1u << (w - 1);
+    }
+    // description: 127 + number of weights, then the weights of symbols 0 .. last-1 (the last one is implied)
+    const int nw = last;
+    H.desc[0] = (u8)(127 + nw);
+    for (int i = 0; i < nw; i += 2) {
+        const u32 w0 = H.len[i] ? (u32)(maxbits + 1 - H.len[i]) : 0u;
+        const u32 w1 = i + 1 < nw && H.len[i + 1] ? (u32)(maxbits + 1 - H.len[i + 1]) : 0u;
+        H.desc[1 + i / 2] = (u8)((w0 << 4) | w1);
+    }
+    H.desc_len = 1u + (u32)(nw + 1) / 2u;
+}
+
+// which kind of literals section window w writes: 0 raw, 2 Compressed (carries the block's tree), 3 Treeless (uses it).
+// The tree rides on the first window with enough literals; windows before it stay raw.
+ZPB_DEVINL u32 ze_lit_mode(u32 w, const u32 *lit_n, u32 nwin, bool have_table) {
+    if (!have_table || lit_n[w] < ZE_HUF_MIN) return 0;
+    for (u32 k = 0; k < w && k < nwin; ++k) if (lit_n[k] >= ZE_HUF_MIN) return 3;
+    return 2;
+}
+
+// one Huffman stream: symbols lit[0, n) coded last to first (huf_compress.c:HUF_compress1X_usingCTable), end mark; returns bytes
+ZPB_DEVINL u32 ze_huf_stream(const u8 *lit, u32 n, u8 *at, u8 *end, const ZeHuf &H, bool *ovf) {
+    ZeBits b;
+    ze_open(b, at, end, true);
+    for (u32 i = n; i-- > 0;) {
+        const u32 s = lit[i];
+        ze_add(b, H.code[s], H.len[s]);
+        ze_flush(b);
+    }
+    ze_add(b, 1u, 1);
+    ze_flush_all(b);
+    *ovf |= b.ovf;
+    return (u32)(b.p - at);
+}
+
+// ---- stage C: one window's sub-block body at `out`: literals section (raw, or Huffman-coded in four streams with the
+// block's table), sequences section.  Returns the body size; 0 when the window has nothing to emit; ZE_FAIL when it does
+// not fit `cap` (the caller then stores the whole block raw).
+ZPB_DEVINL u32 ze_emit_range(const u8 *lit, u32 lit_n, const u64 *seq, u32 nseq, u32 mode, const ZeHuf &H, u8 *out, u32 cap,
+                             const ZeTables &T) {
+    if (lit_n == 0 && nseq == 0) return 0;
+    if (cap < 24) return ZE_FAIL;
+    u32 op = 0;
+    bool ovf = false;
+    if (mode) {
+        // Compressed / Treeless literals, four streams (zstd_compression_format.md: Literals_Section_Header, size formats
+        // 01 / 10 / 11 by the larger of the two sizes; jump table of three 16-bit stream sizes)
+        const u32 fmt = lit_n < 1024 ? 1u : (lit_n < 16384 ? 2u : 3u);
+        const u32 hdr = 3u + (fmt - 1u);
+        const u32 tree = mode == 2 ? H.desc_len : 0u;
+        if (hdr + tree + 6u + 16u >= cap) return ZE_FAIL;
+        for (u32 i = 0; i < tree; ++i) out[hdr + i] = H.desc[i];
+        u8 *jt = out + hdr + tree;
+        u32 pos = hdr + tree + 6u;
+        const u32 seg = (lit_n + 3u) / 4u;
+        u32 sz[4];
+        for (u32 k = 0; k < 4; ++k) {
+            const u32 a = k * seg, n = k < 3 ? seg : lit_n - 3u * seg;
+            sz[k] = ze_huf_stream(lit + a, n, out + pos, out + cap, H, &ovf);
+            pos += sz[k];
+        }
+        const u32 comp = tree + 6u + sz[0] + sz[1] + sz[2] + sz[3];
+        const u32 lim = fmt == 1 ? 1024u : (fmt == 2 ? 16384u : 262144u);
+        if (!ovf && comp < lim && comp < lit_n && sz[0] < 65536u && sz[1] < 65536u && sz[2] < 65536u) {
+            for (u32 k = 0; k < 3; ++k) { jt[2 * k] = (u8)sz[k]; jt[2 * k + 1] = (u8)(sz[k] >> 8); }
+            const u32 bits = 10u + 4u * (fmt - 1u);
+            const u64 h = (u64)mode | ((u64)fmt << 2) | ((u64)lit_n << 4) | ((u64)comp << (4 + bits));
+            for (u32 i = 0; i < hdr; ++i) out[i] = (u8)(h >> (8 * i));
+            op = pos;
+        } else if (mode == 2) return ZE_FAIL;         // the tree carrier must not fall back: later windows count on the table
+        else mode = 0;
+    }
+    if (!mode) {
+        if (3 + lit_n + 8 >= cap) return ZE_FAIL;
+        out[0] = (u8)(0x0Cu | ((lit_n & 0xFu) << 4));  // Raw_Literals_Block, size format 11: 20-bit size
+        out[1] = (u8)(lit_n >> 4);
+        out[2] = (u8)(lit_n >> 12);
+        ZeBits lw;
+        ze_open(lw, out + 3, out + cap, true);
+        for (u32 i = 0; i < lit_n; ++i) { ze_add(lw, lit[i], 8); ze_flush(lw); }
+        ze_flush_all(lw);
+        if (lw.ovf) return ZE_FAIL;
+        op = 3 + lit_n;
+    }
+    if (op + 8 >= cap) return ZE_FAIL;
     // ---- sequences section header: count, then symbol compression modes = 0 (all predefined)
-    if (nseq == 0) { out[op++] = 0; return op <= cap ? op : ZE_FAIL; }
+    if (nseq == 0) { out[op++] = 0; return op; }
     if (nseq < 128) out[op++] = (u8)nseq;
     else if (nseq < 0x7F00) { out[op++] = (u8)((nseq >> 8) + 0x80); out[op++] = (u8)nseq; }
     else { out[op++] = 0xFF; out[op++] = (u8)(nseq - 0x7F00); out[op++] = (u8)((nseq - 0x7F00) >> 8); }
@@ -270,35 +436,105 @@ ZPB_DEVINL u32 ze_encode_range(const u8 *lz, u32 begin, u32 end, u32 tail_end, u
     return (u32)(b.p - out);
 }
 
+#define ZE_LITSLOT (65536u + 256u)                    // a block's staged literals: window w's at ZE_LOFF(payload offset, w)
+#define ZE_LOFF(begin, w) ((((begin) + 3u) & ~3u) + 8u * (w))
+#define ZE_META 48u                                   // u32 per block: 16 body sizes | 16 literal counts | 16 sequence counts
+
 #ifndef ZPB_SIM
-// One THREAD per 4 KB window of the block compressor: the window's sequences become one zstd sub-block (the windows'
-// payload offsets come from lz4_pack_blocks_kernel: winop).  Each walk is serial and latency-bound, so the kernel relies
-// on the number of windows in flight (16 per block, every block of the round at once), not on staging.
-// zbody[b * 16 + w] = body size of window w (0: none, ZE_FAIL: the block is stored raw).  Only the blocks the host marked
-// (PackBlock::pad != 0: they belong to a ZPACK_COMPRESSION_ZSTD file) are encoded.
+// Three launches per round, all over the blocks the host marked (PackBlock::pad != 0: they belong to a
+// ZPACK_COMPRESSION_ZSTD file).  meta = ZE_META words per block, winop = 17 window offsets per block.
+//
+// A: one THREAD per 4 KB window of the block compressor (its payload offsets come from lz4_pack_blocks_kernel: winop):
+//    the window's LZ4 sequences -> staged literal bytes + sequence records.  Each walk is serial and latency-bound, so the
+//    kernel relies on the number of windows in flight (16 per block, every block of the round at once), not on staging.
 __global__ void __launch_bounds__(128)
-zstd_encode_blocks_kernel(const u8 *__restrict__ lz_slots, const u32 *__restrict__ csize, const PackBlock *__restrict__ blocks,
-                          const u32 *__restrict__ winop, u32 nblocks, u8 *zslot, u64 *zseq, u32 *zbody) {
+zstd_parse_windows_kernel(const u8 *__restrict__ lz_slots, const u32 *__restrict__ csize, const PackBlock *__restrict__ blocks,
+                          const u32 *__restrict__ winop, u32 nblocks, u32 *meta, u8 *zlit, u64 *zseq) {
+    const u64 nwork = (u64)nblocks * 16u;
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < nwork; t += (u64)gridDim.x * blockDim.x) {
+        const u32 b = (u32)(t >> 4), w = (u32)(t & 15u);
+        const u32 cs = csize[b], len = blocks[b].len;
+        u32 *m = meta + (u64)b * ZE_META;
+        const u32 *wo = winop + (u64)b * 17u;
+        u32 lit_n = 0, seq_n = ZE_FAIL;
+        if (blocks[b].pad && cs) {
+            const u32 nwin = (len - 12u) / 4096u + 1u;           // as in pack_blocks.cuh (cs != 0 implies len >= 13)
+            seq_n = 0;
+            if (w < nwin) {
+                const u32 begin = wo[w], end = wo[w + 1u];
+                const u32 tail_end = w + 1u == nwin ? cs : end;
+                if (!(begin <= end && tail_end <= cs && end <= tail_end) ||
+                    !ze_parse_range(lz_slots + ((u64)b << 16), begin, end, tail_end, zlit + (u64)b * ZE_LITSLOT + ZE_LOFF(begin, w),
+                                    zseq + t * ZE_WIN_SEQ, ZE_WIN_SEQ, &lit_n, &seq_n))
+                    seq_n = ZE_FAIL;
+            }
+        }
+        m[16u + w] = lit_n;
+        m[32u + w] = seq_n;
+    }
+}
+
+// B: one warp per block: histogram of the block's staged literals in shared memory, lane 0 builds the Huffman code.
+__global__ void __launch_bounds__(128)
+zstd_huf_tables_kernel(const PackBlock *__restrict__ blocks, const u32 *__restrict__ csize, const u32 *__restrict__ winop, u32 nblocks,
+                       const u32 *__restrict__ meta, const u8 *__restrict__ zlit, ZeHuf *hufs) {
+    __shared__ u32 hist_all[4][256];
+    const u32 lane = threadIdx.x & 31u, wp = threadIdx.x >> 5;
+    u32 *hist = hist_all[wp];
+    for (u32 b = blockIdx.x * 4u + wp; b < nblocks; b += gridDim.x * 4u) {
+        const u32 *m = meta + (u64)b * ZE_META;
+        for (u32 i = lane; i < 256; i += 32) hist[i] = 0;
+        __syncwarp();
+        u32 total = 0;
+        bool ok = blocks[b].pad && csize[b];
+        if (ok) {
+            const u32 nwin = (blocks[b].len - 12u) / 4096u + 1u;
+            for (u32 w = 0; w < nwin; ++w) {
+                if (m[32u + w] == ZE_FAIL) { ok = false; break; }
+                const u32 n = m[16u + w];
+                const u8 *p = zlit + (u64)b * ZE_LITSLOT + ZE_LOFF(winop[(u64)b * 17u + w], w);
+                for (u32 i = lane; i < n; i += 32) atomicAdd(&hist[p[i]], 1u);
+                total += n;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (ok && total >= 256u) ze_huf_build(hist, hufs[b]);
+            else hufs[b].desc_len = 0;
+        }
+        __syncwarp();
+    }
+}
+
+// C: one thread per window again: the window's sub-block body.  meta[w]: body size (0: none, ZE_FAIL: the
+// block is stored raw).
+__global__ void __launch_bounds__(128)
+zstd_encode_windows_kernel(const u32 *__restrict__ csize, const PackBlock *__restrict__ blocks, const u32 *__restrict__ winop, u32 nblocks,
+                           u32 *meta, const u8 *__restrict__ zlit, const u64 *__restrict__ zseq, const ZeHuf *__restrict__ hufs, u8 *zslot) {
     __shared__ ZeTables T;
     if (threadIdx.x == 0) ze_build_tables(T);
     __syncthreads();
     const u64 nwork = (u64)nblocks * 16u;
     for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < nwork; t += (u64)gridDim.x * blockDim.x) {
         const u32 b = (u32)(t >> 4), w = (u32)(t & 15u);
-        const u32 cs = csize[b], len = blocks[b].len;
+        u32 *m = meta + (u64)b * ZE_META;
         u32 z = 0;
-        if (blocks[b].pad && cs) {
-            const u32 nwin = (len - 12u) / 4096u + 1u;           // as in pack_blocks.cuh (cs != 0 implies len >= 13)
+        if (blocks[b].pad && csize[b]) {
+            const u32 nwin = (blocks[b].len - 12u) / 4096u + 1u;
             if (w < nwin) {
                 const u32 begin = winop[(u64)b * 17u + w], end = winop[(u64)b * 17u + w + 1u];
-                const u32 tail_end = w + 1u == nwin ? cs : end;
-                z = begin <= end && tail_end <= cs && end <= tail_end
-                        ? ze_encode_range(lz_slots + ((u64)b << 16), begin, end, tail_end, zslot + (u64)b * ZE_SLOT + ZE_OFF(begin, w),
-                                          (tail_end - begin) + ((tail_end - begin) >> 2) + 20u, zseq + t * ZE_WIN_SEQ, ZE_WIN_SEQ, T)
-                        : ZE_FAIL;
+                const u32 tail_end = w + 1u == nwin ? csize[b] : end;
+                const u32 seq_n = m[32u + w];
+                if (seq_n == ZE_FAIL) z = ZE_FAIL;
+                else {
+                    const ZeHuf &H = hufs[b];
+                    const u32 mode = ze_lit_mode(w, m + 16u, nwin, H.desc_len != 0);
+                    z = ze_emit_range(zlit + (u64)b * ZE_LITSLOT + ZE_LOFF(begin, w), m[16u + w], zseq + t * ZE_WIN_SEQ, seq_n, mode, H,
+                                      zslot + (u64)b * ZE_SLOT + ZE_OFF(begin, w), (tail_end - begin) + ((tail_end - begin) >> 2) + 20u, T);
+                }
             }
         } else if (w == 0) z = ZE_FAIL;
-        zbody[t] = z;
+        m[w] = z;
     }
 }
 #endif
