@@ -32,6 +32,9 @@ WORKLOADS = {
     # LZ4 pack of the C2 corpus (run_c3 below); `entries` = files per GPU
     "c3": {"method": 2, "metric": "lz4_pack_xxh3_uncompressed_GBps", "entries": 65536, "kernel": "lz4_pack_blocks_kernel",
            "stage": "pack_ms", "what": "C3: LZ4 pack (independent 64 KB blocks) + XXH3-64 of the input"},
+    # the same through the zstd writer (LZ4 block compressor's matches as zstd blocks: Huffman literals + predefined FSE sequences)
+    "c3z": {"method": 1, "metric": "zstd_pack_xxh3_uncompressed_GBps", "entries": 16384, "kernel": "lz4_pack_blocks_kernel",
+            "stage": "pack_ms", "what": "C3 with the zstd writer: zstd pack (64 KB blocks, one sub-block per 4 KB window) + XXH3-64 of the input"},
     # one entry of gpus x 2 GiB, independent 64 KB blocks, sharded by blocks (run_c5 below); `entries` = blocks per GPU
     "c5": {"method": 2, "metric": "lz4_single_entry_unpack_xxh3_verify_uncompressed_GBps", "entries": 32768,
            "kernel": "lz4_fast_exec_kernel", "stage": "exec_ms",
@@ -198,18 +201,19 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     wl = WORKLOADS[args.workload]
     n_sample = args.ref_entries or args.entries or wl["entries"]
-    if args.workload == "c3":
+    if args.workload in ("c3", "c3z"):
+        pm, pl = (1, 3) if args.workload == "c3z" else (2, 0)
         data, _, _ = build_corpus(n_sample, ENTRY_SIZE, 0, cores)
         for _ in range(args.warmup):
-            cpu_pack_throughput(data, ENTRY_SIZE, min(n_sample, 512), cores)
-        vals = [cpu_pack_throughput(data, ENTRY_SIZE, n_sample, cores) for _ in range(args.steps)]
+            cpu_pack_throughput(data, ENTRY_SIZE, min(n_sample, 512), cores, pm, pl)
+        vals = [cpu_pack_throughput(data, ENTRY_SIZE, n_sample, cores, pm, pl) for _ in range(args.steps)]
         value, kind = float(np.mean([v[0] for v in vals])), vals[0][2]
         line = {"metric": wl["metric"], "value": value, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * n_sample * ENTRY_SIZE / (value * 1e9),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "impl": "reference",
                 "config": {"workload": f"{wl['what']}, sample of {n_sample} x 128 KiB files (zpk-synth-v1), reference "
-                                       "zpack_write_archive (level 0) on host cores", "ratio": vals[0][3]},
+                                       f"zpack_write_archive ({'zstd level 3' if pm == 1 else 'LZ4 level 0'}) on host cores", "ratio": vals[0][3]},
                 "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": kind,
                                  "sample": f"{n_sample} files x 128 KiB per step, {cores} independent writers"},
                 "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -755,7 +759,7 @@ def build_corpus(n, size, first, workers):
     return np.frombuffer(_C3_SHARED, np.uint8), hashes, ref * 17
 
 
-def cpu_pack_throughput(data, size, n_sample, threads):
+def cpu_pack_throughput(data, size, n_sample, threads, method=2, level=0):
     """The reference's own writer (zpack_write_archive into a heap writer, oracle/_ref) over `n_sample` files split
     across `threads` independent writers (the reference writer is single-threaded by contract, lib/zpack.h:476-485:
     this is the T-way sharded variant of SURVEY section 8(d)); the port's frame writer when _ref is absent."""
@@ -769,7 +773,7 @@ def cpu_pack_throughput(data, size, n_sample, threads):
         idx = range(t, n_sample, threads)
         bufs = [data[i * size:(i + 1) * size] for i in idx]
         if use_ref:
-            comp[t] = len(O.write_archive_ref([f"f{i}" for i in idx], bufs, 2, 0))
+            comp[t] = len(O.write_archive_ref([f"f{i}" for i in idx], bufs, method, level))
         else:
             comp[t] = sum(len(O.lz4f_encode_port(b, 0, False)) for b in bufs)
     ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
@@ -798,21 +802,22 @@ def run_c3(args):
     if world > 1:
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    wl = WORKLOADS["c3"]
+    wl = WORKLOADS[args.workload if args.workload in ("c3", "c3z") else "c3"]
+    method = wl["method"]
     n = args.entries or wl["entries"]
     size = ENTRY_SIZE
     t_prep = time.time()
     data, hashes, ref_comp = build_corpus(n, size, rank * n, max(1, (os.cpu_count() or 1) // world))
     prep_s = time.time() - t_prep
     ctx = zpack_b200.Context(local)
-    cap = ctx.pack_bound(2, size)
+    cap = ctx.pack_bound(method, size)
     slot = (cap + 15) & ~15
     f = np.zeros(n, zlib.File)
     f["src_off"] = np.arange(n, dtype=np.uint64) * size
     f["size"] = size
     f["dst_off"] = np.arange(n, dtype=np.uint64) * slot
     f["dst_cap"] = cap
-    f["method"] = 2
+    f["method"] = method
     in_size, out_size = n * size, n * slot
     h_in = torch.from_numpy(data).pin_memory()
     d_in = h_in.cuda()
@@ -831,7 +836,7 @@ def run_c3(args):
     e = np.zeros(n, zlib.Entry)
     e["src_off"], e["comp_size"], e["uncomp_size"] = f["dst_off"], comp, size
     e["dst_off"] = np.arange(n, dtype=np.uint64) * size
-    e["dst_cap"], e["hash"], e["method"] = size, hashes, 2
+    e["dst_cap"], e["hash"], e["method"] = size, hashes, method
     d_back = torch.empty(in_size, dtype=torch.uint8, device="cuda")
     st2, dg2 = ctx.unpack_device(d_out, out_size, d_back, in_size, e, stream)
     assert (st2 == 0).all() and np.array_equal(dg2, hashes), "GPU-written frames do not read back"
@@ -839,7 +844,7 @@ def run_c3(args):
     del d_back
     for i in range(0, n, max(1, n // 32)):
         fr = d_out[int(f["dst_off"][i]):int(f["dst_off"][i]) + int(comp[i])].cpu().numpy()
-        rc, got, _ = O.read_entry_port(2, fr, size, size, int(hashes[i]))
+        rc, got, _ = O.read_entry_port(method, fr, size, size, int(hashes[i]))
         assert rc == 0 and np.array_equal(got, data[i * size:(i + 1) * size]), "CPU checker rejects a GPU-written frame"
     comp_bytes = int(comp.sum())
 
@@ -912,11 +917,11 @@ def run_c3(args):
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             n_ref = min(n, args.ref_entries or 16384)       # ~0.4 s per step on 16 cores at the reference's ~5 GB/s
-            v, dt, kind, ratio = cpu_pack_throughput(data, size, n_ref, cores)
-            v1, _, _, _ = cpu_pack_throughput(data, size, min(n, 1024), 1)
+            v, dt, kind, ratio = cpu_pack_throughput(data, size, n_ref, cores, method, 3 if method == 1 else 0)
+            v1, _, _, _ = cpu_pack_throughput(data, size, min(n, 1024), 1, method, 3 if method == 1 else 0)
             line["cpu_baseline"] = {"value": v, "unit": "GB/s", "cores": cores, "kind": kind, "ratio": ratio,
                                     "sample": f"first {n_ref} files, {cores} independent writers "
-                                              f"(zpack_write_archive, level 0); single writer: {v1:.3f} GB/s"}
+                                              f"(zpack_write_archive, {'zstd level 3' if method == 1 else 'LZ4 level 0'}); single writer: {v1:.3f} GB/s"}
         _emit(args, line)
     if world > 1 and not getattr(args, "nested", False):
         dist.destroy_process_group()
@@ -955,7 +960,7 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
-    runner = {"c5": run_c5, "c3": run_c3}.get(args.workload, run_ours)
+    runner = {"c5": run_c5, "c3": run_c3, "c3z": run_c3}.get(args.workload, run_ours)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not (args.workload == "c2" and args.configs and world == 1 and not args.entries):
         runner(args)
@@ -969,6 +974,7 @@ def main():
     line = args.result
     block = {}
     for key, fn, n_small, what in (("c3", run_c3, 16384, "LZ4 pack, 16384 files x 128 KiB (2 GiB)"),
+                                   ("c3z", run_c3, 8192, "zstd pack, 8192 files x 128 KiB (1 GiB): the LZ4 block compressor's matches as zstd blocks"),
                                    ("c4", run_ours, 8192, "zstd level-3 unpack + verify, 8192 entries x 128 KiB (1 GiB), frames written by the reference"),
                                    ("c5", run_c5, 16384, "one LZ4 entry of 16384 independent 64 KB blocks (1 GiB), block-sharded read")):
         sub = copy.copy(args)
@@ -979,7 +985,8 @@ def main():
             block[key] = {"workload": what, "metric": r["metric"], "value": r["value"], "unit": r["unit"], "ms_per_step": r["ms_per_step"],
                           "roofline_frac": r.get("roofline", {}).get("frac"), "kernel": r.get("roofline", {}).get("kernel"),
                           "e2e": (r.get("e2e") or {}).get("value"), "gpu_launches": r.get("gpu_launches"),
-                          **({"ratio": r["config"].get("ratio")} if isinstance(r.get("config"), dict) and "ratio" in r["config"] else {})}
+                          **({"ratio": r["config"].get("ratio")} if isinstance(r.get("config"), dict) and "ratio" in r["config"] else {}),
+                          **({"ratio_gpu": r["config"].get("ratio_gpu")} if isinstance(r.get("config"), dict) and "ratio_gpu" in r["config"] else {})}
         except Exception as ex:   # a configuration that cannot run here (e.g. no oracle/_ref for the zstd archive) says so
             block[key] = {"workload": what, "unavailable": f"{type(ex).__name__}: {ex}"[:300]}
     line["configs"] = block
