@@ -27,8 +27,8 @@ def main():
     ev = e.copy()
     ev["flags"] |= 2
     unc = float(d.uncomp_size.sum())
-    for chunk in (128, 256, 512, 1024, 2048):
-        for workers in (2, 3, 4, 6):
+    for chunk in [int(x) for x in os.environ.get("SWEEP_CHUNKS", "128,256,512,1024,2048").split(",")]:
+        for workers in [int(x) for x in os.environ.get("SWEEP_WORKERS", "2,3,4,6").split(",")]:
             os.environ["ZPB_HOST_CHUNK_MB"], os.environ["ZPB_HOST_WORKERS"] = str(chunk), str(workers)
             ctx = zpack_b200.Context(0)
             res = {}

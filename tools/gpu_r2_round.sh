@@ -6,8 +6,12 @@ nproc; lscpu | grep 'Model name'
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_c2_reference.json 2> gpurun_out/r2_bench_c2_reference.err; cat gpurun_out/r2_bench_c2_reference.json
-python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_c2.json 2> gpurun_out/r2_bench_c2.err; cut -c1-1500 gpurun_out/r2_bench_c2.json; tail -2 gpurun_out/r2_bench_c2.err
+SECONDS=0; python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_c2.json 2> gpurun_out/r2_bench_c2.err; echo "default bench.py wall time: ${SECONDS} s"; cut -c1-1500 gpurun_out/r2_bench_c2.json; tail -2 gpurun_out/r2_bench_c2.err
 python bench.py --workload c4 --steps 5 --warmup 3 > gpurun_out/r2_bench_c4.json 2> gpurun_out/r2_bench_c4.err; cut -c1-600 gpurun_out/r2_bench_c4.json
+python bench.py --workload c3 --steps 5 --warmup 3 > gpurun_out/r2_bench_c3.json 2> gpurun_out/r2_bench_c3.err; cut -c1-400 gpurun_out/r2_bench_c3.json
+python bench.py --workload c3z --steps 5 --warmup 3 > gpurun_out/r2_bench_c3z.json 2> gpurun_out/r2_bench_c3z.err; cut -c1-400 gpurun_out/r2_bench_c3z.json
+python bench.py --workload c3z --impl reference --entries 8192 --steps 2 --warmup 1 > gpurun_out/r2_bench_c3z_reference.json 2>/dev/null
+python tools/pack_bench.py --entries 8192 --classes=-1,1,2,3,0 --reps 3 > gpurun_out/r2_pack_class_bench.jsonl 2>/dev/null; python tools/pack_bench.py --entries 8192 --classes=-1,1,2,3,0 --reps 3 --method 1 > gpurun_out/r2_zstd_pack_class_bench.jsonl 2>/dev/null; cat gpurun_out/r2_pack_class_bench.jsonl gpurun_out/r2_zstd_pack_class_bench.jsonl
 python bench.py --workload c5 --steps 5 --warmup 3 > gpurun_out/r2_bench_c5.json 2> gpurun_out/r2_bench_c5.err; cut -c1-600 gpurun_out/r2_bench_c5.json
 python tools/c1_cli.py > gpurun_out/r2_c1_cli.jsonl 2> gpurun_out/r2_c1_cli.err; cat gpurun_out/r2_c1_cli.jsonl
 python tools/class_bench.py --entries 14208 --groups 8 --classes 0,1,2,3,-1 --reps 3 > gpurun_out/r2_class_bench.jsonl 2> gpurun_out/class.err; cut -c1-300 gpurun_out/r2_class_bench.jsonl
