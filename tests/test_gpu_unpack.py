@@ -248,3 +248,23 @@ def test_pipelined_host_path_and_discard_flag(oracle, monkeypatch):
         assert (out2 == 0xEE).all()
     finally:
         ctx.close()
+
+
+def test_misaligned_output_slot_is_refused_not_a_fault(gpu_ctx, oracle):
+    """include/zpack_b200.h documents dst_off as 16-byte aligned (the kernels store 16 bytes at a time).  An odd slot on the
+    device path must come back as ZPB_E_ARG — and leave the context usable — instead of a sticky misaligned-address fault."""
+    import torch
+    import zpack_b200
+    bufs = [corpus.entry_bytes(i, 40000) for i in range(4)]
+    frames = [oracle.lz4f_encode_port(b, 0, independent=False) for b in bufs]
+    hashes = [oracle.xxh3_port(b) for b in bufs]
+    arch = container.assemble([f"f{i}" for i in range(4)], frames, [40000] * 4, hashes, [2] * 4)
+    e = container.parse(arch).entries()
+    d_arch = torch.from_numpy(arch).cuda()
+    d_out = torch.zeros(int((e["dst_off"] + e["dst_cap"]).max()) + 64, dtype=torch.uint8, device="cuda")
+    bad = e.copy()
+    bad["dst_off"][2] += 3
+    with pytest.raises(zpack_b200.lib.ZpbError, match="16-byte aligned"):
+        gpu_ctx.unpack_device(d_arch, len(arch), d_out, d_out.numel(), bad)
+    st, dg = gpu_ctx.unpack_device(d_arch, len(arch), d_out, d_out.numel(), e)     # the context is still good
+    assert (st == 0).all() and np.array_equal(dg, np.array(hashes, np.uint64))
