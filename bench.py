@@ -931,7 +931,7 @@ def run_c3(args):
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from one `ncu --set full` capture, as a ratio
 # to the algorithmic bytes of the captured launch (the capture runs fewer entries than the bench; the ratio carries over)
 NCU_TRAFFIC_RATIO = {
-    "c2": (6.3917 / (12297207239 * 28416 / 65536 / 1e9), "profiles/r1_ncu_full_exec_v4_mixed28416.csv: 2.688 + 3.704 GB for 28 416 entries"),
+    "c2": (7.0606 / (12297207239 * 28416 / 65536 / 1e9), "profiles/r2_ncu_full_exec_mixed28416.csv: 3.357 + 3.704 GB for 28 416 entries"),
 }
 
 

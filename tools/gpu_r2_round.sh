@@ -17,7 +17,7 @@ python tools/c1_cli.py > gpurun_out/r2_c1_cli.jsonl 2> gpurun_out/r2_c1_cli.err;
 python tools/class_bench.py --entries 14208 --groups 8 --classes 0,1,2,3,-1 --reps 3 > gpurun_out/r2_class_bench.jsonl 2> gpurun_out/class.err; cut -c1-300 gpurun_out/r2_class_bench.jsonl
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/r2_launches_bench_16384.csv \
     python bench.py --entries 16384 --steps 2 --warmup 1 --no-e2e --no-cpu --no-configs > gpurun_out/ncu_launch.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:lz4_fast_exec -s 2 -c 1 -o gpurun_out/r2_exec_mixed28416 \
+ZPB_OVERLAP=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lz4_fast_exec -s 1 -c 1 -o gpurun_out/r2_exec_mixed28416 \
     python bench.py --entries 28416 --steps 2 --warmup 1 --no-cpu --no-e2e --no-configs > gpurun_out/ncu_exec.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lz4_fast_parse4 -s 1 -c 1 -o gpurun_out/r2_parse4_8192 \
     python bench.py --entries 8192 --steps 2 --warmup 1 --no-cpu --no-e2e --no-configs > gpurun_out/ncu_parse.log 2>&1
