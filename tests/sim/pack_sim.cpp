@@ -27,7 +27,7 @@ extern "C" int sim_lz4_pack_blocks(const uint8_t *in, const uint64_t *src_off, c
 // Returns 1 when the block is encoded, 0 when it has to be stored raw.
 #include "../../zpack_b200/csrc/zstd_encode.cuh"
 extern "C" int sim_zstd_encode_block(const uint8_t *lz, uint32_t csize, uint32_t raw_len, const uint32_t *winop, uint8_t *bodies,
-                                     uint32_t *zbody, int use_huffman, uint32_t *modes) {
+                                     uint32_t *zbody, int use_huffman /* bit 0: Huffman literals, bit 1: fitted FSE tables */, uint32_t *modes) {
     static ZeTables T;
     static bool built = false;
     if (!built) { ze_build_tables(T); built = true; }
@@ -35,8 +35,8 @@ extern "C" int sim_zstd_encode_block(const uint8_t *lz, uint32_t csize, uint32_t
     std::vector<u8> zlit(ZE_LITSLOT + 64, 0);
     std::vector<u64> zseq(16 * ZE_WIN_SEQ);
     u32 lit_n[16] = {0}, seq_n[16] = {0};
-    std::vector<u32> hist(256, 0);
-    u32 total = 0;
+    std::vector<u32> hist(256, 0), hll(36, 0), hof(32, 0), hml(53, 0);
+    u32 total = 0, nseq_total = 0;
     for (u32 w = 0; w < nwin; ++w) {                                                            // stage A
         const u32 begin = winop[w], end = winop[w + 1], tail_end = w + 1 == nwin ? csize : end;
         if (!(begin <= end && tail_end <= csize && end <= tail_end)) return 0;
@@ -44,18 +44,32 @@ extern "C" int sim_zstd_encode_block(const uint8_t *lz, uint32_t csize, uint32_t
             return 0;
         for (u32 i = 0; i < lit_n[w]; ++i) ++hist[zlit[ZE_LOFF(begin, w) + i]];
         total += lit_n[w];
+        for (u32 i = 0; i < seq_n[w]; ++i) {
+            const u64 r = zseq[w * ZE_WIN_SEQ + i];
+            ++hll[ze_ll_code((u32)(r & 0xFFFF))]; ++hml[ze_ml_code((u32)((r >> 16) & 0xFFFF))]; ++hof[ze_highbit((u32)(r >> 32) + 3u)];
+        }
+        nseq_total += seq_n[w];
     }
     ZeHuf H;                                                                                    // stage B
     H.desc_len = 0;
-    if (use_huffman && total >= 256) ze_huf_build(hist.data(), H);
+    if ((use_huffman & 1) && total >= 256) ze_huf_build(hist.data(), H);
+    static ZeBlockTabs B;
+    B.valid = 0;
+    if ((use_huffman & 2) && nseq_total >= ZE_TABS_MIN) {
+        ze_fit(B.ll, B.desc[0], &B.desc_len[0], hll.data(), 36, nseq_total, 9);
+        ze_fit(B.of, B.desc[1], &B.desc_len[1], hof.data(), 32, nseq_total, 8);
+        ze_fit(B.ml, B.desc[2], &B.desc_len[2], hml.data(), 53, nseq_total, 9);
+        B.valid = 1;
+    }
     u32 sum = 0;
     for (u32 w = 0; w < 16; ++w) zbody[w] = 0;
     for (u32 w = 0; w < nwin; ++w) {                                                            // stage C
         const u32 begin = winop[w], end = winop[w + 1], tail_end = w + 1 == nwin ? csize : end;
         const u32 mode = ze_lit_mode(w, lit_n, nwin, H.desc_len != 0);
         if (modes) modes[w] = mode;
+        const u32 seqmode = ze_seq_mode(w, seq_n, nwin, B.valid != 0);
         const u32 z = ze_emit_range(zlit.data() + ZE_LOFF(begin, w), lit_n[w], zseq.data() + w * ZE_WIN_SEQ, seq_n[w], mode, H,
-                                    bodies + ZE_OFF(begin, w), (tail_end - begin) + ((tail_end - begin) >> 2) + 20u, T);
+                                    bodies + ZE_OFF(begin, w), (tail_end - begin) + ((tail_end - begin) >> 2) + 20u, T, seqmode, B);
         if (z == ZE_FAIL) return 0;
         zbody[w] = z;
         if (z) sum += z + 3;

@@ -126,7 +126,7 @@ def zstd_frame(bodies, blocks):
     return np.frombuffer(bytes(fr), np.uint8)
 
 
-@pytest.mark.parametrize("huffman", [0, 1])
+@pytest.mark.parametrize("huffman", [0, 1, 3])     # bit 0: Huffman literals, bit 1: FSE tables fitted to the block
 def test_zstd_blocks_from_the_lz4_matches_decode_with_the_oracle_and_the_reference(sim, oracle, huffman):
     """zstd_encode.cuh: every 4 KB window of the block compressor's LZ4 payload -> one zstd Compressed_Block (Huffman or
     raw literals + predefined-mode FSE sequences).  Frames must decode in the oracle's zstd port and in the UNMODIFIED
@@ -170,7 +170,7 @@ def test_zstd_blocks_from_the_lz4_matches_decode_with_the_oracle_and_the_referen
         lz_total += c if c else len(b)
         z_total += sum(len(x) + 3 for x in subs) if subs is not None else len(b)
     assert sum(x is not None for x in bodies) >= len(blocks) - 6          # the random blocks stay raw
-    assert used == ({0, 2, 3} if huffman else {0})
+    assert used == ({0, 2, 3} if huffman & 1 else {0})
     for k in range(len(blocks)):                       # one frame per block, and all of them in one frame
         fr = zstd_frame([bodies[k]], [blocks[k]])
         rc, got = oracle.zstd_decode_port(fr, len(blocks[k]))

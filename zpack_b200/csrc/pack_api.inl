@@ -90,7 +90,7 @@ static int pack_device_impl(zpb_ctx *ctx, const u8 *d_in, u64 in_size, u8 *d_out
         return fail(ctx, ZPB_E_NOMEM, "block scratch allocation failed");
     if (any_zstd && (!ctx->d_zslot.ensure(max_round * (u64)ZE_SLOT + 64) || !ctx->d_zseq.ensure(max_round * 16 * (u64)ZE_WIN_SEQ * sizeof(u64) + 64) ||
                      !ctx->d_zmeta.ensure(max_round * (17 + ZE_META) * sizeof(u32) + 64) || !ctx->d_zelit.ensure(max_round * (u64)ZE_LITSLOT + 64) ||
-                     !ctx->d_zhuf.ensure(max_round * sizeof(ZeHuf) + 64)))
+                     !ctx->d_zhuf.ensure(max_round * sizeof(ZeHuf) + 64) || !ctx->d_ztabs.ensure(max_round * sizeof(ZeBlockTabs) + 64)))
         return fail(ctx, ZPB_E_NOMEM, "zstd block scratch allocation failed");
     u32 *d_winop = any_zstd ? (u32 *)ctx->d_zmeta.p : nullptr;
     u32 *d_zbody = any_zstd ? d_winop + max_round * 17 : nullptr;      // ZE_META words per block, the body sizes first
@@ -127,9 +127,11 @@ static int pack_device_impl(zpb_ctx *ctx, const u8 *d_in, u64 in_size, u8 *d_out
             zstd_parse_windows_kernel<<<zgrid, 128, 0, s>>>((const u8 *)ctx->d_pscratch.p, (const u32 *)ctx->d_csize.p, zb, d_winop, (u32)rb,
                                                             d_zbody, (u8 *)ctx->d_zelit.p, (u64 *)ctx->d_zseq.p);
             zstd_huf_tables_kernel<<<(u32)std::min<u64>((rb + 3) / 4, (u64)ctx->sm_count * 8), 128, 0, s>>>(
-                zb, (const u32 *)ctx->d_csize.p, d_winop, (u32)rb, d_zbody, (const u8 *)ctx->d_zelit.p, (ZeHuf *)ctx->d_zhuf.p);
+                zb, (const u32 *)ctx->d_csize.p, d_winop, (u32)rb, d_zbody, (const u8 *)ctx->d_zelit.p, (const u64 *)ctx->d_zseq.p, (ZeHuf *)ctx->d_zhuf.p,
+                (ZeBlockTabs *)ctx->d_ztabs.p);
             zstd_encode_windows_kernel<<<zgrid, 128, 0, s>>>((const u32 *)ctx->d_csize.p, zb, d_winop, (u32)rb, d_zbody, (const u8 *)ctx->d_zelit.p,
-                                                             (const u64 *)ctx->d_zseq.p, (const ZeHuf *)ctx->d_zhuf.p, (u8 *)ctx->d_zslot.p);
+                                                             (const u64 *)ctx->d_zseq.p, (const ZeHuf *)ctx->d_zhuf.p, (const ZeBlockTabs *)ctx->d_ztabs.p,
+                                                             (u8 *)ctx->d_zslot.p);
             ctx->launches += 2;
             CK(ctx, cudaGetLastError());
             ctx->launches += 1;

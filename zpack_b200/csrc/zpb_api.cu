@@ -81,7 +81,7 @@ struct zpb_ctx {
     PinBuf h_bounce;           // pack: landing zone of the one D2H per chunk
     DevBuf d_pblk, d_pscratch, d_csize;    // pack: block list, one 64 KB payload slot per block of a round, block sizes
     DevBuf d_zslot, d_zseq, d_zmeta;       // pack, zstd files: block bodies, sequence records, window offsets + per-window words of a round
-    DevBuf d_zelit, d_zhuf;                // ... staged literals, one Huffman code per block
+    DevBuf d_zelit, d_zhuf, d_ztabs;       // ... staged literals, one Huffman code and one set of FSE tables per block
     u64 pack_scratch_blocks = 16384;       // slots per round (ZPB_PACK_SCRATCH_MB, default 1 GiB)
     int p2_per_sm = 1, pk_per_sm = 1;      // resident CTAs of the two pack kernels
     std::vector<cudaEvent_t> pack_evs;     // three per round: before the block compressor, between, after the framing kernel
@@ -206,7 +206,7 @@ extern "C" void zpb_destroy(zpb_ctx *ctx) {
     ctx->d_glist.release(); ctx->d_fdesc.release(); ctx->d_zlist.release(); ctx->d_zlit.release();
     ctx->d_gather.release(); ctx->d_goff.release(); ctx->h_bounce.release();
     ctx->d_pblk.release(); ctx->d_pscratch.release(); ctx->d_csize.release();
-    ctx->d_zslot.release(); ctx->d_zseq.release(); ctx->d_zmeta.release(); ctx->d_zelit.release(); ctx->d_zhuf.release();
+    ctx->d_zslot.release(); ctx->d_zseq.release(); ctx->d_zmeta.release(); ctx->d_zelit.release(); ctx->d_zhuf.release(); ctx->d_ztabs.release();
     for (cudaEvent_t e : ctx->pack_evs) cudaEventDestroy(e);
     ctx->d_partials.release(); ctx->d_acc.release();
     for (auto &ev : ctx->evs) if (ev) cudaEventDestroy(ev);

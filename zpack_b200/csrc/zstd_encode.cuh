@@ -10,10 +10,11 @@
 //     literals (lengths limited to 11 bits, direct 4-bit weight description); the block's first window with enough
 //     literals carries the tree (Compressed_Literals_Block), the later ones reuse it (Treeless_Literals_Block).  Blocks
 //     whose literals use byte values above 128, short sections and sections that would not shrink stay Raw_Literals.
-//   * sequences: Predefined_Mode — the three default FSE distributions, encoded backwards exactly as
-//     ZSTD_encodeSequences does (states initialised from the last sequence, extra bits LL / ML / OF, per earlier sequence
-//     the OF, ML, LL state transitions, final states ML, OF, LL, end mark).  No repeat-offset codes (offset value =
-//     offset + 3 always).
+//   * sequences: encoded backwards exactly as ZSTD_encodeSequences does (states initialised from the last sequence, extra
+//     bits LL / ML / OF, per earlier sequence the OF, ML, LL state transitions, final states ML, OF, LL, end mark), with
+//     FSE tables fitted to the block's own LL / OF / ML codes: the block's first window with sequences describes them
+//     (FSE_Compressed_Mode, or RLE_Mode for a single code), later windows use Repeat_Mode; small blocks keep the
+//     predefined tables.  No repeat-offset codes (offset value = offset + 3 always).
 // The ratio is reported next to ZSTD_compress level 3 by the tests and the bench.  A block that does not shrink stays a
 // Raw_Block.
 #pragma once
@@ -41,12 +42,25 @@ ZE_CONST u32 ZE_ML_BASE[53] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 
 ZE_CONST u8 ZE_ML_BITS[53] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
                               0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
 
-// FSE compression tables of the three predefined distributions (FSE_buildCTable_wksp, fse_compress.c:68-180):
-// next-state table + per symbol (deltaNbBits, deltaFindState).  Built once per CTA into shared memory.
-struct ZeTables {
-    u16 st_ll[64], st_of[32], st_ml[64];
-    u32 dnb_ll[36], dnb_of[29], dnb_ml[53];
-    int dfs_ll[36], dfs_of[29], dfs_ml[53];
+// One FSE compression table (FSE_buildCTable_wksp, fse_compress.c:68-180): next-state table + per symbol (deltaNbBits,
+// deltaFindState), for a table log up to 9; or an RLE "table" (one symbol, no state bits).
+struct ZeSeqTab {
+    u16 st[512];
+    u32 dnb[53];
+    int dfs[53];
+    u32 log;        // state bits (0 for RLE)
+    u32 rle;        // 1: RLE_Mode, `sym` is the only symbol
+    u32 sym;
+};
+// The three predefined distributions, built once per CTA into shared memory.
+struct ZeTables { ZeSeqTab ll, of, ml; };
+// One set per 64 KB block (global memory): tables fitted to the block's own sequence codes + their descriptions
+// (FSE_writeNCount, or the single byte of RLE_Mode), written by the block's first window that has sequences.
+struct ZeBlockTabs {
+    ZeSeqTab ll, of, ml;
+    u8 desc[3][64];
+    u32 desc_len[3];
+    u32 valid;      // 0: the block's sequences use the predefined tables
 };
 
 #ifdef ZPB_SIM
@@ -55,11 +69,12 @@ ZPB_DEVINL int ze_highbit(u32 v) { int r = 0; while (v >>= 1) ++r; return r; }
 ZPB_DEVINL int ze_highbit(u32 v) { return 31 - __clz((int)v); }
 #endif
 
-ZPB_DEVINL void ze_build(u16 *st, u32 *dnb, int *dfs, const short *norm, int nsym, int log) {
+ZPB_DEVINL void ze_build(ZeSeqTab &T, const short *norm, int nsym, int log) {
     const int size = 1 << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
-    u8 sym_of[64];
+    u8 sym_of[512];
     int cumul[54];
     int high = size - 1;
+    T.log = (u32)log; T.rle = 0; T.sym = 0;
     cumul[0] = 0;
     for (int s = 0; s < nsym; ++s) {
         if (norm[s] == -1) { cumul[s + 1] = cumul[s] + 1; sym_of[high--] = (u8)s; }
@@ -71,24 +86,106 @@ ZPB_DEVINL void ze_build(u16 *st, u32 *dnb, int *dfs, const short *norm, int nsy
             sym_of[pos] = (u8)s;
             do pos = (pos + step) & mask; while (pos > high);
         }
-    for (int u = 0; u < size; ++u) { const int s = sym_of[u]; st[cumul[s]++] = (u16)(size + u); }
+    for (int u = 0; u < size; ++u) { const int s = sym_of[u]; T.st[cumul[s]++] = (u16)(size + u); }
     int total = 0;
     for (int s = 0; s < nsym; ++s) {
         const int n = norm[s];
-        if (n == 0) { dnb[s] = (u32)(((log + 1) << 16) - size); dfs[s] = 0; }
-        else if (n == -1 || n == 1) { dnb[s] = (u32)((log << 16) - size); dfs[s] = total - 1; ++total; }
+        if (n == 0) { T.dnb[s] = (u32)(((log + 1) << 16) - size); T.dfs[s] = 0; }
+        else if (n == -1 || n == 1) { T.dnb[s] = (u32)((log << 16) - size); T.dfs[s] = total - 1; ++total; }
         else {
             const int mb = log - ze_highbit((u32)(n - 1));
-            dnb[s] = (u32)((mb << 16) - (n << mb));
-            dfs[s] = total - n;
+            T.dnb[s] = (u32)((mb << 16) - (n << mb));
+            T.dfs[s] = total - n;
             total += n;
         }
     }
 }
 ZPB_DEVINL void ze_build_tables(ZeTables &T) {
-    ze_build(T.st_ll, T.dnb_ll, T.dfs_ll, ZE_LL_NORM, 36, 6);
-    ze_build(T.st_of, T.dnb_of, T.dfs_of, ZE_OF_NORM, 29, 5);
-    ze_build(T.st_ml, T.dnb_ml, T.dfs_ml, ZE_ML_NORM, 53, 6);
+    ze_build(T.ll, ZE_LL_NORM, 36, 6);
+    ze_build(T.of, ZE_OF_NORM, 29, 5);
+    ze_build(T.ml, ZE_ML_NORM, 53, 6);
+}
+
+// Normalised counts for a histogram (the role of FSE_normalizeCount, fse_compress.c:430-490; any distribution that sums to
+// the table size and gives every present symbol at least 1 is valid): proportional shares, the rounding error settled
+// on the largest shares.  Returns the table log, or 0 when only one symbol occurs (RLE_Mode; *only = that symbol).
+ZPB_DEVINL int ze_normalize(const u32 *cnt, int nsym, u32 total, int maxlog, short *norm, int *last, int *only) {
+    int present = 0, lastsym = 0;
+    for (int s = 0; s < nsym; ++s) if (cnt[s]) { ++present; lastsym = s; }
+    *last = lastsym;
+    *only = lastsym;
+    if (present <= 1) return 0;
+    int log = ze_highbit(total) - 2;
+    if (log < 5) log = 5;
+    if (log > maxlog) log = maxlog;
+    while ((1 << log) < present) ++log;
+    const int size = 1 << log;
+    int sum = 0, big = 0;
+    for (int s = 0; s < nsym; ++s) {
+        int v = 0;
+        if (cnt[s]) {
+            v = (int)(((u64)cnt[s] * (u32)size + total / 2) / total);
+            if (v < 1) v = 1;
+        }
+        norm[s] = (short)v;
+        sum += v;
+        if (v > norm[big]) big = s;
+    }
+    if (sum < size) norm[big] = (short)(norm[big] + (size - sum));
+    while (sum > size) {                               // take the excess from the largest shares, one at a time
+        int b = 0;
+        for (int s = 1; s < nsym; ++s) if (norm[s] > norm[b]) b = s;
+        --norm[b];
+        --sum;
+    }
+    return log;
+}
+// table description (FSE_writeNCount_generic, fse_compress.c:290-400; read back by FSE_readNCount): returns bytes
+ZPB_DEVINL u32 ze_write_ncount(u8 *out, const short *norm, int last, int log) {
+    u64 acc = 0;
+    u32 n = 0, op = 0;
+    const int size = 1 << log;
+    int remaining = size + 1, threshold = size, nbits = log + 1, sym = 0;
+    bool prev0 = false;
+    acc |= (u64)(log - 5) << n; n += 4;
+    while (sym <= last && remaining > 1) {
+        if (prev0) {
+            int start = sym;
+            while (sym <= last && norm[sym] == 0) ++sym;
+            int run = sym - start;
+            while (run >= 3) {
+                acc |= (u64)3 << n; n += 2; run -= 3;
+                if (n >= 32) { for (int k = 0; k < 4; ++k) out[op++] = (u8)(acc >> (8 * k)); acc >>= 32; n -= 32; }
+            }
+            acc |= (u64)run << n; n += 2;
+        }
+        int count = norm[sym++];
+        const int max = (2 * threshold - 1) - remaining;
+        remaining -= count < 0 ? -count : count;
+        ++count;
+        if (count >= threshold) count += max;
+        acc |= (u64)count << n;
+        n += (u32)(count < max ? nbits - 1 : nbits);
+        prev0 = count == 1;
+        while (remaining < threshold) { --nbits; threshold >>= 1; }
+        if (n >= 32) { for (int k = 0; k < 4; ++k) out[op++] = (u8)(acc >> (8 * k)); acc >>= 32; n -= 32; }
+    }
+    while (n > 0) { out[op++] = (u8)acc; acc >>= 8; n = n > 8 ? n - 8 : 0; }
+    return op;
+}
+// one table fitted to a histogram of codes: RLE or FSE + its description
+ZPB_DEVINL void ze_fit(ZeSeqTab &T, u8 *desc, u32 *desc_len, const u32 *cnt, int nsym, u32 total, int maxlog) {
+    short norm[53];
+    int last = 0, only = 0;
+    const int log = ze_normalize(cnt, nsym, total, maxlog, norm, &last, &only);
+    if (log == 0) {
+        T.log = 0; T.rle = 1; T.sym = (u32)only;
+        desc[0] = (u8)only;
+        *desc_len = 1;
+        return;
+    }
+    ze_build(T, norm, last + 1, log);
+    *desc_len = ze_write_ncount(desc, norm, last, log);
 }
 
 // codes (zstd_compress_internal.h: ZSTD_LLcode / ZSTD_MLcode, written as searches over the base tables)
@@ -158,15 +255,17 @@ ZPB_DEVINL u32 ze_in_byte(ZeIn &r) {
     else r.w >>= 8;
     return v;
 }
-ZPB_DEVINL u32 ze_init_state(const u16 *st, const u32 *dnb, const int *dfs, u32 sym) {      // FSE_initCState2
-    const u32 nbo = (dnb[sym] + (1u << 15)) >> 16;
-    const u32 value = (nbo << 16) - dnb[sym];
-    return st[(int)(value >> nbo) + dfs[sym]];
+ZPB_DEVINL u32 ze_init_state(const ZeSeqTab &T, u32 sym) {      // FSE_initCState2
+    if (T.rle) return 0;
+    const u32 nbo = (T.dnb[sym] + (1u << 15)) >> 16;
+    const u32 value = (nbo << 16) - T.dnb[sym];
+    return T.st[(int)(value >> nbo) + T.dfs[sym]];
 }
-ZPB_DEVINL u32 ze_encode(ZeBits &b, const u16 *st, const u32 *dnb, const int *dfs, u32 state, u32 sym) {   // FSE_encodeSymbol
-    const u32 nbo = (state + dnb[sym]) >> 16;
+ZPB_DEVINL u32 ze_encode(ZeBits &b, const ZeSeqTab &T, u32 state, u32 sym) {   // FSE_encodeSymbol
+    if (T.rle) return 0;
+    const u32 nbo = (state + T.dnb[sym]) >> 16;
     ze_add(b, state & ((1u << nbo) - 1u), nbo);
-    return st[(int)(state >> nbo) + dfs[sym]];
+    return T.st[(int)(state >> nbo) + T.dfs[sym]];
 }
 
 #define ZE_FAIL 0xFFFFFFFFu
@@ -323,6 +422,15 @@ ZPB_DEVINL u32 ze_lit_mode(u32 w, const u32 *lit_n, u32 nwin, bool have_table) {
     return 2;
 }
 
+// which sequence tables window w uses: 0 predefined, 2 the block's own tables, which this window also describes (it is the
+// block's first window with sequences), 3 the block's own tables, already described (Repeat_Mode)
+ZPB_DEVINL u32 ze_seq_mode(u32 w, const u32 *seq_n, u32 nwin, bool have_tabs) {
+    if (!have_tabs || seq_n[w] == 0) return 0;
+    for (u32 k = 0; k < w && k < nwin; ++k) if (seq_n[k]) return 3;
+    return 2;
+}
+#define ZE_TABS_MIN 64u        // blocks with fewer sequences keep the predefined tables
+
 // one Huffman stream: symbols lit[0, n) coded last to first (huf_compress.c:HUF_compress1X_usingCTable), end mark; returns bytes
 ZPB_DEVINL u32 ze_huf_stream(const u8 *lit, u32 n, u8 *at, u8 *end, const ZeHuf &H, bool *ovf) {
     ZeBits b;
@@ -341,8 +449,10 @@ ZPB_DEVINL u32 ze_huf_stream(const u8 *lit, u32 n, u8 *at, u8 *end, const ZeHuf 
 // ---- stage C: one window's sub-block body at `out`: literals section (raw, or Huffman-coded in four streams with the
 // block's table), sequences section.  Returns the body size; 0 when the window has nothing to emit; ZE_FAIL when it does
 // not fit `cap` (the caller then stores the whole block raw).
+// seqmode: 0 predefined tables (T), 2 this window carries the block's own tables (B: descriptions written, FSE_Compressed /
+// RLE modes), 3 it reuses them (Repeat_Mode).
 ZPB_DEVINL u32 ze_emit_range(const u8 *lit, u32 lit_n, const u64 *seq, u32 nseq, u32 mode, const ZeHuf &H, u8 *out, u32 cap,
-                             const ZeTables &T) {
+                             const ZeTables &T, u32 seqmode, const ZeBlockTabs &B) {
     if (lit_n == 0 && nseq == 0) return 0;
     if (cap < 24) return ZE_FAIL;
     u32 op = 0;
@@ -393,7 +503,13 @@ ZPB_DEVINL u32 ze_emit_range(const u8 *lit, u32 lit_n, const u64 *seq, u32 nseq,
     if (nseq < 128) out[op++] = (u8)nseq;
     else if (nseq < 0x7F00) { out[op++] = (u8)((nseq >> 8) + 0x80); out[op++] = (u8)nseq; }
     else { out[op++] = 0xFF; out[op++] = (u8)(nseq - 0x7F00); out[op++] = (u8)((nseq - 0x7F00) >> 8); }
-    out[op++] = 0;
+    const ZeSeqTab &TL = seqmode ? B.ll : T.ll, &TO = seqmode ? B.of : T.of, &TM = seqmode ? B.ml : T.ml;
+    if (seqmode == 2) {
+        out[op++] = (u8)(((TL.rle ? 1u : 2u) << 6) | ((TO.rle ? 1u : 2u) << 4) | ((TM.rle ? 1u : 2u) << 2));
+        if (op + B.desc_len[0] + B.desc_len[1] + B.desc_len[2] + 8 >= cap) return ZE_FAIL;
+        for (u32 k = 0; k < 3; ++k)                  // LL, OF, ML (zstd_compression_format.md: Sequences_Section_Header)
+            for (u32 i = 0; i < B.desc_len[k]; ++i) out[op++] = B.desc[k][i];
+    } else out[op++] = seqmode == 3 ? 0xFCu : 0u;
     // ---- the bitstream, from the last sequence to the first (zstd_compress_sequences.c:ZSTD_encodeSequences_body)
     ZeBits b;
     ze_open(b, out + op, out + cap, true);
@@ -402,9 +518,9 @@ ZPB_DEVINL u32 ze_emit_range(const u8 *lit, u32 lit_n, const u64 *seq, u32 nseq,
         const u64 r = seq[nseq - 1];
         const u32 ll = (u32)(r & 0xFFFF), ml = (u32)((r >> 16) & 0xFFFF), ob = (u32)(r >> 32) + 3u;
         const u32 cl = ze_ll_code(ll), cm = ze_ml_code(ml), co = (u32)ze_highbit(ob);
-        st_ml = ze_init_state(T.st_ml, T.dnb_ml, T.dfs_ml, cm);
-        st_of = ze_init_state(T.st_of, T.dnb_of, T.dfs_of, co);
-        st_ll = ze_init_state(T.st_ll, T.dnb_ll, T.dfs_ll, cl);
+        st_ml = ze_init_state(TM, cm);
+        st_of = ze_init_state(TO, co);
+        st_ll = ze_init_state(TL, cl);
         ze_add(b, ll - ZE_LL_BASE[cl], ZE_LL_BITS[cl]);
         ze_add(b, ml - ZE_ML_BASE[cm], ZE_ML_BITS[cm]);
         ze_flush(b);
@@ -417,9 +533,9 @@ ZPB_DEVINL u32 ze_emit_range(const u8 *lit, u32 lit_n, const u64 *seq, u32 nseq,
         if (k) r_next = seq[k - 1];                  // the record after this one is on its way while this one is encoded
         const u32 ll = (u32)(r & 0xFFFF), ml = (u32)((r >> 16) & 0xFFFF), ob = (u32)(r >> 32) + 3u;
         const u32 cl = ze_ll_code(ll), cm = ze_ml_code(ml), co = (u32)ze_highbit(ob);
-        st_of = ze_encode(b, T.st_of, T.dnb_of, T.dfs_of, st_of, co);
-        st_ml = ze_encode(b, T.st_ml, T.dnb_ml, T.dfs_ml, st_ml, cm);
-        st_ll = ze_encode(b, T.st_ll, T.dnb_ll, T.dfs_ll, st_ll, cl);
+        st_of = ze_encode(b, TO, st_of, co);
+        st_ml = ze_encode(b, TM, st_ml, cm);
+        st_ll = ze_encode(b, TL, st_ll, cl);
         ze_flush(b);
         ze_add(b, ll - ZE_LL_BASE[cl], ZE_LL_BITS[cl]);
         ze_add(b, ml - ZE_ML_BASE[cm], ZE_ML_BITS[cm]);
@@ -427,9 +543,11 @@ ZPB_DEVINL u32 ze_emit_range(const u8 *lit, u32 lit_n, const u64 *seq, u32 nseq,
         ze_add(b, ob - (1u << co), co);
         ze_flush(b);
     }
-    ze_add(b, st_ml & 63u, 6);                       // FSE_flushCState: ML, OF, LL
-    ze_add(b, st_of & 31u, 5);
-    ze_add(b, st_ll & 63u, 6);
+    ze_add(b, st_ml & ((1u << TM.log) - 1u), TM.log);     // FSE_flushCState: ML, OF, LL
+    ze_flush(b);
+    ze_add(b, st_of & ((1u << TO.log) - 1u), TO.log);
+    ze_add(b, st_ll & ((1u << TL.log) - 1u), TL.log);
+    ze_flush(b);
     ze_add(b, 1u, 1);                                // BIT_closeCStream: the end mark
     ze_flush_all(b);
     if (b.ovf) return ZE_FAIL;
@@ -474,18 +592,21 @@ zstd_parse_windows_kernel(const u8 *__restrict__ lz_slots, const u32 *__restrict
     }
 }
 
-// B: one warp per block: histogram of the block's staged literals in shared memory, lane 0 builds the Huffman code.
+// B: one warp per block: histograms of the block's staged literals and of its sequence codes in shared memory; lane 0
+// builds the Huffman code and the three FSE tables.
 __global__ void __launch_bounds__(128)
 zstd_huf_tables_kernel(const PackBlock *__restrict__ blocks, const u32 *__restrict__ csize, const u32 *__restrict__ winop, u32 nblocks,
-                       const u32 *__restrict__ meta, const u8 *__restrict__ zlit, ZeHuf *hufs) {
-    __shared__ u32 hist_all[4][256];
+                       const u32 *__restrict__ meta, const u8 *__restrict__ zlit, const u64 *__restrict__ zseq, ZeHuf *hufs,
+                       ZeBlockTabs *tabs) {
+    __shared__ u32 hist_all[4][256 + 128];
     const u32 lane = threadIdx.x & 31u, wp = threadIdx.x >> 5;
     u32 *hist = hist_all[wp];
+    u32 *hll = hist + 256, *hof = hist + 256 + 36, *hml = hist + 256 + 36 + 32;      // 36 + 32 + 53 code counters
     for (u32 b = blockIdx.x * 4u + wp; b < nblocks; b += gridDim.x * 4u) {
         const u32 *m = meta + (u64)b * ZE_META;
-        for (u32 i = lane; i < 256; i += 32) hist[i] = 0;
+        for (u32 i = lane; i < 256 + 128; i += 32) hist[i] = 0;
         __syncwarp();
-        u32 total = 0;
+        u32 total = 0, nseq = 0;
         bool ok = blocks[b].pad && csize[b];
         if (ok) {
             const u32 nwin = (blocks[b].len - 12u) / 4096u + 1u;
@@ -495,10 +616,29 @@ zstd_huf_tables_kernel(const PackBlock *__restrict__ blocks, const u32 *__restri
                 const u8 *p = zlit + (u64)b * ZE_LITSLOT + ZE_LOFF(winop[(u64)b * 17u + w], w);
                 for (u32 i = lane; i < n; i += 32) atomicAdd(&hist[p[i]], 1u);
                 total += n;
+                const u32 ns = m[32u + w];
+                const u64 *q = zseq + ((u64)b * 16u + w) * ZE_WIN_SEQ;
+                for (u32 i = lane; i < ns; i += 32) {
+                    const u64 r = q[i];
+                    atomicAdd(&hll[ze_ll_code((u32)(r & 0xFFFF))], 1u);
+                    atomicAdd(&hml[ze_ml_code((u32)((r >> 16) & 0xFFFF))], 1u);
+                    atomicAdd(&hof[ze_highbit((u32)(r >> 32) + 3u)], 1u);
+                }
+                nseq += ns;
             }
         }
         __syncwarp();
-        if (lane == 0) {
+        // four serial builds on four lanes: the three FSE fits run in lockstep, the Huffman code next to them
+        const bool fit = ok && nseq >= ZE_TABS_MIN;
+        if (lane < 3) {
+            ZeBlockTabs &B = tabs[b];
+            if (fit) {
+                ZeSeqTab &T = lane == 0 ? B.ll : (lane == 1 ? B.of : B.ml);
+                ze_fit(T, B.desc[lane], &B.desc_len[lane], lane == 0 ? hll : (lane == 1 ? hof : hml), lane == 0 ? 36 : (lane == 1 ? 32 : 53),
+                       nseq, lane == 1 ? 8 : 9);
+            }
+            if (lane == 0) B.valid = fit ? 1u : 0u;
+        } else if (lane == 3) {
             if (ok && total >= 256u) ze_huf_build(hist, hufs[b]);
             else hufs[b].desc_len = 0;
         }
@@ -510,7 +650,8 @@ zstd_huf_tables_kernel(const PackBlock *__restrict__ blocks, const u32 *__restri
 // block is stored raw).
 __global__ void __launch_bounds__(128)
 zstd_encode_windows_kernel(const u32 *__restrict__ csize, const PackBlock *__restrict__ blocks, const u32 *__restrict__ winop, u32 nblocks,
-                           u32 *meta, const u8 *__restrict__ zlit, const u64 *__restrict__ zseq, const ZeHuf *__restrict__ hufs, u8 *zslot) {
+                           u32 *meta, const u8 *__restrict__ zlit, const u64 *__restrict__ zseq, const ZeHuf *__restrict__ hufs,
+                           const ZeBlockTabs *__restrict__ tabs, u8 *zslot) {
     __shared__ ZeTables T;
     if (threadIdx.x == 0) ze_build_tables(T);
     __syncthreads();
@@ -528,9 +669,12 @@ zstd_encode_windows_kernel(const u32 *__restrict__ csize, const PackBlock *__res
                 if (seq_n == ZE_FAIL) z = ZE_FAIL;
                 else {
                     const ZeHuf &H = hufs[b];
+                    const ZeBlockTabs &B = tabs[b];
                     const u32 mode = ze_lit_mode(w, m + 16u, nwin, H.desc_len != 0);
+                    const u32 seqmode = ze_seq_mode(w, m + 32u, nwin, B.valid != 0);
                     z = ze_emit_range(zlit + (u64)b * ZE_LITSLOT + ZE_LOFF(begin, w), m[16u + w], zseq + t * ZE_WIN_SEQ, seq_n, mode, H,
-                                      zslot + (u64)b * ZE_SLOT + ZE_OFF(begin, w), (tail_end - begin) + ((tail_end - begin) >> 2) + 20u, T);
+                                      zslot + (u64)b * ZE_SLOT + ZE_OFF(begin, w), (tail_end - begin) + ((tail_end - begin) >> 2) + 20u, T,
+                                      seqmode, B);
                 }
             }
         } else if (w == 0) z = ZE_FAIL;
