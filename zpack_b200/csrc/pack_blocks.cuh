@@ -282,34 +282,49 @@ lz4_pack_blocks_body(const u8 *__restrict__ in, const PackBlock *__restrict__ bl
             bool has = false;
             const u32 mlim = s1 < matchlimit ? s1 : matchlimit;
             const bool any = __any_sync(0xffffffffu, nmatch != 0);
-            while (any && p < s1 && p <= mflimit) {
-                const u32 d = P2_U16(stg + 2u * (p - s0));
-                if (d == 0 || p + 4u > mlim) { ++p; continue; }
-                u32 len = 4;
-                for (;;) {
-                    if (p + len + 4u > mlim) {
-                        while (p + len < mlim && sm[D + p + len] == sm[D + p + len - d]) ++len;
-                        break;
+            // Every loop below has ONE exit, so the 32 lanes — each on its own sub-chunk — come back together after each of
+            // them: an iteration of the outer loop costs the longest skip + the longest extension + the longest literal
+            // run among the lanes, not their sum.
+            bool live = any;
+            while (live) {
+                // (a) on to the next position that has a candidate
+                u32 d = 0;
+                bool found = false;
+                while (!found && p < s1 && p <= mflimit) {
+                    d = P2_U16(stg + 2u * (p - s0));
+                    found = d != 0 && p + 4u <= mlim;
+                    if (!found) ++p;
+                }
+                live = found;
+                if (live) {
+                    // (b) extend forwards, four bytes at a time, then byte-wise up to the limit
+                    u32 len = 4;
+                    bool go = true, tail = false;
+                    while (go) {
+                        if (p + len + 4u > mlim) { go = false; tail = true; }
+                        else {
+                            const u32 x = p2_load32(sm, D + p + len) ^ p2_load32(sm, D + p + len - d);
+                            if (x) { len += (u32)(__ffs(x) - 1) >> 3; go = false; }
+                            else len += 4u;
+                        }
                     }
-                    const u32 x = p2_load32(sm, D + p + len) ^ p2_load32(sm, D + p + len - d);
-                    if (x) { len += (u32)(__ffs(x) - 1) >> 3; break; }
-                    len += 4u;
+                    while (tail && p + len < mlim && sm[D + p + len] == sm[D + p + len - d]) ++len;
+                    while (p > la && p > d && sm[D + p - 1] == sm[D + p - 1 - d]) { --p; ++len; }   // catch up (lz4.c:1051-1054), within the sub-chunk
+                    if (!has) { has = true; f_pos = p; f_off = d; f_len = len; }
+                    else if (p + len == s1) { l_pos = p; l_off = d; l_len = len; l_ls = la; }   // may go on in the next sub-chunk
+                    else {
+                        // staged over this lane's distances: the bytes written stay behind the next index read (a sequence
+                        // of lit + len input bytes takes at most lit + 5, and advances the reads by 2 * (lit + len))
+                        const u32 lit = p - la, mlc = len - 4u;
+                        sm[stg + so++] = (u8)(((lit < 15u ? lit : 15u) << 4) | (mlc < 15u ? mlc : 15u));
+                        if (lit >= 15u) sm[stg + so++] = (u8)(lit - 15u);         // lit < 128: one extension byte
+                        for (u32 i = 0; i < lit; ++i) sm[stg + so++] = sm[D + la + i];
+                        sm[stg + so++] = (u8)d; sm[stg + so++] = (u8)(d >> 8);
+                        if (mlc >= 15u) sm[stg + so++] = (u8)(mlc - 15u);         // len <= 128: one extension byte
+                    }
+                    p += len;
+                    la = p;
                 }
-                while (p > la && p > d && sm[D + p - 1] == sm[D + p - 1 - d]) { --p; ++len; }   // catch up (lz4.c:1051-1054), within the sub-chunk
-                if (!has) { has = true; f_pos = p; f_off = d; f_len = len; }
-                else if (p + len == s1) { l_pos = p; l_off = d; l_len = len; l_ls = la; }   // may go on in the next sub-chunk
-                else {
-                    // staged over this lane's distances: the bytes written stay behind the next index read (a sequence
-                    // of lit + len input bytes takes at most lit + 5, and advances the reads by 2 * (lit + len))
-                    const u32 lit = p - la, mlc = len - 4u;
-                    sm[stg + so++] = (u8)(((lit < 15u ? lit : 15u) << 4) | (mlc < 15u ? mlc : 15u));
-                    if (lit >= 15u) sm[stg + so++] = (u8)(lit - 15u);         // lit < 128: one extension byte
-                    for (u32 i = 0; i < lit; ++i) sm[stg + so++] = sm[D + la + i];
-                    sm[stg + so++] = (u8)d; sm[stg + so++] = (u8)(d >> 8);
-                    if (mlc >= 15u) sm[stg + so++] = (u8)(mlc - 15u);         // len <= 128: one extension byte
-                }
-                p += len;
-                la = p;
             }
             __syncwarp();
             // ---- (3) join.  What the window emits is counted first (its first literal run taken as empty); the output
