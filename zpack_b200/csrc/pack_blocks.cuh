@@ -318,7 +318,13 @@ lz4_pack_blocks_body(const u8 *__restrict__ in, const PackBlock *__restrict__ bl
                         const u32 lit = p - la, mlc = len - 4u;
                         sm[stg + so++] = (u8)(((lit < 15u ? lit : 15u) << 4) | (mlc < 15u ? mlc : 15u));
                         if (lit >= 15u) sm[stg + so++] = (u8)(lit - 15u);         // lit < 128: one extension byte
-                        for (u32 i = 0; i < lit; ++i) sm[stg + so++] = sm[D + la + i];
+                        u32 i = 0;
+                        for (; i + 4u <= lit; i += 4u) {                              // four literals per unaligned word load
+                            const u32 x = p2_load32(sm, D + la + i);
+                            sm[stg + so] = (u8)x; sm[stg + so + 1u] = (u8)(x >> 8); sm[stg + so + 2u] = (u8)(x >> 16); sm[stg + so + 3u] = (u8)(x >> 24);
+                            so += 4u;
+                        }
+                        for (; i < lit; ++i) sm[stg + so++] = sm[D + la + i];
                         sm[stg + so++] = (u8)d; sm[stg + so++] = (u8)(d >> 8);
                         if (mlc >= 15u) sm[stg + so++] = (u8)(mlc - 15u);         // len <= 128: one extension byte
                     }
