@@ -244,8 +244,11 @@ lz4_pack_blocks_body(const u8 *__restrict__ in, const PackBlock *__restrict__ bl
             }
             __syncwarp();
             if (lane == 0) { __threadfence_block(); ctl[2] = w + 1u; }
-            // ---- (1c) verify: candidate -> match distance (0 = none)
+            // ---- (1c) verify: candidate -> match distance (0 = none).  The four ballots of one round are the "has a match" bits of
+            // the 128 positions of ONE sub-chunk: the lane that will walk it keeps them (mk), and skips from match to match
+            // with a find-first-set instead of reading distance after distance.
             u32 nmatch = 0;
+            u32 mk[4] = {0u, 0u, 0u, 0u};
             for (u32 s = 0; s < P2_WIN; s += 128) {
                 const u32 e = dso + 2u * (s + 2u * (s >> 7) + lane);
                 u32 c[4], x[4], y[4];
@@ -267,8 +270,11 @@ lz4_pack_blocks_body(const u8 *__restrict__ in, const PackBlock *__restrict__ bl
                 for (u32 k = 0; k < 4; ++k) {
                     const u32 p = w0 + s + 32 * k + lane;
                     const bool hit = x[k] == y[k] && p <= mflimit;            // c < p, or c == p == 0: distance 0 = none
-                    P2_U16(e + 64 * k) = (u16)(hit ? p - c[k] : 0u);
-                    nmatch += hit;
+                    const u32 dv = hit ? p - c[k] : 0u;
+                    P2_U16(e + 64 * k) = (u16)dv;
+                    const u32 bal = __ballot_sync(0xffffffffu, dv != 0u);
+                    if (lane == (s >> 7)) mk[k] = bal;
+                    nmatch |= bal;
                 }
             }
             __syncwarp();
@@ -281,20 +287,24 @@ lz4_pack_blocks_body(const u8 *__restrict__ in, const PackBlock *__restrict__ bl
             u32 so = 0;                          // staged bytes
             bool has = false;
             const u32 mlim = s1 < matchlimit ? s1 : matchlimit;
-            const bool any = __any_sync(0xffffffffu, nmatch != 0);
+            const bool any = nmatch != 0;
             // Every loop below has ONE exit, so the 32 lanes — each on its own sub-chunk — come back together after each of
             // them: an iteration of the outer loop costs the longest skip + the longest extension + the longest literal
             // run among the lanes, not their sum.
             bool live = any;
             while (live) {
-                // (a) on to the next position that has a candidate
-                u32 d = 0;
+                // (a) on to the next position that has a match: find-first-set over the sub-chunk's bits
+                u32 r = p - s0;
                 bool found = false;
-                while (!found && p < s1 && p <= mflimit) {
-                    d = P2_U16(stg + 2u * (p - s0));
-                    found = d != 0 && p + 4u <= mlim;
-                    if (!found) ++p;
+                while (!found && r < P2_SUB) {
+                    const u32 wsel = r < 64u ? (r < 32u ? mk[0] : mk[1]) : (r < 96u ? mk[2] : mk[3]);
+                    const u32 wv = wsel >> (r & 31u);
+                    if (wv) { r += (u32)__ffs(wv) - 1u; found = true; }
+                    else r = (r | 31u) + 1u;
                 }
+                p = s0 + r;
+                found = found && p + 4u <= mlim;       // a match too close to the end of the sub-chunk (or of the block): nothing behind it can be used either
+                const u32 d = found ? P2_U16(stg + 2u * r) : 0u;
                 live = found;
                 if (live) {
                     // (b) extend forwards, four bytes at a time, then byte-wise up to the limit
