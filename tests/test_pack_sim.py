@@ -183,3 +183,45 @@ def test_zstd_blocks_from_the_lz4_matches_decode_with_the_oracle_and_the_referen
         assert np.array_equal(oracle.zstd_decompress_ref(fr, len(plain)), plain)
         ref = sum(len(oracle.zstd_compress_ref(b, 3)) for b in blocks)
         print(f"\nzstd blocks (huffman={huffman}): {z_total} bytes (LZ4 payloads {lz_total}) vs ZSTD_compress level 3: {ref}")
+
+
+def test_zstd_writer_on_random_shapes(sim, oracle):
+    """Blocks of varied statistics (alphabet size, repetition distance and length, sizes that are not window multiples):
+    every normalisation / table-description / Huffman-limit path the writer takes must give frames the oracle's port decodes."""
+    sim.sim_zstd_encode_block.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    sim.sim_zstd_encode_block.restype = C.c_int
+    rng = np.random.default_rng(77)
+    blocks = []
+    for t in range(12):
+        n = int(rng.choice([65536, 65536, 50000, 20000, 9000, 4100]))
+        alpha = int(rng.choice([2, 5, 16, 64, 120, 200]))
+        b = rng.integers(0, alpha, n, dtype=np.uint8)
+        if t % 3 == 1:                                   # skewed symbols
+            b = (rng.zipf(1.3, n) % alpha).astype(np.uint8)
+        reps = int(rng.choice([0, 50, 400, 3000]))
+        for _ in range(reps):                            # repeats of random length at random (also very short) distances
+            ln = int(rng.choice([4, 5, 8, 20, 70, 300]))
+            p = int(rng.integers(ln + 1, max(ln + 2, n - ln)))
+            d = int(rng.choice([1, 2, 3, 7, 64, 1000, 30000]))
+            d = min(d, p)
+            for k in range(ln):
+                b[p + k] = b[p + k - d]
+        blocks.append(b)
+    packed = pack_blocks(sim, blocks, want_winop=True)
+    encoded = 0
+    for b, (c, payload, winop) in zip(blocks, packed):
+        subs = None
+        if c:
+            slot = np.zeros(65536 + 16384 + 512 + 64, np.uint8)
+            zbody, pay = np.zeros(16, np.uint32), np.zeros(65536 + 16, np.uint8)
+            pay[:c] = payload
+            if sim.sim_zstd_encode_block(pay.ctypes.data, c, len(b), winop.ctypes.data, slot.ctypes.data, zbody.ctypes.data, 3, None):
+                nwin = (len(b) - 12) // 4096 + 1
+                subs = [slot[int(winop[w]) + (int(winop[w]) >> 2) + 24 * w:][:int(zbody[w])].copy() for w in range(nwin) if zbody[w]]
+                encoded += 1
+        fr = zstd_frame([subs], [b])
+        rc, got = oracle.zstd_decode_port(fr, len(b))
+        assert rc == 0 and np.array_equal(got[:len(b)], b), (len(b), c)
+        if subs is not None and oracle.have_ref():
+            assert np.array_equal(oracle.zstd_decompress_ref(fr, len(b)), b)
+    assert encoded >= 6
