@@ -215,3 +215,50 @@ def test_pipelined_pack_host_matches_the_device_path(oracle, monkeypatch):
         assert (h_out[~touched] == 0xA5).all()       # nothing outside the frames was written on the host side
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("method", [2, 1])
+def test_files_of_varied_statistics_round_trip(gpu_ctx, oracle, method):
+    """Alphabets from 2 to 256 symbols, skewed symbols, repeats at distances from 1 to 60 000, sizes that are not block or
+    window multiples: LZ4 and zstd frames from the GPU writer must decode in the CPU checker and on the GPU reader."""
+    rng = np.random.default_rng(123 + method)
+    bufs = []
+    for t in range(40):
+        n = int(rng.choice([1, 12, 13, 4095, 4109, 65535, 65536, 65537, 100000, 200000, 262144]))
+        alpha = int(rng.choice([2, 5, 16, 64, 120, 256]))
+        b = rng.integers(0, alpha, n, dtype=np.uint8) if t % 3 else (rng.zipf(1.3, n) % alpha).astype(np.uint8)
+        for _ in range(int(rng.choice([0, 50, 400, 3000]))):
+            ln = int(rng.choice([4, 5, 8, 20, 70, 300]))
+            if n <= 2 * ln + 2:
+                break
+            p = int(rng.integers(ln + 1, n - ln))
+            d = min(int(rng.choice([1, 2, 3, 7, 64, 1000, 60000])), p)
+            for k in range(ln):
+                b[p + k] = b[p + k - d]
+        bufs.append(b)
+    f = np.zeros(len(bufs), zlib.File)
+    in_off = out_off = 0
+    for i, b in enumerate(bufs):
+        cap = gpu_ctx.pack_bound(method, len(b))
+        f["src_off"][i], f["size"][i], f["dst_off"][i], f["dst_cap"][i], f["method"][i] = in_off, len(b), out_off, cap, method
+        in_off += (len(b) + 15) & ~15
+        out_off += (cap + 15) & ~15
+    h_in = np.zeros(in_off + 16, np.uint8)
+    for i, b in enumerate(bufs):
+        h_in[int(f["src_off"][i]):int(f["src_off"][i]) + len(b)] = b
+    h_out = np.zeros(out_off + 16, np.uint8)
+    comp, digest, status = gpu_ctx.pack_host(h_in, len(h_in), h_out, len(h_out), f)
+    assert (status == 0).all(), status
+    frames = [h_out[int(f["dst_off"][i]):int(f["dst_off"][i] + comp[i])].copy() for i in range(len(bufs))]
+    for i, (b, fr) in enumerate(zip(bufs, frames)):
+        assert int(digest[i]) == oracle.xxh3_port(b)
+        rc, got = (oracle.lz4f_decode_port if method == 2 else oracle.zstd_decode_port)(fr, len(b))
+        assert rc == 0 and np.array_equal(got[:len(b)], b), (i, len(b))
+    arch = container.assemble([f"v{i}" for i in range(len(bufs))], frames, [len(b) for b in bufs], digest, [method] * len(bufs))
+    e = container.parse(arch).entries()
+    out = np.zeros(int((e["dst_off"] + e["dst_cap"]).max()) + 16, np.uint8)
+    st, dg = gpu_ctx.unpack_host(arch, len(arch), out, len(out), e)
+    assert (st == 0).all(), st
+    for i, b in enumerate(bufs):
+        o = int(e["dst_off"][i])
+        assert np.array_equal(out[o:o + len(b)], b), i
