@@ -46,7 +46,7 @@ extern "C" int sim_zstd_encode_block(const uint8_t *lz, uint32_t csize, uint32_t
         total += lit_n[w];
         for (u32 i = 0; i < seq_n[w]; ++i) {
             const u64 r = zseq[w * ZE_WIN_SEQ + i];
-            ++hll[ze_ll_code((u32)(r & 0xFFFF))]; ++hml[ze_ml_code((u32)((r >> 16) & 0xFFFF))]; ++hof[ze_highbit((u32)(r >> 32) + 3u)];
+            ++hll[ze_ll_code((u32)(r & 0xFFFF))]; ++hml[ze_ml_code((u32)((r >> 16) & 0xFFFF))]; ++hof[ze_highbit((u32)(r >> 32))];
         }
         nseq_total += seq_n[w];
     }

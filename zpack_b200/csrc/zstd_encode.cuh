@@ -290,6 +290,7 @@ ZPB_DEVINL bool ze_parse_range(const u8 *lz, u32 begin, u32 end, u32 tail_end, u
     ZeBits lw;
     ze_open(lw, lit_dst, lit_dst + (tail_end - begin) + 8u, false);
     bool bad = false;                                 // single-exit loops: the lanes of a warp (one window each) reconverge every iteration
+    u32 rp0 = 0, rp1 = 0, rp2 = 0, known = 0;         // the part of the repeat-offset history this window has built itself
     while (in.pos < tail_end && !bad) {
         const u32 token = ze_in_byte(in);
         u32 ll = token >> 4;
@@ -314,7 +315,24 @@ ZPB_DEVINL bool ze_parse_range(const u8 *lz, u32 begin, u32 end, u32 tail_end, u
             }
             ml += 4;
             if (off == 0 || nseq >= seq_cap || ll > 65535u || ml > 65535u) bad = true;
-            else seq[nseq++] = (u64)ll | ((u64)ml << 16) | ((u64)off << 32);
+            else {
+                // offset VALUE (zstd_compression_format.md, "Repeat offsets"): 1-3 name one of the three most recent offsets,
+                // anything else is offset + 3.  The window does not know what the windows before it left in that history,
+                // so it only names entries it has pushed itself (`known` of them); the decoder's history evolves the same
+                // way whatever the older entries are.
+                u32 ofv = off + 3u;
+                if (ll) {
+                    if (known >= 1 && off == rp0) ofv = 1;
+                    else if (known >= 2 && off == rp1) { ofv = 2; rp1 = rp0; rp0 = off; }
+                    else if (known >= 3 && off == rp2) { ofv = 3; rp2 = rp1; rp1 = rp0; rp0 = off; }
+                } else {                               // literal length 0 shifts the meaning: 1 -> second, 2 -> third, 3 -> first - 1
+                    if (known >= 2 && off == rp1) { ofv = 1; rp1 = rp0; rp0 = off; }
+                    else if (known >= 3 && off == rp2) { ofv = 2; rp2 = rp1; rp1 = rp0; rp0 = off; }
+                    else if (known >= 1 && off == rp0 - 1u && off) { ofv = 3; rp2 = rp1; rp1 = rp0; rp0 = off; if (known < 3) ++known; }
+                }
+                if (ofv > 3u) { rp2 = rp1; rp1 = rp0; rp0 = off; if (known < 3) ++known; }
+                seq[nseq++] = (u64)ll | ((u64)ml << 16) | ((u64)ofv << 32);
+            }
         }
     }
     ze_flush_all(lw);
@@ -516,7 +534,7 @@ ZPB_DEVINL u32 ze_emit_range(const u8 *lit, u32 lit_n, const u64 *seq, u32 nseq,
     u32 st_ll, st_of, st_ml;
     {
         const u64 r = seq[nseq - 1];
-        const u32 ll = (u32)(r & 0xFFFF), ml = (u32)((r >> 16) & 0xFFFF), ob = (u32)(r >> 32) + 3u;
+        const u32 ll = (u32)(r & 0xFFFF), ml = (u32)((r >> 16) & 0xFFFF), ob = (u32)(r >> 32);
         const u32 cl = ze_ll_code(ll), cm = ze_ml_code(ml), co = (u32)ze_highbit(ob);
         st_ml = ze_init_state(TM, cm);
         st_of = ze_init_state(TO, co);
@@ -531,7 +549,7 @@ ZPB_DEVINL u32 ze_emit_range(const u8 *lit, u32 lit_n, const u64 *seq, u32 nseq,
     for (u32 k = nseq - 1; k-- > 0;) {
         const u64 r = r_next;
         if (k) r_next = seq[k - 1];                  // the record after this one is on its way while this one is encoded
-        const u32 ll = (u32)(r & 0xFFFF), ml = (u32)((r >> 16) & 0xFFFF), ob = (u32)(r >> 32) + 3u;
+        const u32 ll = (u32)(r & 0xFFFF), ml = (u32)((r >> 16) & 0xFFFF), ob = (u32)(r >> 32);
         const u32 cl = ze_ll_code(ll), cm = ze_ml_code(ml), co = (u32)ze_highbit(ob);
         st_of = ze_encode(b, TO, st_of, co);
         st_ml = ze_encode(b, TM, st_ml, cm);
@@ -622,7 +640,7 @@ zstd_huf_tables_kernel(const PackBlock *__restrict__ blocks, const u32 *__restri
                     const u64 r = q[i];
                     atomicAdd(&hll[ze_ll_code((u32)(r & 0xFFFF))], 1u);
                     atomicAdd(&hml[ze_ml_code((u32)((r >> 16) & 0xFFFF))], 1u);
-                    atomicAdd(&hof[ze_highbit((u32)(r >> 32) + 3u)], 1u);
+                    atomicAdd(&hof[ze_highbit((u32)(r >> 32))], 1u);
                 }
                 nseq += ns;
             }
