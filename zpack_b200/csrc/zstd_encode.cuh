@@ -1,4 +1,5 @@
-// zstd_encode.cuh — zstd Compressed_Blocks from the LZ4 block compressor's matches: one thread per 64 KB block.
+// zstd_encode.cuh — zstd Compressed_Blocks from the LZ4 block compressor's matches: one thread per 4 KB window, one set of
+// entropy tables per 64 KB block.
 //
 // The role of ZSTD_compressBlock_internal's back end (/root/reference/externals/zstd/lib/compress/zstd_compress.c,
 // zstd_compress_sequences.c:ZSTD_encodeSequences, huf_compress.c, fse_compress.c) for the writer's
@@ -14,13 +15,12 @@
 //     bits LL / ML / OF, per earlier sequence the OF, ML, LL state transitions, final states ML, OF, LL, end mark), with
 //     FSE tables fitted to the block's own LL / OF / ML codes: the block's first window with sequences describes them
 //     (FSE_Compressed_Mode, or RLE_Mode for a single code), later windows use Repeat_Mode; small blocks keep the
-//     predefined tables.  No repeat-offset codes (offset value = offset + 3 always).
+//     predefined tables.  Repeat-offset codes are used for the part of the offset history a window has built itself.
 // The ratio is reported next to ZSTD_compress level 3 by the tests and the bench.  A block that does not shrink stays a
 // Raw_Block.
 #pragma once
 #include "common.cuh"
 
-#define ZE_SEQ_MAX 16384u      // sequences of one 64 KB block: each covers at least 4 input bytes
 #ifdef ZPB_SIM
 #define ZE_CONST static const
 #else
