@@ -227,6 +227,50 @@ int zpb_group_last_ms(const zpb_group *g, float *ms, int cap);   /* wall time of
 void *zpb_host_alloc(uint64_t bytes);
 void  zpb_host_free(void *p);
 
+/* the container level on the device -------------------------------------------------------------- */
+/* an archive image that stays in HBM is opened, assembled and copied entry by entry without a
+ * host pass over its bytes.  The host side of each call touches only the per-entry table it is given (argument checks and
+ * two sums) and the 42 fixed bytes of an archive.
+ *
+ *   zpb_archive_open_device   zpack_read_archive_memory -> zpack_read_cdr_memory -> zpack_read_file_entries_memory
+ *                             (/root/reference/lib/zpack_read.c:225-260, 168-188, 109-166), without its malloc per entry
+ *   zpb_archive_build_device  the offset table of zpack_write_files (ZPACK_ADD_OFFSET_AND_SIZE, lib/zpack_write.c:280-343),
+ *                             zpack_write_header / _data_header, zpack_write_cdr_ex, zpack_write_eocdr
+ *                             (lib/zpack_write.c:640-685, 713-776, 778-800) and the payload moves in between
+ *   zpb_copy_entries_device   the memcpy loop of zpack_write_files_from_archive (lib/zpack_write.c:345-428) */
+typedef struct zpb_arc_entry {
+    uint64_t src_off;      /* where the entry's compressed bytes are in the source buffer (a pack slot, or entry.offset of the
+                            * archive it is copied from); open: = offset                                                  */
+    uint64_t comp_size;    /* entry.comp_size                                                                            */
+    uint64_t uncomp_size;  /* entry.uncomp_size                                                                          */
+    uint64_t hash;         /* entry.hash                                                                                 */
+    uint64_t name_off;     /* of the file name inside the names blob (not NUL-terminated)                                */
+    uint32_t name_len;     /* <= 65535 (ZPACK_MAX_FILENAME_LENGTH, lib/zpack.h:48)                                       */
+    uint32_t method;       /* entry.comp_method                                                                          */
+    uint64_t offset;       /* entry.offset in the archive: written by build, read by copy (the destination), = src_off after open */
+    uint64_t reserved;
+} zpb_arc_entry;
+
+/* Parse the central directory of the archive image at d_archive (device).  *result = the zpack_result the reference's open
+ * returns for these bytes (0, FILE_TOO_SMALL 5, SIGNATURE_INVALID 6, READ_FAILED 7, BLOCK_SIZE_INVALID 8,
+ * VERSION_INCOMPATIBLE 9); *n = the directory's file count as soon as its header is readable.  entries (HOST, cap elements)
+ * receives one row per file; names (HOST, optional, names_cap >= *names_size) receives the directory block that name_off
+ * points into.  ZPB_E_ARG when cap < *n (call again with a larger table) or the directory is >= 4 GB. */
+int zpb_archive_open_device(zpb_ctx *ctx, const uint8_t *d_archive, uint64_t archive_size, zpb_arc_entry *entries, uint64_t cap,
+                            uint64_t *n, uint8_t *names, uint64_t names_cap, uint64_t *names_size, int32_t *result, void *stream);
+/* Write a whole archive into d_archive (device): header, the n payloads back to back in table order (read from d_src +
+ * src_off: pack slots, or another archive), central directory, end record.  entries / names are HOST arrays; offset of every
+ * entry is assigned on the device and returned in the table.  d_src and d_archive must not overlap. */
+int zpb_archive_build_device(zpb_ctx *ctx, const uint8_t *d_src, uint64_t src_size, zpb_arc_entry *entries, uint64_t n,
+                             const uint8_t *names, uint64_t names_size, uint8_t *d_archive, uint64_t archive_cap,
+                             uint64_t *archive_size, void *stream);
+/* d_dst[offset .. offset + comp_size) = d_src[src_off .. src_off + comp_size) for every entry; ranges of different entries
+ * must not overlap in d_dst, and d_dst must not overlap d_src. */
+int zpb_copy_entries_device(zpb_ctx *ctx, const uint8_t *d_src, uint64_t src_size, uint8_t *d_dst, uint64_t dst_size,
+                            const zpb_arc_entry *entries, uint64_t n, void *stream);
+/* device time (ms) of the last call's kernels: [0] offset table + directory, [1] payload copy, [2] directory parse */
+int zpb_last_archive_ms(const zpb_ctx *ctx, float *ms3);
+
 /* tuning knobs: lanes per dependency chain (4, 8, 16, 32; 0 = keep) and resident CTAs per SM
  * (0 = occupancy API, -1 = keep).  Defaults can also come from ZPB_GROUP / ZPB_CTAS_PER_SM. */
 int zpb_set_tuning(zpb_ctx *ctx, int group_lanes, int ctas_per_sm);

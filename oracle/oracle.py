@@ -261,6 +261,14 @@ class RefReader:
             raise RuntimeError(f"zpack_init_reader_memory_shared failed: {rc}")
         self.count = int(self.r.file_count)
 
+    @staticmethod
+    def open_result(archive: np.ndarray) -> int:
+        """zpack_result of opening these bytes with the unmodified reference (lib/zpack_read.c:225-260)"""
+        lib, buf, r = ref(), np.ascontiguousarray(archive), Reader()
+        rc = lib.zpack_init_reader_memory_shared(C.byref(r), buf.ctypes.data, len(buf))
+        lib.zpack_close_reader(C.byref(r))
+        return int(rc)
+
     def entry(self, i: int) -> FileEntry:
         return self.r.file_entries[i]
 

@@ -9,6 +9,6 @@ Only what the path needs lives here:
 
 There is no CPU codec in this package: without a CUDA device `lib.Context()` raises.
 """
-from .lib import Context, Group, ZpbError, Entry, File, load_library  # noqa: F401
+from .lib import Context, Group, ZpbError, Entry, File, ArcEntry, load_library  # noqa: F401
 
-__all__ = ["Context", "Group", "ZpbError", "Entry", "File", "load_library"]
+__all__ = ["Context", "Group", "ZpbError", "Entry", "File", "ArcEntry", "load_library"]

@@ -1,0 +1,292 @@
+// archive_kernels.cuh — the container level on the device: an archive image that stays in HBM
+// is opened (central directory -> entry table), assembled (payload slots -> header + data + CDR + EOCDR) and copied
+// entry by entry into another archive without a host pass over its bytes.
+//
+//   arc_layout_kernel   exclusive prefix sums over the entries: entry.offset (the offset table of
+//                       zpack_write_files / ZPACK_ADD_OFFSET_AND_SIZE, /root/reference/lib/zpack_write.c:280-343), the
+//                       position of every CDR record (zpack_write_cdr_ex's block size loop, zpack_write.c:720-736) and
+//                       the first 64 KB copy chunk of every entry
+//   arc_copy_kernel     the byte moves of zpack_write_files_from_archive (zpack_write.c:345-428: one memcpy per entry)
+//                       as 64 KB chunks dealt round-robin to the CTAs; 16-byte stores, the source realigned in registers
+//   arc_cdr_kernel      zpack_write_cdr_memory + zpack_write_eocdr (+ the archive header) (zpack_write.c:687-711, 778-785)
+//   cdr_*_kernel        zpack_read_file_entries_memory (/root/reference/lib/zpack_read.c:109-166).  The records are a
+//                       linked list (each starts where the previous one's name ends), which the reference walks serially;
+//                       here every byte of the directory is taken as a possible record start and walked to the end of
+//                       its 1 KB tile (shared memory), the tile exits are composed over 64 KB super-tiles, one thread
+//                       hops over the super-tiles, and the true starts come back down the same two levels — 64 K entries
+//                       cost ~60 dependent global loads on the serial thread instead of 64 K.
+//
+// HBM-bound (copy) or latency-bound at microsecond scale (the rest); nothing here is a contraction.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+struct ArcEntry {          // = zpb_arc_entry (include/zpack_b200.h), 64 bytes
+    u64 src_off;           // where the entry's compressed bytes are in the source buffer
+    u64 comp_size, uncomp_size, hash;
+    u64 name_off;          // of the name in the names blob (build) / in the CDR body (open)
+    u32 name_len, method;
+    u64 offset;            // entry.offset in the archive (build: out, or in when the layout is the caller's)
+    u64 reserved;
+};
+static_assert(sizeof(ArcEntry) == 64, "zpb_arc_entry layout");
+
+#define ARC_CHUNK_LOG 16u
+#define ARC_CHUNK (1u << ARC_CHUNK_LOG)   // bytes of one copy work item
+#define ARC_COPY_THREADS 256
+#define ARC_SCAN_THREADS 1024
+#define ARC_FIXED 35u                     // ZPACK_FILE_ENTRY_FIXED_SIZE (lib/zpack.h:44)
+#define ARC_CDR_HDR 20u
+#define ARC_DATA_START 10u
+
+ZPB_DEVINL void arc_sts64(u32 a, u64 v) { sts32(a, (u32)v); sts32(a + 4, (u32)(v >> 32)); }
+ZPB_DEVINL u64 arc_lds64(u32 a) { return (u64)lds32(a) | ((u64)lds32(a + 4) << 32); }
+ZPB_DEVINL void arc_st16(u8 *p, u32 v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); }
+ZPB_DEVINL void arc_st32(u8 *p, u32 v) { arc_st16(p, v); arc_st16(p + 2, v >> 16); }
+ZPB_DEVINL void arc_st64(u8 *p, u64 v) { arc_st32(p, (u32)v); arc_st32(p + 4, (u32)(v >> 32)); }
+
+// ---- layout: one CTA, three running sums.  totals: Σ comp_size, Σ (35 + name_len), Σ chunks.
+ZPB_DEVINL void arc_layout_body(ArcEntry *e, u64 n, u64 base, u32 assign, u64 *rec_off, u64 *chunk_first, u64 *totals) {
+    ZPB_DYN_SMEM(smem);
+    const u32 sm = smem_window(smem);            // 32 warps x 3 sums x 8 bytes
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nw = blockDim.x >> 5;
+    u64 c0 = 0, c1 = 0, c2 = 0;
+    for (u64 i0 = 0; i0 < n; i0 += blockDim.x) {
+        const u64 i = i0 + tid;
+        u64 a = 0, b = 0, c = 0;
+        if (i < n) { a = e[i].comp_size; b = ARC_FIXED + (u64)e[i].name_len; c = (a + ARC_CHUNK - 1) >> ARC_CHUNK_LOG; }
+        u64 sa = a, sb = b, sc = c;
+        for (u32 d = 1; d < 32; d <<= 1) {
+            const u64 ta = __shfl_up_sync(0xffffffffu, sa, d), tb = __shfl_up_sync(0xffffffffu, sb, d),
+                      tc = __shfl_up_sync(0xffffffffu, sc, d);
+            if (lane >= d) { sa += ta; sb += tb; sc += tc; }
+        }
+        if (lane == 31) { arc_sts64(sm + warp * 24, sa); arc_sts64(sm + warp * 24 + 8, sb); arc_sts64(sm + warp * 24 + 16, sc); }
+        __syncthreads();
+        u64 pa = 0, pb = 0, pc = 0, ta = 0, tb = 0, tc = 0;
+        for (u32 w = 0; w < nw; ++w) {
+            const u64 x = arc_lds64(sm + w * 24), y = arc_lds64(sm + w * 24 + 8), z = arc_lds64(sm + w * 24 + 16);
+            if (w < warp) { pa += x; pb += y; pc += z; }
+            ta += x; tb += y; tc += z;
+        }
+        __syncthreads();
+        if (i < n) {
+            if (assign) e[i].offset = base + c0 + pa + sa - a;
+            rec_off[i] = c1 + pb + sb - b;
+            chunk_first[i] = c2 + pc + sc - c;
+        }
+        c0 += ta; c1 += tb; c2 += tc;
+    }
+    if (tid == 0) { totals[0] = c0; totals[1] = c1; totals[2] = c2; chunk_first[n] = c2; }
+}
+
+// ---- copy: dst and src never overlap (different buffers, or the caller's disjoint ranges)
+ZPB_DEVINL uint4 arc_realign(uint4 A, uint4 B, u32 w, u32 b) {
+    u32 x0, x1, x2, x3, x4;
+    switch (w) {
+        case 0: x0 = A.x; x1 = A.y; x2 = A.z; x3 = A.w; x4 = B.x; break;
+        case 1: x0 = A.y; x1 = A.z; x2 = A.w; x3 = B.x; x4 = B.y; break;
+        case 2: x0 = A.z; x1 = A.w; x2 = B.x; x3 = B.y; x4 = B.z; break;
+        default: x0 = A.w; x1 = B.x; x2 = B.y; x3 = B.z; x4 = B.w; break;
+    }
+    return make_uint4(__funnelshift_r(x0, x1, b), __funnelshift_r(x1, x2, b), __funnelshift_r(x2, x3, b), __funnelshift_r(x3, x4, b));
+}
+
+ZPB_DEVINL void arc_copy_span(u8 *dst, const u8 *src, u32 len) {
+    const u32 tid = threadIdx.x, nt = blockDim.x;
+    u32 head = (u32)(-(intptr_t)dst) & 15u;
+    if (head > len) head = len;
+    if (tid < head) dst[tid] = src[tid];
+    dst += head; src += head; len -= head;
+    const u32 rel = (u32)(uintptr_t)src & 15u;
+    u32 nvec;
+    if (rel == 0) {
+        nvec = len >> 4;
+        for (u32 v = tid; v < nvec; v += 4 * nt) {
+            uint4 r[4];
+#pragma unroll
+            for (u32 k = 0; k < 4; ++k) if (v + k * nt < nvec) r[k] = ldg128_stream(src + 16 * (size_t)(v + k * nt));
+#pragma unroll
+            for (u32 k = 0; k < 4; ++k) if (v + k * nt < nvec) stg128(dst + 16 * (size_t)(v + k * nt), r[k]);
+        }
+    } else {
+        // the second vector of the last chunk must stay inside [src, src + len): keep 16 bytes for the byte loop
+        nvec = len >= 32 ? (len - 16) >> 4 : 0;
+        const u8 *sa = src - rel;
+        const u32 w = rel >> 2, b = (rel & 3u) * 8u;
+        for (u32 v = tid; v < nvec; v += 2 * nt) {
+            uint4 A[2], B[2];
+#pragma unroll
+            for (u32 k = 0; k < 2; ++k) if (v + k * nt < nvec) {
+                A[k] = ldg128(sa + 16 * (size_t)(v + k * nt));
+                B[k] = ldg128(sa + 16 * (size_t)(v + k * nt) + 16);
+            }
+#pragma unroll
+            for (u32 k = 0; k < 2; ++k) if (v + k * nt < nvec) stg128(dst + 16 * (size_t)(v + k * nt), arc_realign(A[k], B[k], w, b));
+        }
+    }
+    for (u32 i = (nvec << 4) + tid; i < len; i += nt) dst[i] = src[i];
+}
+
+ZPB_DEVINL void arc_copy_body(const u8 *src, u8 *dst, const ArcEntry *e, u64 n, const u64 *chunk_first, u64 nchunks) {
+    for (u64 c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        u64 lo = 0, hi = n;                       // chunk_first[lo] <= c < chunk_first[hi]; empty entries are skipped
+        while (hi - lo > 1) {
+            const u64 mid = (lo + hi) >> 1;
+            if (chunk_first[mid] <= c) lo = mid; else hi = mid;
+        }
+        const u64 off = (c - chunk_first[lo]) << ARC_CHUNK_LOG;
+        const u64 left = e[lo].comp_size - off;
+        arc_copy_span(dst + e[lo].offset + off, src + e[lo].src_off + off, left < ARC_CHUNK ? (u32)left : ARC_CHUNK);
+    }
+}
+
+// ---- central directory + end record (+ the 10 header bytes)
+ZPB_DEVINL void arc_cdr_body(u8 *arch, const ArcEntry *e, u64 n, const u8 *names, const u64 *rec_off, u64 cdr_off,
+                             u64 block_size, u32 write_header) {
+    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x, step = (u64)gridDim.x * blockDim.x;
+    if (gid == 0) {
+        if (write_header) { arc_st32(arch, 0x154B505Au); arc_st16(arch + 4, 1u); arc_st32(arch + 6, 0x144B505Au); }
+        u8 *p = arch + cdr_off;
+        arc_st32(p, 0x134B505Au); arc_st64(p + 4, n); arc_st64(p + 12, block_size);
+        p += ARC_CDR_HDR + block_size;
+        arc_st32(p, 0x124B505Au); arc_st64(p + 4, cdr_off);
+    }
+    for (u64 i = gid; i < n; i += step) {
+        u8 *p = arch + cdr_off + ARC_CDR_HDR + rec_off[i];
+        const u32 len = e[i].name_len;
+        const u8 *nm = names + e[i].name_off;
+        arc_st16(p, len);
+        for (u32 k = 0; k < len; ++k) p[2 + k] = nm[k];
+        p += 2 + len;
+        arc_st64(p, e[i].offset); arc_st64(p + 8, e[i].comp_size); arc_st64(p + 16, e[i].uncomp_size); arc_st64(p + 24, e[i].hash);
+        p[32] = (u8)e[i].method;
+    }
+}
+
+// ---- open: the directory body (block_size = B bytes after the 20-byte CDR header) -> entry table
+#define CDR_T 1024u                    // tile
+#define CDR_S 64u                      // tiles per super-tile
+#define CDR_ST (CDR_T * CDR_S)
+#define CDR_END 0xFFFFFFFFu            // "the record here does not fit the block" / "no anchor"
+#define CDR_MAX_BODY 0xFFF00000ull     // positions are 32-bit
+
+// every byte of tile t as a record start: where the walk leaves the tile (absolute) and how many records it saw
+ZPB_DEVINL void cdr_tile_body(const u8 *body, u64 B, u32 *jump, u8 *cnt) {
+    ZPB_DYN_SMEM(smem);
+    const u32 sm = smem_window(smem);
+    const u64 g0 = (u64)blockIdx.x * CDR_T;
+    const u32 have = (u32)(B - g0 < CDR_T + 2 ? B - g0 : CDR_T + 2);
+    for (u32 i = threadIdx.x; i < have; i += blockDim.x) sts8(sm + i, body[g0 + i]);
+    __syncthreads();
+    for (u32 s = threadIdx.x; s < CDR_T && g0 + s < B; s += blockDim.x) {
+        u32 pos = s, c = 0, out;
+        for (;;) {
+            if (pos >= CDR_T) { out = (u32)(g0 + pos); break; }
+            const u64 gp = g0 + pos;
+            if (gp + ARC_FIXED > B) { out = CDR_END; break; }
+            const u32 len = lds8(sm + pos) | (lds8(sm + pos + 1) << 8);
+            if (gp + ARC_FIXED + len > B) { out = CDR_END; break; }
+            pos += ARC_FIXED + len; ++c;
+        }
+        jump[g0 + s] = out; cnt[g0 + s] = (u8)c;
+    }
+}
+
+// the same over a super-tile, for every start inside its first tile
+ZPB_DEVINL void cdr_super_body(u64 B, const u32 *jump, const u8 *cnt, u32 *jump2, u32 *cnt2, u64 nsuper) {
+    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nsuper * CDR_T) return;
+    const u64 st = gid / CDR_T, limit = (st + 1) * CDR_ST;
+    u64 p = st * CDR_ST + gid % CDR_T;
+    u32 c = 0;
+    while (p != CDR_END && p < limit && p < B) { c += cnt[p]; p = jump[p]; }
+    jump2[gid] = (u32)p; cnt2[gid] = c;
+}
+
+// one thread: from super-tile to super-tile; leaves the first record start of each and its index
+ZPB_DEVINL void cdr_chain_body(u64 B, const u32 *jump, const u8 *cnt, const u32 *jump2, const u32 *cnt2, u32 *sup_pos,
+                               u32 *sup_idx, u64 *found) {
+    if (blockIdx.x || threadIdx.x) return;
+    u64 p = 0, cur = ~0ull;
+    u32 idx = 0;
+    while (p != CDR_END && p < B) {
+        const u64 st = p / CDR_ST, rel = p - st * CDR_ST;
+        if (st != cur) { sup_pos[st] = (u32)p; sup_idx[st] = idx; cur = st; }
+        if (rel < CDR_T) { idx += cnt2[st * CDR_T + rel]; p = jump2[st * CDR_T + rel]; }
+        else { idx += cnt[p]; p = jump[p]; }
+    }
+    *found = idx;
+}
+
+// thread per super-tile: the first record start of each of its tiles
+ZPB_DEVINL void cdr_anchor_body(u64 B, const u32 *jump, const u8 *cnt, const u32 *sup_pos, const u32 *sup_idx, u32 *tile_pos,
+                                u32 *tile_idx, u64 nsuper) {
+    const u64 st = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (st >= nsuper) return;
+    u64 p = sup_pos[st];
+    if (p == CDR_END) return;
+    u32 idx = sup_idx[st];
+    const u64 limit = (st + 1) * CDR_ST;
+    u64 cur = ~0ull;
+    while (p != CDR_END && p < limit && p < B) {
+        const u64 t = p / CDR_T;
+        if (t != cur) { tile_pos[t] = (u32)p; tile_idx[t] = idx; cur = t; }
+        idx += cnt[p]; p = jump[p];
+    }
+}
+
+// thread per tile: the records that start in it
+ZPB_DEVINL void cdr_emit_body(const u8 *body, u64 B, const u32 *tile_pos, const u32 *tile_idx, ArcEntry *out, u64 count,
+                              u64 ntiles) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    u64 p = tile_pos[t];
+    if (p == CDR_END) return;
+    u64 idx = tile_idx[t];
+    const u64 limit = (t + 1) * CDR_T;
+    while (p < limit && idx < count && p + ARC_FIXED <= B) {
+        const u32 len = ld16u(body + p);
+        if (p + ARC_FIXED + len > B) break;
+        const u8 *f = body + p + 2 + len;
+        const u64 off = ld64u(f), cs = ld64u(f + 8), us = ld64u(f + 16), h = ld64u(f + 24);
+        uint4 *o = reinterpret_cast<uint4 *>(out + idx);
+        stg128(o, make_uint4((u32)off, (u32)(off >> 32), (u32)cs, (u32)(cs >> 32)));
+        stg128(o + 1, make_uint4((u32)us, (u32)(us >> 32), (u32)h, (u32)(h >> 32)));
+        stg128(o + 2, make_uint4((u32)(p + 2), (u32)((p + 2) >> 32), len, (u32)f[32]));
+        stg128(o + 3, make_uint4((u32)off, (u32)(off >> 32), 0u, 0u));
+        p += ARC_FIXED + len; ++idx;
+    }
+}
+
+#ifndef ZPB_SIM
+__global__ void __launch_bounds__(ARC_SCAN_THREADS)
+arc_layout_kernel(ArcEntry *e, u64 n, u64 base, u32 assign, u64 *rec_off, u64 *chunk_first, u64 *totals) {
+    arc_layout_body(e, n, base, assign, rec_off, chunk_first, totals);
+}
+__global__ void __launch_bounds__(ARC_COPY_THREADS)
+arc_copy_kernel(const u8 *__restrict__ src, u8 *__restrict__ dst, const ArcEntry *__restrict__ e, u64 n,
+                const u64 *__restrict__ chunk_first, u64 nchunks) {
+    arc_copy_body(src, dst, e, n, chunk_first, nchunks);
+}
+__global__ void arc_cdr_kernel(u8 *arch, const ArcEntry *e, u64 n, const u8 *names, const u64 *rec_off, u64 cdr_off,
+                               u64 block_size, u32 write_header) {
+    arc_cdr_body(arch, e, n, names, rec_off, cdr_off, block_size, write_header);
+}
+__global__ void __launch_bounds__(256) cdr_tile_kernel(const u8 *body, u64 B, u32 *jump, u8 *cnt) { cdr_tile_body(body, B, jump, cnt); }
+__global__ void cdr_super_kernel(u64 B, const u32 *jump, const u8 *cnt, u32 *jump2, u32 *cnt2, u64 nsuper) {
+    cdr_super_body(B, jump, cnt, jump2, cnt2, nsuper);
+}
+__global__ void cdr_chain_kernel(u64 B, const u32 *jump, const u8 *cnt, const u32 *jump2, const u32 *cnt2, u32 *sup_pos,
+                                 u32 *sup_idx, u64 *found) {
+    cdr_chain_body(B, jump, cnt, jump2, cnt2, sup_pos, sup_idx, found);
+}
+__global__ void cdr_anchor_kernel(u64 B, const u32 *jump, const u8 *cnt, const u32 *sup_pos, const u32 *sup_idx, u32 *tile_pos,
+                                  u32 *tile_idx, u64 nsuper) {
+    cdr_anchor_body(B, jump, cnt, sup_pos, sup_idx, tile_pos, tile_idx, nsuper);
+}
+__global__ void cdr_emit_kernel(const u8 *body, u64 B, const u32 *tile_pos, const u32 *tile_idx, ArcEntry *out, u64 count,
+                                u64 ntiles) {
+    cdr_emit_body(body, B, tile_pos, tile_idx, out, count, ntiles);
+}
+#endif

@@ -17,6 +17,7 @@
 #include "pack_kernel.cuh"
 #include "zstd_decode.cuh"
 #include "xxh3_chain.cuh"
+#include "archive_kernels.cuh"
 
 static thread_local std::string g_last_error = "";
 
@@ -95,6 +96,9 @@ struct zpb_ctx {
     float chain_ms = 0.f;
     int host_workers = 6;              // ZPB_HOST_WORKERS (tools/e2e_sweep.py: profiles/r1_e2e_sweep.jsonl)
     u64 host_chunk_bytes = 256u << 20; // decoded bytes per pipeline chunk (ZPB_HOST_CHUNK_MB)
+    // device-resident container operations (archive_api.inl): entry table, record offsets, chunk table, totals, names; CDR walk tables
+    DevBuf d_arc_e, d_arc_rec, d_arc_chunk, d_arc_tot, d_arc_names, d_cdr_jump, d_cdr_cnt, d_cdr_j2, d_cdr_anchor;
+    float arc_ms[3] = {0, 0, 0};       // layout + directory kernels, copy kernel, open kernels of the last call
 };
 
 #define CK(ctx, call)                                                                      \
@@ -209,6 +213,8 @@ extern "C" void zpb_destroy(zpb_ctx *ctx) {
     ctx->d_zslot.release(); ctx->d_zseq.release(); ctx->d_zmeta.release(); ctx->d_zelit.release(); ctx->d_zhuf.release(); ctx->d_ztabs.release();
     for (cudaEvent_t e : ctx->pack_evs) cudaEventDestroy(e);
     ctx->d_partials.release(); ctx->d_acc.release();
+    ctx->d_arc_e.release(); ctx->d_arc_rec.release(); ctx->d_arc_chunk.release(); ctx->d_arc_tot.release(); ctx->d_arc_names.release();
+    ctx->d_cdr_jump.release(); ctx->d_cdr_cnt.release(); ctx->d_cdr_j2.release(); ctx->d_cdr_anchor.release();
     for (auto &ev : ctx->evs) if (ev) cudaEventDestroy(ev);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -763,3 +769,6 @@ extern "C" int zpb_xxh3_host(zpb_ctx *ctx, const uint8_t *h_data, uint64_t lengt
 
 // ------------------------------------------------------------------------------------ several GPUs, one call
 #include "group_api.inl"
+
+// ------------------------------------------------------------------------------------ the container level on the device
+#include "archive_api.inl"

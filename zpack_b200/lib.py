@@ -45,7 +45,12 @@ File = np.dtype(
 Block = np.dtype([("src_off", "<u8"), ("comp_size", "<u4"), ("flags", "<u4")])
 BLK_STORED = 1
 INDEX_UNSUPPORTED = 1
-assert Entry.itemsize == 64 and File.itemsize == 64 and Block.itemsize == 16
+#: numpy dtype of `struct zpb_arc_entry` (64 bytes): one row of a device-resident archive's directory
+ArcEntry = np.dtype(
+    [("src_off", "<u8"), ("comp_size", "<u8"), ("uncomp_size", "<u8"), ("hash", "<u8"), ("name_off", "<u8"),
+     ("name_len", "<u4"), ("method", "<u4"), ("offset", "<u8"), ("reserved", "<u8")]
+)
+assert Entry.itemsize == 64 and File.itemsize == 64 and Block.itemsize == 16 and ArcEntry.itemsize == 64
 
 EXPORTS = [
     "zpb_abi_version", "zpb_create", "zpb_destroy", "zpb_last_error", "zpb_device_info",
@@ -54,6 +59,7 @@ EXPORTS = [
     "zpb_last_stage_ms", "zpb_set_fast_path", "zpb_set_overlap", "zpb_last_zstd_ms",
     "zpb_lz4_frame_index", "zpb_unpack_blocks_device", "zpb_blocks_digest", "zpb_last_chain_ms",
     "zpb_unpack_entry_blocks_host", "zpb_device_count",
+    "zpb_archive_open_device", "zpb_archive_build_device", "zpb_copy_entries_device", "zpb_last_archive_ms",
 ]
 
 
@@ -112,6 +118,10 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.zpb_group_unpack_host.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, vp]
     lib.zpb_group_pack_host.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, vp, vp]
     lib.zpb_group_last_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+    lib.zpb_archive_open_device.argtypes = [vp, vp, u64, vp, u64, u64p, vp, u64, u64p, i32p, vp]
+    lib.zpb_archive_build_device.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, u64, u64p, vp]
+    lib.zpb_copy_entries_device.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp]
+    lib.zpb_last_archive_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.zpb_host_alloc.restype = vp
     lib.zpb_host_alloc.argtypes = [u64]
     lib.zpb_host_free.argtypes = [vp]
@@ -345,6 +355,44 @@ class Context:
         out = np.empty(len(off), np.uint64)
         self._check(self.lib.zpb_xxh3_device(self.h, _ptr(d_data), _ptr(off), _ptr(ln), len(off), _ptr(out), stream))
         return out
+
+    # ---- the container level on the device ------------------------------------------------------
+    def archive_open_device(self, d_archive, archive_size: int, want_names: bool = True, stream: int = 0):
+        """(zpack_result, ArcEntry table, directory block that name_off points into) of the archive image in HBM."""
+        n, nsz, res = C.c_uint64(), C.c_uint64(), C.c_int32(-1)
+        rc = self.lib.zpb_archive_open_device(self.h, _ptr(d_archive), archive_size, None, 0, C.byref(n), None, 0, C.byref(nsz),
+                                              C.byref(res), stream)
+        if rc == 0:                      # refused by the fixed fields, or an empty archive
+            return res.value, np.zeros(0, ArcEntry), np.zeros(0, np.uint8)
+        if n.value == 0:
+            self._check(rc)
+        entries = np.zeros(n.value, ArcEntry)
+        names = np.zeros(nsz.value if want_names else 0, np.uint8)
+        self._check(self.lib.zpb_archive_open_device(self.h, _ptr(d_archive), archive_size, _ptr(entries), len(entries), C.byref(n),
+                                                     _ptr(names) if want_names else None, len(names), C.byref(nsz), C.byref(res), stream))
+        if res.value != 0:
+            return res.value, np.zeros(0, ArcEntry), np.zeros(0, np.uint8)
+        return 0, entries, names
+
+    def archive_build_device(self, d_src, src_size: int, entries: np.ndarray, names: np.ndarray, d_archive, archive_cap: int,
+                             stream: int = 0) -> int:
+        """Header + payloads (from d_src + src_off, table order) + CDR + EOCDR into d_archive; fills entries['offset']."""
+        assert entries.dtype == ArcEntry and entries.flags.c_contiguous
+        names = np.ascontiguousarray(names, np.uint8)
+        size = C.c_uint64()
+        self._check(self.lib.zpb_archive_build_device(self.h, _ptr(d_src) if d_src is not None else None, src_size, _ptr(entries), len(entries),
+                                                      _ptr(names) if len(names) else None, len(names), _ptr(d_archive), archive_cap,
+                                                      C.byref(size), stream))
+        return size.value
+
+    def copy_entries_device(self, d_src, src_size: int, d_dst, dst_size: int, entries: np.ndarray, stream: int = 0):
+        assert entries.dtype == ArcEntry and entries.flags.c_contiguous
+        self._check(self.lib.zpb_copy_entries_device(self.h, _ptr(d_src), src_size, _ptr(d_dst), dst_size, _ptr(entries), len(entries), stream))
+
+    def last_archive_ms(self):
+        ms = (C.c_float * 3)()
+        self._check(self.lib.zpb_last_archive_ms(self.h, ms))
+        return tuple(float(x) for x in ms)
 
     # ---- pack --------------------------------------------------------------------------------
     def pack_bound(self, method: int, size: int) -> int:
