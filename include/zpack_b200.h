@@ -34,6 +34,7 @@ extern "C" {
 #define ZPB_E_CUDA         -2   /* a CUDA call failed; see zpb_last_error()  */
 #define ZPB_E_ARG          -3   /* bad argument (NULL, misaligned, overflow) */
 #define ZPB_E_NOMEM        -4   /* device or pinned allocation failed        */
+#define ZPB_E_IO           -5   /* pread / pwrite failed or the file is short */
 
 /* compression methods — values of zpack_compression_method (lib/zpack.h:60-66) */
 #define ZPB_METHOD_NONE 0
@@ -270,6 +271,13 @@ int zpb_copy_entries_device(zpb_ctx *ctx, const uint8_t *d_src, uint64_t src_siz
                             const zpb_arc_entry *entries, uint64_t n, void *stream);
 /* device time (ms) of the last call's kernels: [0] offset table + directory, [1] payload copy, [2] directory parse */
 int zpb_last_archive_ms(const zpb_ctx *ctx, float *ms3);
+/* File <-> HBM for a device-resident archive: bytes [file_off, file_off + size) of the open file descriptor fd to / from
+ * device memory, read / written by several host threads through pinned buffers on their own streams (pread, H2D and the next
+ * pread overlap; no GPUDirect-Storage driver is assumed).  Replaces the reference's fread of entry and directory bytes
+ * (/root/reference/lib/zpack_read.c:298-324, 190-223) and its seek + fwrite (lib/zpack_common.c:72-81) when the other side of
+ * the transfer is the device.  ZPB_E_IO when the file is shorter than the range or a system call fails. */
+int zpb_file_read_device(zpb_ctx *ctx, int fd, uint64_t file_off, uint64_t size, uint8_t *d_dst);
+int zpb_file_write_device(zpb_ctx *ctx, int fd, uint64_t file_off, uint64_t size, const uint8_t *d_src);
 
 /* tuning knobs: lanes per dependency chain (4, 8, 16, 32; 0 = keep) and resident CTAs per SM
  * (0 = occupancy API, -1 = keep).  Defaults can also come from ZPB_GROUP / ZPB_CTAS_PER_SM. */

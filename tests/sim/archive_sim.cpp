@@ -20,8 +20,12 @@ extern "C" int sim_archive_build(const uint8_t *src, ArcEntry *e, uint64_t n, co
     if (with_cdr)
         sim::launch(sim::Dim3((unsigned)grid), sim::Dim3(64), 0, [&] { arc_cdr_body(dst, e, n, names, rp, cdr_off, block, 1u); }, seed);
     const u64 nchunks = totals[2];
-    if (nchunks)
-        sim::launch(sim::Dim3((unsigned)grid), sim::Dim3(64), 0, [&] { arc_copy_body(src, dst, e, n, cp, nchunks); }, seed);
+    if (nchunks) {
+        std::vector<ArcChunk> work(nchunks);
+        ArcChunk *wp = work.data();
+        sim::launch(sim::Dim3((unsigned)((nchunks + 31) / 32)), sim::Dim3(32), 0, [&] { arc_chunks_body(e, n, cp, nchunks, wp); }, seed);
+        sim::launch(sim::Dim3((unsigned)grid), sim::Dim3(64), 0, [&] { arc_copy_body(src, dst, wp, nchunks); }, seed);
+    }
     return 0;
 }
 

@@ -215,3 +215,73 @@ def test_pack_assemble_and_read_back_without_leaving_the_device(gpu_ctx, oracle)
         for i in (0, 1, n // 2, n - 1):
             rc, got = rd.read(i)
             assert rc == 0 and np.array_equal(got, bufs[i])
+
+
+def test_file_to_device_and_back(gpu_ctx, tmp_path):
+    """zpb_file_read_device / zpb_file_write_device: ranges of a file <-> HBM through the pinned pipeline (several lanes,
+    more than two rounds per lane, a ragged tail), and the error for a file that is too short."""
+    import torch
+    rng = np.random.default_rng(25)
+    size = (72 << 20) + 12345
+    data = rng.integers(0, 256, size, dtype=np.uint8)
+    p = tmp_path / "blob.bin"
+    data.tofile(p)
+    fd = os.open(p, os.O_RDONLY)
+    try:
+        for off, n in ((0, size), (7, 100), (size - 5, 5), (3, (9 << 20) + 1), (11, 0)):
+            d = torch.zeros(n + 16, dtype=torch.uint8, device="cuda")
+            gpu_ctx.file_read_device(fd, off, n, d)
+            got = d.cpu().numpy()
+            assert np.array_equal(got[:n], data[off:off + n]) and (got[n:] == 0).all(), (off, n)
+        with pytest.raises(Exception):
+            gpu_ctx.file_read_device(fd, size - 10, 100, torch.zeros(128, dtype=torch.uint8, device="cuda"))
+    finally:
+        os.close(fd)
+    q = tmp_path / "out.bin"
+    fd = os.open(q, os.O_RDWR | os.O_CREAT)
+    try:
+        d = dev(data)
+        gpu_ctx.file_write_device(fd, 5, size, d)
+        gpu_ctx.file_write_device(fd, 0, 5, d)
+    finally:
+        os.close(fd)
+    back = np.fromfile(q, np.uint8)
+    assert len(back) == size + 5 and np.array_equal(back[5:], data) and np.array_equal(back[:5], data[:5])
+
+
+def test_archive_file_to_verified_plaintext_without_a_host_copy_of_the_archive(gpu_ctx, oracle, tmp_path):
+    """file -> HBM -> directory parse -> unpack + verify: the host sees the 42 fixed bytes, the entry table and the names."""
+    import torch
+    n = 64
+    bufs = [corpus.entry_bytes(i, 100000 + 997 * i) for i in range(n)]
+    frames = [oracle.lz4f_encode_port(b, 0) for b in bufs]
+    hashes = [oracle.xxh3_port(b) for b in bufs]
+    arch = container.assemble([corpus.entry_name(i) for i in range(n)], frames, [len(b) for b in bufs], hashes, [2] * n)
+    p = tmp_path / "a.zpk"
+    arch.tofile(p)
+    fd = os.open(p, os.O_RDONLY)
+    try:
+        d_arch = torch.zeros(len(arch) + 16, dtype=torch.uint8, device="cuda")
+        gpu_ctx.file_read_device(fd, 0, len(arch), d_arch)
+    finally:
+        os.close(fd)
+    res, e, nb = gpu_ctx.archive_open_device(d_arch, len(arch))
+    assert res == 0 and len(e) == n
+    ent = np.zeros(n, zpack_entry_dtype())
+    ent["src_off"], ent["comp_size"], ent["uncomp_size"], ent["hash"], ent["method"] = e["offset"], e["comp_size"], e["uncomp_size"], e["hash"], e["method"]
+    ent["dst_cap"] = e["uncomp_size"]
+    padded = (e["uncomp_size"] + np.uint64(15)) & ~np.uint64(15)
+    ent["dst_off"] = np.concatenate([[0], np.cumsum(padded)[:-1]])
+    out_size = int(padded.sum())
+    d_out = torch.zeros(out_size + 16, dtype=torch.uint8, device="cuda")
+    st, dg = gpu_ctx.unpack_device(d_arch, len(arch), d_out, out_size, ent)
+    assert (st == 0).all() and np.array_equal(dg, np.array(hashes, np.uint64))
+    out = d_out.cpu().numpy()
+    for i, b in enumerate(bufs):
+        o = int(ent["dst_off"][i])
+        assert np.array_equal(out[o:o + len(b)], b)
+
+
+def zpack_entry_dtype():
+    from zpack_b200.lib import Entry
+    return Entry

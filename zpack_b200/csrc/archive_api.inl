@@ -16,11 +16,14 @@ static int arc_upload_entries(zpb_ctx *ctx, const zpb_arc_entry *entries, u64 n,
 
 static int arc_launch_copy(zpb_ctx *ctx, const u8 *d_src, u8 *d_dst, u64 n, u64 nchunks, cudaStream_t s) {
     if (!nchunks) return ZPB_OK;
-    const u32 grid = (u32)std::min<u64>(nchunks, (u64)ctx->sm_count * 8);
-    arc_copy_kernel<<<grid, ARC_COPY_THREADS, 0, s>>>(d_src, d_dst, (const ArcEntry *)ctx->d_arc_e.p, n,
-                                                      (const u64 *)ctx->d_arc_chunk.p, nchunks);
+    if (!ctx->d_arc_work.ensure(nchunks * sizeof(ArcChunk) + 64)) return fail(ctx, ZPB_E_NOMEM, "scratch allocation failed");
+    arc_chunks_kernel<<<(u32)((nchunks + 255) / 256), 256, 0, s>>>((const ArcEntry *)ctx->d_arc_e.p, n, (const u64 *)ctx->d_arc_chunk.p,
+                                                                   nchunks, (ArcChunk *)ctx->d_arc_work.p);
     CK(ctx, cudaGetLastError());
-    ctx->launches += 1;
+    const u32 grid = (u32)std::min<u64>(nchunks, (u64)ctx->sm_count * ctx->arc_ctas_per_sm);
+    arc_copy_kernel<<<grid, ARC_COPY_THREADS, 0, s>>>(d_src, d_dst, (const ArcChunk *)ctx->d_arc_work.p, nchunks);
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 2;
     return ZPB_OK;
 }
 
@@ -185,4 +188,97 @@ extern "C" int zpb_last_archive_ms(const zpb_ctx *ctx, float *ms3) {
     if (!ctx || !ms3) return ZPB_E_ARG;
     for (int k = 0; k < 3; ++k) ms3[k] = ctx->arc_ms[k];
     return ZPB_OK;
+}
+
+// ------------------------------------------------------------------------------------ file <-> device
+// The file side of a device-resident archive: the reference's fread of an entry's bytes / of the directory block
+// (/root/reference/lib/zpack_read.c:298-324, 190-223) and its seek + fwrite of payloads, directory and end record
+// (/root/reference/lib/zpack_common.c:72-81; lib/zpack_write.c:308, 393, 747, 800), with HBM on the other side.  No
+// GPUDirect-Storage driver is assumed: FILE_IO_THREADS host threads pread / pwrite through pinned buffers of
+// FILE_IO_CHUNK bytes, each on its own stream, so that disk (page cache) reads, PCIe copies and the next read overlap.
+#include <unistd.h>
+#define FILE_IO_THREADS 4
+#define FILE_IO_CHUNK (8u << 20)
+
+struct FileIoLane {
+    cudaStream_t s = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    u8 *buf[2] = {nullptr, nullptr};
+    int rc = ZPB_OK;
+    std::string err;
+};
+
+static int file_io_device(zpb_ctx *ctx, int fd, u64 file_off, u64 size, u8 *d_ptr, bool to_device) {
+    if (!ctx || fd < 0 || (!d_ptr && size)) return fail(ctx, ZPB_E_ARG, "null argument");
+    if (size == 0) return ZPB_OK;
+    if (file_off + size < file_off) return fail(ctx, ZPB_E_ARG, "offset overflow");
+    const u64 nchunk = (size + FILE_IO_CHUNK - 1) / FILE_IO_CHUNK;
+    const int nlane = (int)std::min<u64>(FILE_IO_THREADS, nchunk);
+    std::vector<FileIoLane> lanes(nlane);
+    auto work = [&](int k) {
+        FileIoLane &L = lanes[k];
+        auto bad = [&](int code, const std::string &m) { L.rc = code; L.err = m; };
+        if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking) != cudaSuccess)
+            return bad(ZPB_E_CUDA, "stream creation failed");
+        for (int b = 0; b < 2; ++b)
+            if (cudaMallocHost((void **)&L.buf[b], FILE_IO_CHUNK) != cudaSuccess || cudaEventCreateWithFlags(&L.ev[b], cudaEventDisableTiming) != cudaSuccess)
+                return bad(ZPB_E_NOMEM, "pinned buffer allocation failed");
+        u64 round = 0;
+        for (u64 c = (u64)k; c < nchunk && L.rc == ZPB_OK; c += (u64)nlane, ++round) {
+            const int b = (int)(round & 1);
+            const u64 off = c * FILE_IO_CHUNK, len = std::min<u64>(FILE_IO_CHUNK, size - off);
+            if (round >= 2 && cudaEventSynchronize(L.ev[b]) != cudaSuccess) return bad(ZPB_E_CUDA, "event wait failed");
+            if (to_device) {
+                for (u64 got = 0; got < len;) {
+                    const ssize_t r = pread(fd, L.buf[b] + got, len - got, (off_t)(file_off + off + got));
+                    if (r <= 0) return bad(ZPB_E_IO, r == 0 ? "file shorter than the requested range" : "pread failed");
+                    got += (u64)r;
+                }
+                if (cudaMemcpyAsync(d_ptr + off, L.buf[b], len, cudaMemcpyHostToDevice, L.s) != cudaSuccess) return bad(ZPB_E_CUDA, "H2D copy failed");
+                cudaEventRecord(L.ev[b], L.s);
+            } else {
+                // two chunks in flight: the copy of this round's chunk is issued, the previous round's chunk is written out
+                if (cudaMemcpyAsync(L.buf[b], d_ptr + off, len, cudaMemcpyDeviceToHost, L.s) != cudaSuccess) return bad(ZPB_E_CUDA, "D2H copy failed");
+                cudaEventRecord(L.ev[b], L.s);
+                if (round >= 1) {
+                    const u64 poff = (c - (u64)nlane) * FILE_IO_CHUNK, plen = std::min<u64>(FILE_IO_CHUNK, size - poff);
+                    if (cudaEventSynchronize(L.ev[b ^ 1]) != cudaSuccess) return bad(ZPB_E_CUDA, "event wait failed");
+                    for (u64 put = 0; put < plen;) {
+                        const ssize_t r = pwrite(fd, L.buf[b ^ 1] + put, plen - put, (off_t)(file_off + poff + put));
+                        if (r <= 0) return bad(ZPB_E_IO, "pwrite failed");
+                        put += (u64)r;
+                    }
+                }
+            }
+        }
+        if (L.rc == ZPB_OK && !to_device && round >= 1) {          // the lane's last chunk
+            const u64 c = (u64)k + (round - 1) * (u64)nlane, off = c * FILE_IO_CHUNK, len = std::min<u64>(FILE_IO_CHUNK, size - off);
+            const int b = (int)((round - 1) & 1);
+            if (cudaEventSynchronize(L.ev[b]) != cudaSuccess) return bad(ZPB_E_CUDA, "event wait failed");
+            for (u64 put = 0; put < len;) {
+                const ssize_t r = pwrite(fd, L.buf[b] + put, len - put, (off_t)(file_off + off + put));
+                if (r <= 0) return bad(ZPB_E_IO, "pwrite failed");
+                put += (u64)r;
+            }
+        }
+        if (L.s && cudaStreamSynchronize(L.s) != cudaSuccess && L.rc == ZPB_OK) bad(ZPB_E_CUDA, "stream synchronize failed");
+    };
+    std::vector<std::thread> th;
+    for (int k = 1; k < nlane; ++k) th.emplace_back(work, k);
+    work(0);
+    for (auto &t : th) t.join();
+    int rc = ZPB_OK;
+    for (FileIoLane &L : lanes) {
+        if (L.rc != ZPB_OK && rc == ZPB_OK) { rc = L.rc; ctx->err = L.err; g_last_error = L.err; }
+        if (L.s) { cudaStreamSynchronize(L.s); cudaStreamDestroy(L.s); }
+        for (int b = 0; b < 2; ++b) { if (L.ev[b]) cudaEventDestroy(L.ev[b]); if (L.buf[b]) cudaFreeHost(L.buf[b]); }
+    }
+    return rc;
+}
+
+extern "C" int zpb_file_read_device(zpb_ctx *ctx, int fd, uint64_t file_off, uint64_t size, uint8_t *d_dst) {
+    return file_io_device(ctx, fd, file_off, size, d_dst, true);
+}
+extern "C" int zpb_file_write_device(zpb_ctx *ctx, int fd, uint64_t file_off, uint64_t size, const uint8_t *d_src) {
+    return file_io_device(ctx, fd, file_off, size, const_cast<u8 *>(d_src), false);
 }

@@ -6,6 +6,7 @@
 //                       zpack_write_files / ZPACK_ADD_OFFSET_AND_SIZE, /root/reference/lib/zpack_write.c:280-343), the
 //                       position of every CDR record (zpack_write_cdr_ex's block size loop, zpack_write.c:720-736) and
 //                       the first 64 KB copy chunk of every entry
+//   arc_chunks_kernel   thread per 64 KB copy chunk: its entry (binary search over the chunk table) and byte ranges
 //   arc_copy_kernel     the byte moves of zpack_write_files_from_archive (zpack_write.c:345-428: one memcpy per entry)
 //                       as 64 KB chunks dealt round-robin to the CTAs; 16-byte stores, the source realigned in registers
 //   arc_cdr_kernel      zpack_write_cdr_memory + zpack_write_eocdr (+ the archive header) (zpack_write.c:687-711, 778-785)
@@ -114,30 +115,55 @@ ZPB_DEVINL void arc_copy_span(u8 *dst, const u8 *src, u32 len) {
         nvec = len >= 32 ? (len - 16) >> 4 : 0;
         const u8 *sa = src - rel;
         const u32 w = rel >> 2, b = (rel & 3u) * 8u;
-        for (u32 v = tid; v < nvec; v += 2 * nt) {
-            uint4 A[2], B[2];
+        for (u32 v = tid; v < nvec; v += 4 * nt) {
+            uint4 A[4], B[4];
 #pragma unroll
-            for (u32 k = 0; k < 2; ++k) if (v + k * nt < nvec) {
+            for (u32 k = 0; k < 4; ++k) if (v + k * nt < nvec) {
                 A[k] = ldg128(sa + 16 * (size_t)(v + k * nt));
                 B[k] = ldg128(sa + 16 * (size_t)(v + k * nt) + 16);
             }
 #pragma unroll
-            for (u32 k = 0; k < 2; ++k) if (v + k * nt < nvec) stg128(dst + 16 * (size_t)(v + k * nt), arc_realign(A[k], B[k], w, b));
+            for (u32 k = 0; k < 4; ++k) if (v + k * nt < nvec) stg128(dst + 16 * (size_t)(v + k * nt), arc_realign(A[k], B[k], w, b));
         }
     }
     for (u32 i = (nvec << 4) + tid; i < len; i += nt) dst[i] = src[i];
 }
 
-ZPB_DEVINL void arc_copy_body(const u8 *src, u8 *dst, const ArcEntry *e, u64 n, const u64 *chunk_first, u64 nchunks) {
-    for (u64 c = blockIdx.x; c < nchunks; c += gridDim.x) {
-        u64 lo = 0, hi = n;                       // chunk_first[lo] <= c < chunk_first[hi]; empty entries are skipped
-        while (hi - lo > 1) {
-            const u64 mid = (lo + hi) >> 1;
-            if (chunk_first[mid] <= c) lo = mid; else hi = mid;
-        }
-        const u64 off = (c - chunk_first[lo]) << ARC_CHUNK_LOG;
-        const u64 left = e[lo].comp_size - off;
-        arc_copy_span(dst + e[lo].offset + off, src + e[lo].src_off + off, left < ARC_CHUNK ? (u32)left : ARC_CHUNK);
+struct ArcChunk { u64 src_off, dst_off; u32 len, entry; u64 pad; };   // one copy work item, 32 bytes
+static_assert(sizeof(ArcChunk) == 32, "chunk descriptor");
+
+// thread per chunk: which entry it belongs to (binary search over the chunk table — 16 dependent loads that the copy CTAs
+// would otherwise each pay in front of a 2.5 us copy) and the byte ranges it moves
+ZPB_DEVINL void arc_chunks_body(const ArcEntry *e, u64 n, const u64 *chunk_first, u64 nchunks, ArcChunk *out) {
+    const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    u64 lo = 0, hi = n;                           // chunk_first[lo] <= c < chunk_first[hi]; empty entries are skipped
+    while (hi - lo > 1) {
+        const u64 mid = (lo + hi) >> 1;
+        if (chunk_first[mid] <= c) lo = mid; else hi = mid;
+    }
+    const u64 off = (c - chunk_first[lo]) << ARC_CHUNK_LOG;
+    const u64 left = e[lo].comp_size - off;
+    uint4 *o = reinterpret_cast<uint4 *>(out + c);
+    const u64 so = e[lo].src_off + off, d = e[lo].offset + off;
+    stg128(o, make_uint4((u32)so, (u32)(so >> 32), (u32)d, (u32)(d >> 32)));
+    stg128(o + 1, make_uint4(left < ARC_CHUNK ? (u32)left : ARC_CHUNK, (u32)lo, 0u, 0u));
+}
+
+ZPB_DEVINL void arc_copy_body(const u8 *src, u8 *dst, const ArcChunk *chunks, u64 nchunks) {
+    u64 c = blockIdx.x;
+    if (c >= nchunks) return;
+    uint4 a = ldg128(chunks + c);
+    u32 len = chunks[c].len;
+    for (;;) {                                    // the next descriptor is fetched while this chunk moves
+        const u64 cn = c + gridDim.x;
+        const bool more = cn < nchunks;
+        uint4 an = a;
+        u32 lenn = 0;
+        if (more) { an = ldg128(chunks + cn); lenn = chunks[cn].len; }
+        arc_copy_span(dst + ((u64)a.z | ((u64)a.w << 32)), src + ((u64)a.x | ((u64)a.y << 32)), len);
+        if (!more) break;
+        a = an; len = lenn; c = cn;
     }
 }
 
@@ -264,10 +290,12 @@ __global__ void __launch_bounds__(ARC_SCAN_THREADS)
 arc_layout_kernel(ArcEntry *e, u64 n, u64 base, u32 assign, u64 *rec_off, u64 *chunk_first, u64 *totals) {
     arc_layout_body(e, n, base, assign, rec_off, chunk_first, totals);
 }
-__global__ void __launch_bounds__(ARC_COPY_THREADS)
-arc_copy_kernel(const u8 *__restrict__ src, u8 *__restrict__ dst, const ArcEntry *__restrict__ e, u64 n,
-                const u64 *__restrict__ chunk_first, u64 nchunks) {
-    arc_copy_body(src, dst, e, n, chunk_first, nchunks);
+__global__ void __launch_bounds__(ARC_COPY_THREADS, 4)
+arc_copy_kernel(const u8 *__restrict__ src, u8 *__restrict__ dst, const ArcChunk *__restrict__ chunks, u64 nchunks) {
+    arc_copy_body(src, dst, chunks, nchunks);
+}
+__global__ void arc_chunks_kernel(const ArcEntry *e, u64 n, const u64 *chunk_first, u64 nchunks, ArcChunk *out) {
+    arc_chunks_body(e, n, chunk_first, nchunks, out);
 }
 __global__ void arc_cdr_kernel(u8 *arch, const ArcEntry *e, u64 n, const u8 *names, const u64 *rec_off, u64 cdr_off,
                                u64 block_size, u32 write_header) {

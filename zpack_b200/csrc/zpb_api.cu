@@ -97,7 +97,8 @@ struct zpb_ctx {
     int host_workers = 6;              // ZPB_HOST_WORKERS (tools/e2e_sweep.py: profiles/r1_e2e_sweep.jsonl)
     u64 host_chunk_bytes = 256u << 20; // decoded bytes per pipeline chunk (ZPB_HOST_CHUNK_MB)
     // device-resident container operations (archive_api.inl): entry table, record offsets, chunk table, totals, names; CDR walk tables
-    DevBuf d_arc_e, d_arc_rec, d_arc_chunk, d_arc_tot, d_arc_names, d_cdr_jump, d_cdr_cnt, d_cdr_j2, d_cdr_anchor;
+    DevBuf d_arc_e, d_arc_rec, d_arc_chunk, d_arc_work, d_arc_tot, d_arc_names, d_cdr_jump, d_cdr_cnt, d_cdr_j2, d_cdr_anchor;
+    int arc_ctas_per_sm = 8;           // resident CTAs of the copy kernel (ZPB_ARC_CTAS)
     float arc_ms[3] = {0, 0, 0};       // layout + directory kernels, copy kernel, open kernels of the last call
 };
 
@@ -153,6 +154,7 @@ extern "C" zpb_ctx *zpb_create(int device) {
     }
     if (const char *s = getenv("ZPB_CTAS_PER_SM")) ctx->ctas_per_sm = atoi(s);
     if (const char *s = getenv("ZPB_FAST")) ctx->fast = atoi(s);
+    if (const char *s = getenv("ZPB_ARC_CTAS")) ctx->arc_ctas_per_sm = std::max(1, std::min(8, atoi(s)));
     if (const char *s = getenv("ZPB_HOST_WORKERS")) ctx->host_workers = std::max(1, std::min(8, atoi(s)));
     if (const char *s = getenv("ZPB_HOST_CHUNK_MB")) ctx->host_chunk_bytes = (u64)std::max(1, atoi(s)) << 20;
     for (auto &ev : ctx->evs)
@@ -213,7 +215,7 @@ extern "C" void zpb_destroy(zpb_ctx *ctx) {
     ctx->d_zslot.release(); ctx->d_zseq.release(); ctx->d_zmeta.release(); ctx->d_zelit.release(); ctx->d_zhuf.release(); ctx->d_ztabs.release();
     for (cudaEvent_t e : ctx->pack_evs) cudaEventDestroy(e);
     ctx->d_partials.release(); ctx->d_acc.release();
-    ctx->d_arc_e.release(); ctx->d_arc_rec.release(); ctx->d_arc_chunk.release(); ctx->d_arc_tot.release(); ctx->d_arc_names.release();
+    ctx->d_arc_e.release(); ctx->d_arc_rec.release(); ctx->d_arc_chunk.release(); ctx->d_arc_work.release(); ctx->d_arc_tot.release(); ctx->d_arc_names.release();
     ctx->d_cdr_jump.release(); ctx->d_cdr_cnt.release(); ctx->d_cdr_j2.release(); ctx->d_cdr_anchor.release();
     for (auto &ev : ctx->evs) if (ev) cudaEventDestroy(ev);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

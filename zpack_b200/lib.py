@@ -60,6 +60,7 @@ EXPORTS = [
     "zpb_lz4_frame_index", "zpb_unpack_blocks_device", "zpb_blocks_digest", "zpb_last_chain_ms",
     "zpb_unpack_entry_blocks_host", "zpb_device_count",
     "zpb_archive_open_device", "zpb_archive_build_device", "zpb_copy_entries_device", "zpb_last_archive_ms",
+    "zpb_file_read_device", "zpb_file_write_device",
 ]
 
 
@@ -122,6 +123,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.zpb_archive_build_device.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, u64, u64p, vp]
     lib.zpb_copy_entries_device.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp]
     lib.zpb_last_archive_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.zpb_file_read_device.argtypes = [vp, C.c_int, u64, u64, vp]
+    lib.zpb_file_write_device.argtypes = [vp, C.c_int, u64, u64, vp]
     lib.zpb_host_alloc.restype = vp
     lib.zpb_host_alloc.argtypes = [u64]
     lib.zpb_host_free.argtypes = [vp]
@@ -388,6 +391,12 @@ class Context:
     def copy_entries_device(self, d_src, src_size: int, d_dst, dst_size: int, entries: np.ndarray, stream: int = 0):
         assert entries.dtype == ArcEntry and entries.flags.c_contiguous
         self._check(self.lib.zpb_copy_entries_device(self.h, _ptr(d_src), src_size, _ptr(d_dst), dst_size, _ptr(entries), len(entries), stream))
+
+    def file_read_device(self, fd: int, file_off: int, size: int, d_dst):
+        self._check(self.lib.zpb_file_read_device(self.h, fd, file_off, size, _ptr(d_dst)))
+
+    def file_write_device(self, fd: int, file_off: int, size: int, d_src):
+        self._check(self.lib.zpb_file_write_device(self.h, fd, file_off, size, _ptr(d_src)))
 
     def last_archive_ms(self):
         ms = (C.c_float * 3)()
