@@ -935,6 +935,65 @@ NCU_TRAFFIC_RATIO = {
 }
 
 
+def archive_block(n=16384):
+    """The container level on the device for the `configs` block: archive build from pack-shaped
+    slots (offset table + directory kernels, payload copy kernel), directory parse, archive-to-archive copy of every second
+    entry.  Kernel times are the library's CUDA events around its own launches; the gate: the directory bytes equal the host
+    mirror's, the parsed table equals the table that was built, sampled payloads equal their slots."""
+    import torch
+    import zpack_b200
+    from zpack_b200 import container
+    from zpack_b200.lib import ArcEntry
+    hbm, _ = peaks()
+    ctx = zpack_b200.Context(int(os.environ.get("LOCAL_RANK", "0")))
+    rng = np.random.default_rng(3)
+    comp = rng.integers(30000, 84000, n).astype(np.uint64)
+    names = [f"dir{i % 64:02d}/entry_{i:07d}.bin" for i in range(n)]
+    blob = np.frombuffer("".join(names).encode(), np.uint8)
+    e = np.zeros(n, ArcEntry)
+    e["comp_size"], e["uncomp_size"], e["hash"], e["method"] = comp, ENTRY_SIZE, rng.integers(0, 2**63, n).astype(np.uint64), 2
+    e["name_len"] = [len(x) for x in names]
+    e["name_off"] = np.concatenate([[0], np.cumsum(e["name_len"])[:-1]])
+    cap = (comp + np.uint64(32768 + 15)) & ~np.uint64(15)
+    e["src_off"] = np.concatenate([[0], np.cumsum(cap)[:-1]])
+    src_size = int(cap.sum())
+    d_src = torch.randint(0, 256, (src_size,), dtype=torch.uint8, device="cuda")
+    total = 10 + int(comp.sum()) + 20 + 35 * n + len(blob) + 12
+    d_arch = torch.empty(total + 64, dtype=torch.uint8, device="cuda")
+    best = None
+    for it in range(5):
+        size = ctx.archive_build_device(d_src, src_size, e, blob, d_arch, total + 64)
+        ms = ctx.last_archive_ms()
+        if it >= 2 and (best is None or ms[1] < best[1]):
+            best = ms
+    assert size == total
+    cdr_off = 10 + int(comp.sum())
+    want_cdr = container.cdr_bytes(names, e["offset"], comp, e["uncomp_size"], e["hash"], e["method"])
+    got_cdr = d_arch[cdr_off:cdr_off + len(want_cdr)].cpu().numpy()
+    assert bytes(got_cdr) == want_cdr, "directory differs from the host mirror"
+    for i in rng.integers(0, n, 48):
+        a, b, k = int(e["offset"][i]), int(e["src_off"][i]), int(comp[i])
+        assert torch.equal(d_arch[a:a + k], d_src[b:b + k]), "payload differs from its slot"
+    for it in range(3):
+        res, eo, nb = ctx.archive_open_device(d_arch, size)
+    open_ms = ctx.last_archive_ms()[2]
+    assert res == 0 and np.array_equal(eo["hash"], e["hash"]) and np.array_equal(eo["offset"], e["offset"])
+    sub = np.ascontiguousarray(eo[::2])
+    d_new = torch.empty(total + 64, dtype=torch.uint8, device="cuda")
+    for it in range(3):
+        ctx.archive_build_device(d_arch, size, sub, nb, d_new, total + 64)
+    a2a = ctx.last_archive_ms()
+    moved, moved2 = 2 * int(comp.sum()), 2 * int(sub["comp_size"].sum())
+    launches = ctx.launch_count
+    ctx.close()
+    return {"workload": f"device-resident archive of {n} entries ({int(comp.sum()) / 1e9:.2f} GB of payload): build from pack slots, "
+                        "directory parse, archive-to-archive copy of every second entry",
+            "metric": "archive_copy_read_plus_write_GBps", "value": round(moved / best[1] / 1e6, 1), "unit": "GB/s",
+            "kernel": "arc_copy_kernel", "roofline_frac": round(moved / best[1] / 1e6 / hbm, 3),
+            "copy_ms": round(best[1], 4), "offset_table_and_directory_ms": round(best[0], 4), "directory_parse_ms": round(open_ms, 4),
+            "archive_to_archive_GBps": round(moved2 / a2a[1] / 1e6, 1), "gpu_launches": int(launches)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -989,6 +1048,10 @@ def main():
                           **({"ratio_gpu": r["config"].get("ratio_gpu")} if isinstance(r.get("config"), dict) and "ratio_gpu" in r["config"] else {})}
         except Exception as ex:   # a configuration that cannot run here (e.g. no oracle/_ref for the zstd archive) says so
             block[key] = {"workload": what, "unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+    try:
+        block["archive"] = archive_block()
+    except Exception as ex:
+        block["archive"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
     line["configs"] = block
     print(json.dumps(line))
 

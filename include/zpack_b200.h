@@ -269,7 +269,7 @@ int zpb_archive_build_device(zpb_ctx *ctx, const uint8_t *d_src, uint64_t src_si
  * must not overlap in d_dst, and d_dst must not overlap d_src. */
 int zpb_copy_entries_device(zpb_ctx *ctx, const uint8_t *d_src, uint64_t src_size, uint8_t *d_dst, uint64_t dst_size,
                             const zpb_arc_entry *entries, uint64_t n, void *stream);
-/* device time (ms) of the last call's kernels: [0] offset table + directory, [1] payload copy, [2] directory parse */
+/* device time (ms) of the last call's kernels: [0] offset table + directory + copy work items, [1] the payload copy kernel, [2] directory parse */
 int zpb_last_archive_ms(const zpb_ctx *ctx, float *ms3);
 /* File <-> HBM for a device-resident archive: bytes [file_off, file_off + size) of the open file descriptor fd to / from
  * device memory, read / written by several host threads through pinned buffers on their own streams (pread, H2D and the next

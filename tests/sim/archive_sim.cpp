@@ -14,7 +14,7 @@ extern "C" int sim_archive_build(const uint8_t *src, ArcEntry *e, uint64_t n, co
                                  uint64_t cdr_off, uint64_t block, int scan_threads, int grid, uint64_t seed, uint64_t *totals) {
     std::vector<u64> rec(n + 1), chunk(n + 2);
     u64 *rp = rec.data(), *cp = chunk.data();
-    sim::launch(sim::Dim3(1), sim::Dim3((unsigned)scan_threads), 32 * 24, [&] {
+    sim::launch(sim::Dim3(1), sim::Dim3((unsigned)scan_threads), 33 * 24, [&] {
         arc_layout_body(e, n, ARC_DATA_START, with_cdr ? 1u : 0u, rp, cp, totals);
     }, seed);
     if (with_cdr)

@@ -14,16 +14,22 @@ static int arc_upload_entries(zpb_ctx *ctx, const zpb_arc_entry *entries, u64 n,
     return ZPB_OK;
 }
 
-static int arc_launch_copy(zpb_ctx *ctx, const u8 *d_src, u8 *d_dst, u64 n, u64 nchunks, cudaStream_t s) {
+// the copy's work items (before the event that starts the copy kernel's interval), then the copy itself
+static int arc_launch_chunks(zpb_ctx *ctx, u64 n, u64 nchunks, cudaStream_t s) {
     if (!nchunks) return ZPB_OK;
     if (!ctx->d_arc_work.ensure(nchunks * sizeof(ArcChunk) + 64)) return fail(ctx, ZPB_E_NOMEM, "scratch allocation failed");
     arc_chunks_kernel<<<(u32)((nchunks + 255) / 256), 256, 0, s>>>((const ArcEntry *)ctx->d_arc_e.p, n, (const u64 *)ctx->d_arc_chunk.p,
                                                                    nchunks, (ArcChunk *)ctx->d_arc_work.p);
     CK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return ZPB_OK;
+}
+static int arc_launch_copy(zpb_ctx *ctx, const u8 *d_src, u8 *d_dst, u64 nchunks, cudaStream_t s) {
+    if (!nchunks) return ZPB_OK;
     const u32 grid = (u32)std::min<u64>(nchunks, (u64)ctx->sm_count * ctx->arc_ctas_per_sm);
     arc_copy_kernel<<<grid, ARC_COPY_THREADS, 0, s>>>(d_src, d_dst, (const ArcChunk *)ctx->d_arc_work.p, nchunks);
     CK(ctx, cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches += 1;
     return ZPB_OK;
 }
 
@@ -46,12 +52,13 @@ extern "C" int zpb_copy_entries_device(zpb_ctx *ctx, const uint8_t *d_src, uint6
     int rc = arc_upload_entries(ctx, entries, n, s);
     if (rc) return rc;
     CK(ctx, cudaEventRecord(ctx->evs[0], s));
-    arc_layout_kernel<<<1, ARC_SCAN_THREADS, 32 * 24, s>>>((ArcEntry *)ctx->d_arc_e.p, n, 0, 0u, (u64 *)ctx->d_arc_rec.p,
+    arc_layout_kernel<<<1, ARC_SCAN_THREADS, 33 * 24, s>>>((ArcEntry *)ctx->d_arc_e.p, n, 0, 0u, (u64 *)ctx->d_arc_rec.p,
                                                           (u64 *)ctx->d_arc_chunk.p, (u64 *)ctx->d_arc_tot.p);
     CK(ctx, cudaGetLastError());
     ctx->launches += 1;
+    if ((rc = arc_launch_chunks(ctx, n, nchunks, s))) return rc;
     CK(ctx, cudaEventRecord(ctx->evs[1], s));
-    if ((rc = arc_launch_copy(ctx, d_src, d_dst, n, nchunks, s))) return rc;
+    if ((rc = arc_launch_copy(ctx, d_src, d_dst, nchunks, s))) return rc;
     CK(ctx, cudaEventRecord(ctx->evs[2], s));
     CK(ctx, cudaStreamSynchronize(s));
     CK(ctx, cudaEventElapsedTime(&ctx->arc_ms[0], ctx->evs[0], ctx->evs[1]));
@@ -87,7 +94,7 @@ extern "C" int zpb_archive_build_device(zpb_ctx *ctx, const uint8_t *d_src, uint
         CK(ctx, cudaMemcpyAsync(ctx->d_arc_names.p, ctx->h_bounce.p, names_size, cudaMemcpyHostToDevice, s));
     }
     CK(ctx, cudaEventRecord(ctx->evs[0], s));
-    arc_layout_kernel<<<1, ARC_SCAN_THREADS, 32 * 24, s>>>((ArcEntry *)ctx->d_arc_e.p, n, ARC_DATA_START, 1u, (u64 *)ctx->d_arc_rec.p,
+    arc_layout_kernel<<<1, ARC_SCAN_THREADS, 33 * 24, s>>>((ArcEntry *)ctx->d_arc_e.p, n, ARC_DATA_START, 1u, (u64 *)ctx->d_arc_rec.p,
                                                           (u64 *)ctx->d_arc_chunk.p, (u64 *)ctx->d_arc_tot.p);
     CK(ctx, cudaGetLastError());
     const u32 cgrid = (u32)std::max<u64>(1, std::min<u64>((n + 255) / 256, (u64)ctx->sm_count * 8));
@@ -95,8 +102,9 @@ extern "C" int zpb_archive_build_device(zpb_ctx *ctx, const uint8_t *d_src, uint
                                          (const u64 *)ctx->d_arc_rec.p, cdr_off, block, 1u);
     CK(ctx, cudaGetLastError());
     ctx->launches += 2;
+    if ((rc = arc_launch_chunks(ctx, n, nchunks, s))) return rc;
     CK(ctx, cudaEventRecord(ctx->evs[1], s));
-    if ((rc = arc_launch_copy(ctx, d_src, d_archive, n, nchunks, s))) return rc;
+    if ((rc = arc_launch_copy(ctx, d_src, d_archive, nchunks, s))) return rc;
     CK(ctx, cudaEventRecord(ctx->evs[2], s));
     if (n) CK(ctx, cudaMemcpyAsync(ctx->h_stage.p, ctx->d_arc_e.p, (size_t)n * sizeof(ArcEntry), cudaMemcpyDeviceToHost, s));
     CK(ctx, cudaStreamSynchronize(s));

@@ -49,14 +49,19 @@ ZPB_DEVINL void arc_st64(u8 *p, u64 v) { arc_st32(p, (u32)v); arc_st32(p + 4, (u
 // ---- layout: one CTA, three running sums.  totals: Σ comp_size, Σ (35 + name_len), Σ chunks.
 ZPB_DEVINL void arc_layout_body(ArcEntry *e, u64 n, u64 base, u32 assign, u64 *rec_off, u64 *chunk_first, u64 *totals) {
     ZPB_DYN_SMEM(smem);
-    const u32 sm = smem_window(smem);            // 32 warps x 3 sums x 8 bytes
+    const u32 sm = smem_window(smem);            // (32 warps + the CTA) x 3 sums x 8 bytes
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nw = blockDim.x >> 5;
     u64 c0 = 0, c1 = 0, c2 = 0;
-    for (u64 i0 = 0; i0 < n; i0 += blockDim.x) {
-        const u64 i = i0 + tid;
-        u64 a = 0, b = 0, c = 0;
-        if (i < n) { a = e[i].comp_size; b = ARC_FIXED + (u64)e[i].name_len; c = (a + ARC_CHUNK - 1) >> ARC_CHUNK_LOG; }
-        u64 sa = a, sb = b, sc = c;
+    for (u64 i0 = 0; i0 < n; i0 += (u64)blockDim.x * 4) {     // four consecutive entries per thread: their loads overlap
+        const u64 i = i0 + (u64)tid * 4;
+        u64 a[4], b[4], c[4];
+#pragma unroll
+        for (u32 j = 0; j < 4; ++j) {
+            a[j] = b[j] = c[j] = 0;
+            if (i + j < n) { a[j] = e[i + j].comp_size; b[j] = ARC_FIXED + (u64)e[i + j].name_len; c[j] = (a[j] + ARC_CHUNK - 1) >> ARC_CHUNK_LOG; }
+        }
+        const u64 ma = a[0] + a[1] + a[2] + a[3], mb = b[0] + b[1] + b[2] + b[3], mc = c[0] + c[1] + c[2] + c[3];
+        u64 sa = ma, sb = mb, sc = mc;
         for (u32 d = 1; d < 32; d <<= 1) {
             const u64 ta = __shfl_up_sync(0xffffffffu, sa, d), tb = __shfl_up_sync(0xffffffffu, sb, d),
                       tc = __shfl_up_sync(0xffffffffu, sc, d);
@@ -64,17 +69,31 @@ ZPB_DEVINL void arc_layout_body(ArcEntry *e, u64 n, u64 base, u32 assign, u64 *r
         }
         if (lane == 31) { arc_sts64(sm + warp * 24, sa); arc_sts64(sm + warp * 24 + 8, sb); arc_sts64(sm + warp * 24 + 16, sc); }
         __syncthreads();
-        u64 pa = 0, pb = 0, pc = 0, ta = 0, tb = 0, tc = 0;
-        for (u32 w = 0; w < nw; ++w) {
-            const u64 x = arc_lds64(sm + w * 24), y = arc_lds64(sm + w * 24 + 8), z = arc_lds64(sm + w * 24 + 16);
-            if (w < warp) { pa += x; pb += y; pc += z; }
-            ta += x; tb += y; tc += z;
+        if (warp == 0) {                         // the warps' totals: scanned by one warp, exclusive prefixes back in place
+            u64 x = 0, y = 0, z = 0;
+            if (lane < nw) { x = arc_lds64(sm + lane * 24); y = arc_lds64(sm + lane * 24 + 8); z = arc_lds64(sm + lane * 24 + 16); }
+            u64 sx = x, sy = y, sz = z;
+            for (u32 d = 1; d < 32; d <<= 1) {
+                const u64 tx = __shfl_up_sync(0xffffffffu, sx, d), ty = __shfl_up_sync(0xffffffffu, sy, d),
+                          tz = __shfl_up_sync(0xffffffffu, sz, d);
+                if (lane >= d) { sx += tx; sy += ty; sz += tz; }
+            }
+            if (lane < nw) { arc_sts64(sm + lane * 24, sx - x); arc_sts64(sm + lane * 24 + 8, sy - y); arc_sts64(sm + lane * 24 + 16, sz - z); }
+            if (lane == 31) { arc_sts64(sm + 32 * 24, sx); arc_sts64(sm + 32 * 24 + 8, sy); arc_sts64(sm + 32 * 24 + 16, sz); }
         }
         __syncthreads();
-        if (i < n) {
-            if (assign) e[i].offset = base + c0 + pa + sa - a;
-            rec_off[i] = c1 + pb + sb - b;
-            chunk_first[i] = c2 + pc + sc - c;
+        const u64 pa = arc_lds64(sm + warp * 24), pb = arc_lds64(sm + warp * 24 + 8), pc = arc_lds64(sm + warp * 24 + 16);
+        const u64 ta = arc_lds64(sm + 32 * 24), tb = arc_lds64(sm + 32 * 24 + 8), tc = arc_lds64(sm + 32 * 24 + 16);
+        __syncthreads();
+        u64 ra = c0 + pa + sa - ma, rb = c1 + pb + sb - mb, rc = c2 + pc + sc - mc;
+#pragma unroll
+        for (u32 j = 0; j < 4; ++j) {
+            if (i + j < n) {
+                if (assign) e[i + j].offset = base + ra;
+                rec_off[i + j] = rb;
+                chunk_first[i + j] = rc;
+            }
+            ra += a[j]; rb += b[j]; rc += c[j];
         }
         c0 += ta; c1 += tb; c2 += tc;
     }
