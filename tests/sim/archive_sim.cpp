@@ -24,7 +24,11 @@ extern "C" int sim_archive_build(const uint8_t *src, ArcEntry *e, uint64_t n, co
         std::vector<ArcChunk> work(nchunks);
         ArcChunk *wp = work.data();
         sim::launch(sim::Dim3((unsigned)((nchunks + 31) / 32)), sim::Dim3(32), 0, [&] { arc_chunks_body(e, n, cp, nchunks, wp); }, seed);
-        sim::launch(sim::Dim3((unsigned)grid), sim::Dim3(64), 0, [&] { arc_copy_body(src, dst, wp, nchunks); }, seed);
+        unsigned long long *next = (seed & 2) ? (unsigned long long *)(totals + 4) : nullptr;
+        const u32 mask = (seed & 4) ? 127u : 15u;
+        sim::launch(sim::Dim3((unsigned)grid), sim::Dim3(seed & 4 ? 128 : 64), 16, [&] {
+            if (seed & 1) arc_copy_body<4>(src, dst, wp, nchunks, next, mask); else arc_copy_body<8>(src, dst, wp, nchunks, next, mask);
+        }, seed);
     }
     return 0;
 }

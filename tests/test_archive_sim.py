@@ -74,7 +74,7 @@ def sim_build(sim, e, src, blob, seed=1, grid=3, scan_threads=128):
     cdr_off = 10 + data
     total = cdr_off + 20 + block + 12
     out, keep = aligned(total, 0)
-    totals = np.zeros(3, np.uint64)
+    totals = np.zeros(8, np.uint64)
     sim.sim_archive_build(src.ctypes.data, e.ctypes.data, n, blob.ctypes.data if len(blob) else None, out.ctypes.data, 1, cdr_off, block,
                           scan_threads, grid, seed, totals.ctypes.data)
     assert int(totals[0]) == data and int(totals[1]) == block
@@ -89,9 +89,10 @@ def test_build_equals_the_host_mirror(sim):
     name_lens = [int(k) for k in rng.integers(1, 40, len(SIZES))]
     name_lens[3], name_lens[7] = 0, 700
     payloads, names, e, src, keep, blob = make_case(rng, SIZES, name_lens)
-    out = sim_build(sim, e, src, blob)
     ref = container.assemble(names, payloads, e["uncomp_size"], e["hash"], e["method"])
-    assert len(out) == len(ref) and np.array_equal(out, ref)
+    for seed in range(1, 8):       # bits of the seed pick the copy variant in archive_sim.cpp: vectors in flight, deal, head grid
+        out = sim_build(sim, e, src, blob, seed=seed)
+        assert len(out) == len(ref) and np.array_equal(out, ref), seed
     assert np.array_equal(e["offset"], container.parse(ref).offset)
 
 
@@ -117,7 +118,7 @@ def test_copy_entries_to_given_offsets(sim):
         pos += sizes[i] + 5
     dst, keep2 = aligned(pos + 8)
     dst[:] = 0xEE
-    totals = np.zeros(3, np.uint64)
+    totals = np.zeros(8, np.uint64)
     sim.sim_archive_build(src.ctypes.data, e.ctypes.data, len(e), None, dst.ctypes.data, 0, 0, 0, 64, 2, 3, totals.ctypes.data)
     want = np.full(len(dst), 0xEE, np.uint8)
     for i in order:

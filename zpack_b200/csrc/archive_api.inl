@@ -27,7 +27,9 @@ static int arc_launch_chunks(zpb_ctx *ctx, u64 n, u64 nchunks, cudaStream_t s) {
 static int arc_launch_copy(zpb_ctx *ctx, const u8 *d_src, u8 *d_dst, u64 nchunks, cudaStream_t s) {
     if (!nchunks) return ZPB_OK;
     const u32 grid = (u32)std::min<u64>(nchunks, (u64)ctx->sm_count * ctx->arc_ctas_per_sm);
-    arc_copy_kernel<<<grid, ARC_COPY_THREADS, 0, s>>>(d_src, d_dst, (const ArcChunk *)ctx->d_arc_work.p, nchunks);
+    arc_copy_kernel<<<grid, ARC_COPY_THREADS, 16, s>>>(d_src, d_dst, (const ArcChunk *)ctx->d_arc_work.p, nchunks,
+                                                       ctx->arc_dynamic ? (unsigned long long *)ctx->d_arc_tot.p + 4 : nullptr,
+                                                       (u32)ctx->arc_head_mask);
     CK(ctx, cudaGetLastError());
     ctx->launches += 1;
     return ZPB_OK;

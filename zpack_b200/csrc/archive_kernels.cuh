@@ -8,7 +8,8 @@
 //                       the first 64 KB copy chunk of every entry
 //   arc_chunks_kernel   thread per 64 KB copy chunk: its entry (binary search over the chunk table) and byte ranges
 //   arc_copy_kernel     the byte moves of zpack_write_files_from_archive (zpack_write.c:345-428: one memcpy per entry)
-//                       as 64 KB chunks dealt round-robin to the CTAs; 16-byte stores, the source realigned in registers
+//                       as 64 KB chunks that the CTAs draw from a counter as they become free; 16-byte stores, every aligned source vector loaded
+//                       once and realigned in registers (neighbouring lane's vector by shuffle, word select, funnel shift)
 //   arc_cdr_kernel      zpack_write_cdr_memory + zpack_write_eocdr (+ the archive header) (zpack_write.c:687-711, 778-785)
 //   cdr_*_kernel        zpack_read_file_entries_memory (/root/reference/lib/zpack_read.c:109-166).  The records are a
 //                       linked list (each starts where the previous one's name ends), which the reference walks serially;
@@ -97,7 +98,7 @@ ZPB_DEVINL void arc_layout_body(ArcEntry *e, u64 n, u64 base, u32 assign, u64 *r
         }
         c0 += ta; c1 += tb; c2 += tc;
     }
-    if (tid == 0) { totals[0] = c0; totals[1] = c1; totals[2] = c2; chunk_first[n] = c2; }
+    if (tid == 0) { totals[0] = c0; totals[1] = c1; totals[2] = c2; totals[4] = 0; chunk_first[n] = c2; }   // [4]: the copy kernel's chunk counter
 }
 
 // ---- copy: dst and src never overlap (different buffers, or the caller's disjoint ranges)
@@ -112,9 +113,10 @@ ZPB_DEVINL uint4 arc_realign(uint4 A, uint4 B, u32 w, u32 b) {
     return make_uint4(__funnelshift_r(x0, x1, b), __funnelshift_r(x1, x2, b), __funnelshift_r(x2, x3, b), __funnelshift_r(x3, x4, b));
 }
 
-ZPB_DEVINL void arc_copy_span(u8 *dst, const u8 *src, u32 len) {
+template <u32 ARC_U>   // 16-byte vectors in flight per thread in the realigning path
+ZPB_DEVINL void arc_copy_span(u8 *dst, const u8 *src, u32 len, u32 head_mask) {
     const u32 tid = threadIdx.x, nt = blockDim.x;
-    u32 head = (u32)(-(intptr_t)dst) & 15u;
+    u32 head = (u32)(-(intptr_t)dst) & head_mask;    // 15: vectors on the 16-byte grid; 127: warp stores on whole lines
     if (head > len) head = len;
     if (tid < head) dst[tid] = src[tid];
     dst += head; src += head; len -= head;
@@ -130,19 +132,41 @@ ZPB_DEVINL void arc_copy_span(u8 *dst, const u8 *src, u32 len) {
             for (u32 k = 0; k < 4; ++k) if (v + k * nt < nvec) stg128(dst + 16 * (size_t)(v + k * nt), r[k]);
         }
     } else {
-        // the second vector of the last chunk must stay inside [src, src + len): keep 16 bytes for the byte loop
+        // Source and destination are not congruent mod 16: destination vector v is made of aligned source vectors v and
+        // v + 1.  A warp takes 32 * ARC_U consecutive vectors per round, lane L the vectors base + 32 k + L: every aligned
+        // source vector is loaded once, v + 1 comes from the next lane by shuffle (lane 31: from lane 0's next slot; after
+        // the last slot, from one extra vector that lane 0 loads).  The last source vector read is vector nvec, which has
+        // to lie inside [src, src + len): 16 bytes are kept for the byte loop.
         nvec = len >= 32 ? (len - 16) >> 4 : 0;
         const u8 *sa = src - rel;
-        const u32 w = rel >> 2, b = (rel & 3u) * 8u;
-        for (u32 v = tid; v < nvec; v += 4 * nt) {
-            uint4 A[4], B[4];
+        const u32 w = rel >> 2, b = (rel & 3u) * 8u, lane = tid & 31u;
+        for (u32 base = (tid >> 5) * (32u * ARC_U); base < nvec; base += nt * ARC_U) {
+            const u8 *p = sa + 16 * (size_t)(base + lane);
+            u8 *q = dst + 16 * (size_t)(base + lane);
+            const bool full = base + 32u * ARC_U <= nvec;      // warp-uniform: every load and store of the round is in range
+            uint4 A[ARC_U], X = make_uint4(0, 0, 0, 0);
+            if (full) {
 #pragma unroll
-            for (u32 k = 0; k < 4; ++k) if (v + k * nt < nvec) {
-                A[k] = ldg128(sa + 16 * (size_t)(v + k * nt));
-                B[k] = ldg128(sa + 16 * (size_t)(v + k * nt) + 16);
+                for (u32 k = 0; k < ARC_U; ++k) A[k] = ldg128_stream(p + 512u * k);
+                if (lane == 0) X = ldg128_stream(p + 512u * ARC_U);
+            } else {
+#pragma unroll
+                for (u32 k = 0; k < ARC_U; ++k) {
+                    A[k] = make_uint4(0, 0, 0, 0);
+                    if (base + 32u * k + lane <= nvec) A[k] = ldg128_stream(p + 512u * k);
+                }
             }
 #pragma unroll
-            for (u32 k = 0; k < 4; ++k) if (v + k * nt < nvec) stg128(dst + 16 * (size_t)(v + k * nt), arc_realign(A[k], B[k], w, b));
+            for (u32 k = 0; k < ARC_U; ++k) {
+                const uint4 N = k + 1 < ARC_U ? A[k + 1 < ARC_U ? k + 1 : k] : X;
+                uint4 B, W;
+                B.x = __shfl_down_sync(0xffffffffu, A[k].x, 1); B.y = __shfl_down_sync(0xffffffffu, A[k].y, 1);
+                B.z = __shfl_down_sync(0xffffffffu, A[k].z, 1); B.w = __shfl_down_sync(0xffffffffu, A[k].w, 1);
+                W.x = __shfl_sync(0xffffffffu, N.x, 0); W.y = __shfl_sync(0xffffffffu, N.y, 0);
+                W.z = __shfl_sync(0xffffffffu, N.z, 0); W.w = __shfl_sync(0xffffffffu, N.w, 0);
+                if (lane == 31) B = W;
+                if (full || base + 32u * k + lane < nvec) stg128(q + 512u * k, arc_realign(A[k], B, w, b));
+            }
         }
     }
     for (u32 i = (nvec << 4) + tid; i < len; i += nt) dst[i] = src[i];
@@ -169,18 +193,37 @@ ZPB_DEVINL void arc_chunks_body(const ArcEntry *e, u64 n, const u64 *chunk_first
     stg128(o + 1, make_uint4(left < ARC_CHUNK ? (u32)left : ARC_CHUNK, (u32)lo, 0u, 0u));
 }
 
-ZPB_DEVINL void arc_copy_body(const u8 *src, u8 *dst, const ArcChunk *chunks, u64 nchunks) {
+// `next` == NULL: chunks dealt round-robin (c, c + grid, ...), the next work item fetched while this one moves;
+// otherwise the CTAs draw chunk numbers from the counter (zeroed by arc_layout_kernel) as they become free.
+template <u32 ARC_U>
+ZPB_DEVINL void arc_copy_body(const u8 *src, u8 *dst, const ArcChunk *chunks, u64 nchunks, unsigned long long *next, u32 head_mask) {
+    if (next) {
+        ZPB_DYN_SMEM(smem);
+        const u32 sm = smem_window(smem);
+        for (;;) {
+            if (threadIdx.x == 0) {
+                const unsigned long long c = atomicAdd(next, 1ull);
+                sts32(sm, (u32)c); sts32(sm + 4, (u32)(c >> 32));
+            }
+            __syncthreads();
+            const u64 c = (u64)lds32(sm) | ((u64)lds32(sm + 4) << 32);
+            __syncthreads();
+            if (c >= nchunks) return;
+            const uint4 a = ldg128(chunks + c);
+            arc_copy_span<ARC_U>(dst + ((u64)a.z | ((u64)a.w << 32)), src + ((u64)a.x | ((u64)a.y << 32)), chunks[c].len, head_mask);
+        }
+    }
     u64 c = blockIdx.x;
     if (c >= nchunks) return;
     uint4 a = ldg128(chunks + c);
     u32 len = chunks[c].len;
-    for (;;) {                                    // the next descriptor is fetched while this chunk moves
+    for (;;) {
         const u64 cn = c + gridDim.x;
         const bool more = cn < nchunks;
         uint4 an = a;
         u32 lenn = 0;
         if (more) { an = ldg128(chunks + cn); lenn = chunks[cn].len; }
-        arc_copy_span(dst + ((u64)a.z | ((u64)a.w << 32)), src + ((u64)a.x | ((u64)a.y << 32)), len);
+        arc_copy_span<ARC_U>(dst + ((u64)a.z | ((u64)a.w << 32)), src + ((u64)a.x | ((u64)a.y << 32)), len, head_mask);
         if (!more) break;
         a = an; len = lenn; c = cn;
     }
@@ -310,9 +353,11 @@ arc_layout_kernel(ArcEntry *e, u64 n, u64 base, u32 assign, u64 *rec_off, u64 *c
     arc_layout_body(e, n, base, assign, rec_off, chunk_first, totals);
 }
 __global__ void __launch_bounds__(ARC_COPY_THREADS, 4)
-arc_copy_kernel(const u8 *__restrict__ src, u8 *__restrict__ dst, const ArcChunk *__restrict__ chunks, u64 nchunks) {
-    arc_copy_body(src, dst, chunks, nchunks);
+arc_copy_kernel(const u8 *__restrict__ src, u8 *__restrict__ dst, const ArcChunk *__restrict__ chunks, u64 nchunks,
+                unsigned long long *next, u32 head_mask) {
+    arc_copy_body<4>(src, dst, chunks, nchunks, next, head_mask);
 }
+
 __global__ void arc_chunks_kernel(const ArcEntry *e, u64 n, const u64 *chunk_first, u64 nchunks, ArcChunk *out) {
     arc_chunks_body(e, n, chunk_first, nchunks, out);
 }

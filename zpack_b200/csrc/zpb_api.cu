@@ -98,7 +98,8 @@ struct zpb_ctx {
     u64 host_chunk_bytes = 256u << 20; // decoded bytes per pipeline chunk (ZPB_HOST_CHUNK_MB)
     // device-resident container operations (archive_api.inl): entry table, record offsets, chunk table, totals, names; CDR walk tables
     DevBuf d_arc_e, d_arc_rec, d_arc_chunk, d_arc_work, d_arc_tot, d_arc_names, d_cdr_jump, d_cdr_cnt, d_cdr_j2, d_cdr_anchor;
-    int arc_ctas_per_sm = 8;           // resident CTAs of the copy kernel (ZPB_ARC_CTAS)
+    int arc_dynamic = 1, arc_head_mask = 127;  // copy kernel: chunks drawn from a counter (ZPB_ARC_DYNAMIC=0: fixed deal), head bytes up to the 128-byte grid (ZPB_ARC_HEAD=15: 16-byte grid)
+    int arc_ctas_per_sm = 4;           // copy kernel: CTAs per SM (ZPB_ARC_CTAS)
     float arc_ms[3] = {0, 0, 0};       // layout + directory kernels, copy kernel, open kernels of the last call
 };
 
@@ -154,6 +155,8 @@ extern "C" zpb_ctx *zpb_create(int device) {
     }
     if (const char *s = getenv("ZPB_CTAS_PER_SM")) ctx->ctas_per_sm = atoi(s);
     if (const char *s = getenv("ZPB_FAST")) ctx->fast = atoi(s);
+    if (const char *s = getenv("ZPB_ARC_DYNAMIC")) ctx->arc_dynamic = atoi(s) != 0;
+    if (const char *s = getenv("ZPB_ARC_HEAD")) ctx->arc_head_mask = atoi(s) == 127 ? 127 : 15;
     if (const char *s = getenv("ZPB_ARC_CTAS")) ctx->arc_ctas_per_sm = std::max(1, std::min(8, atoi(s)));
     if (const char *s = getenv("ZPB_HOST_WORKERS")) ctx->host_workers = std::max(1, std::min(8, atoi(s)));
     if (const char *s = getenv("ZPB_HOST_CHUNK_MB")) ctx->host_chunk_bytes = (u64)std::max(1, atoi(s)) << 20;
