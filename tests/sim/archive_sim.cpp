@@ -14,8 +14,12 @@ extern "C" int sim_archive_build(const uint8_t *src, ArcEntry *e, uint64_t n, co
                                  uint64_t cdr_off, uint64_t block, int scan_threads, int grid, uint64_t seed, uint64_t *totals) {
     std::vector<u64> rec(n + 1), chunk(n + 2);
     u64 *rp = rec.data(), *cp = chunk.data();
-    sim::launch(sim::Dim3(1), sim::Dim3((unsigned)scan_threads), 33 * 24, [&] {
-        arc_layout_body(e, n, ARC_DATA_START, with_cdr ? 1u : 0u, rp, cp, totals);
+    const u64 ntiles = n ? (n + 4 * (u64)scan_threads - 1) / (4 * (u64)scan_threads) : 1;
+    std::vector<u64> chain(ntiles * 4, 0);
+    u64 *chp = chain.data();
+    for (int k = 0; k < 8; ++k) totals[k] = 0;
+    sim::launch(sim::Dim3((unsigned)ntiles), sim::Dim3((unsigned)scan_threads), 37 * 24, [&] {
+        arc_layout_body(e, n, ARC_DATA_START, with_cdr ? 1u : 0u, rp, cp, totals, chp);
     }, seed);
     if (with_cdr)
         sim::launch(sim::Dim3((unsigned)grid), sim::Dim3(64), 0, [&] { arc_cdr_body(dst, e, n, names, rp, cdr_off, block, 1u); }, seed);

@@ -14,6 +14,19 @@ static int arc_upload_entries(zpb_ctx *ctx, const zpb_arc_entry *entries, u64 n,
     return ZPB_OK;
 }
 
+// the offset table: one CTA per tile of 4 x ARC_SCAN_THREADS entries (archive_kernels.cuh)
+static int arc_launch_layout(zpb_ctx *ctx, u64 n, u64 base, u32 assign, cudaStream_t s) {
+    const u64 ntiles = std::max<u64>(1, (n + 4 * ARC_SCAN_THREADS - 1) / (4 * ARC_SCAN_THREADS));
+    if (!ctx->d_arc_scan.ensure(ntiles * 32 + 64)) return fail(ctx, ZPB_E_NOMEM, "scratch allocation failed");
+    CK(ctx, cudaMemsetAsync(ctx->d_arc_scan.p, 0, ntiles * 32, s));
+    CK(ctx, cudaMemsetAsync(ctx->d_arc_tot.p, 0, 64, s));
+    arc_layout_kernel<<<(u32)ntiles, ARC_SCAN_THREADS, 37 * 24, s>>>((ArcEntry *)ctx->d_arc_e.p, n, base, assign, (u64 *)ctx->d_arc_rec.p,
+                                                                    (u64 *)ctx->d_arc_chunk.p, (u64 *)ctx->d_arc_tot.p, (u64 *)ctx->d_arc_scan.p);
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return ZPB_OK;
+}
+
 // the copy's work items (before the event that starts the copy kernel's interval), then the copy itself
 static int arc_launch_chunks(zpb_ctx *ctx, u64 n, u64 nchunks, cudaStream_t s) {
     if (!nchunks) return ZPB_OK;
@@ -54,10 +67,7 @@ extern "C" int zpb_copy_entries_device(zpb_ctx *ctx, const uint8_t *d_src, uint6
     int rc = arc_upload_entries(ctx, entries, n, s);
     if (rc) return rc;
     CK(ctx, cudaEventRecord(ctx->evs[0], s));
-    arc_layout_kernel<<<1, ARC_SCAN_THREADS, 33 * 24, s>>>((ArcEntry *)ctx->d_arc_e.p, n, 0, 0u, (u64 *)ctx->d_arc_rec.p,
-                                                          (u64 *)ctx->d_arc_chunk.p, (u64 *)ctx->d_arc_tot.p);
-    CK(ctx, cudaGetLastError());
-    ctx->launches += 1;
+    if ((rc = arc_launch_layout(ctx, n, 0, 0u, s))) return rc;
     if ((rc = arc_launch_chunks(ctx, n, nchunks, s))) return rc;
     CK(ctx, cudaEventRecord(ctx->evs[1], s));
     if ((rc = arc_launch_copy(ctx, d_src, d_dst, nchunks, s))) return rc;
@@ -96,14 +106,12 @@ extern "C" int zpb_archive_build_device(zpb_ctx *ctx, const uint8_t *d_src, uint
         CK(ctx, cudaMemcpyAsync(ctx->d_arc_names.p, ctx->h_bounce.p, names_size, cudaMemcpyHostToDevice, s));
     }
     CK(ctx, cudaEventRecord(ctx->evs[0], s));
-    arc_layout_kernel<<<1, ARC_SCAN_THREADS, 33 * 24, s>>>((ArcEntry *)ctx->d_arc_e.p, n, ARC_DATA_START, 1u, (u64 *)ctx->d_arc_rec.p,
-                                                          (u64 *)ctx->d_arc_chunk.p, (u64 *)ctx->d_arc_tot.p);
-    CK(ctx, cudaGetLastError());
+    if ((rc = arc_launch_layout(ctx, n, ARC_DATA_START, 1u, s))) return rc;
     const u32 cgrid = (u32)std::max<u64>(1, std::min<u64>((n + 255) / 256, (u64)ctx->sm_count * 8));
     arc_cdr_kernel<<<cgrid, 256, 0, s>>>(d_archive, (const ArcEntry *)ctx->d_arc_e.p, n, (const u8 *)ctx->d_arc_names.p,
                                          (const u64 *)ctx->d_arc_rec.p, cdr_off, block, 1u);
     CK(ctx, cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches += 1;
     if ((rc = arc_launch_chunks(ctx, n, nchunks, s))) return rc;
     CK(ctx, cudaEventRecord(ctx->evs[1], s));
     if ((rc = arc_launch_copy(ctx, d_src, d_archive, nchunks, s))) return rc;

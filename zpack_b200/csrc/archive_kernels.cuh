@@ -2,7 +2,7 @@
 // is opened (central directory -> entry table), assembled (payload slots -> header + data + CDR + EOCDR) and copied
 // entry by entry into another archive without a host pass over its bytes.
 //
-//   arc_layout_kernel   exclusive prefix sums over the entries: entry.offset (the offset table of
+//   arc_layout_kernel   exclusive prefix sums over the entries (CTA per tile of 4096, running totals handed from tile to tile): entry.offset (the offset table of
 //                       zpack_write_files / ZPACK_ADD_OFFSET_AND_SIZE, /root/reference/lib/zpack_write.c:280-343), the
 //                       position of every CDR record (zpack_write_cdr_ex's block size loop, zpack_write.c:720-736) and
 //                       the first 64 KB copy chunk of every entry
@@ -47,58 +47,75 @@ ZPB_DEVINL void arc_st16(u8 *p, u32 v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); }
 ZPB_DEVINL void arc_st32(u8 *p, u32 v) { arc_st16(p, v); arc_st16(p + 2, v >> 16); }
 ZPB_DEVINL void arc_st64(u8 *p, u64 v) { arc_st32(p, (u32)v); arc_st32(p + 4, (u32)(v >> 32)); }
 
-// ---- layout: one CTA, three running sums.  totals: Σ comp_size, Σ (35 + name_len), Σ chunks.
-ZPB_DEVINL void arc_layout_body(ArcEntry *e, u64 n, u64 base, u32 assign, u64 *rec_off, u64 *chunk_first, u64 *totals) {
+// ---- layout: three exclusive prefix sums over the table.  totals: [0] Σ comp_size, [1] Σ (35 + name_len), [2] Σ chunks,
+// [4] the copy kernel's chunk counter, [5] the tile ticket (both zeroed by the host before the launch).
+// One CTA per tile of 4 x blockDim entries, tiles taken by ticket so that a tile's predecessor has always started: every
+// CTA scans its tile on its own (loads of all tiles overlap — one SM alone pulls the 64-byte records at ~35 GB/s), then
+// thread 0 waits for the predecessor's running totals in `chain` (4 u64 per tile: three sums and a ready flag), adds its
+// own and publishes them; only that hand-over is serial.
+ZPB_DEVINL void arc_layout_body(ArcEntry *e, u64 n, u64 base, u32 assign, u64 *rec_off, u64 *chunk_first, u64 *totals,
+                                volatile u64 *chain) {
     ZPB_DYN_SMEM(smem);
-    const u32 sm = smem_window(smem);            // (32 warps + the CTA) x 3 sums x 8 bytes
+    const u32 sm = smem_window(smem);            // (32 warps + the CTA) x 3 sums x 8 bytes, + 3 x 8 bytes for the tile's base, + the ticket
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nw = blockDim.x >> 5;
-    u64 c0 = 0, c1 = 0, c2 = 0;
-    for (u64 i0 = 0; i0 < n; i0 += (u64)blockDim.x * 4) {     // four consecutive entries per thread: their loads overlap
-        const u64 i = i0 + (u64)tid * 4;
-        u64 a[4], b[4], c[4];
-#pragma unroll
-        for (u32 j = 0; j < 4; ++j) {
-            a[j] = b[j] = c[j] = 0;
-            if (i + j < n) { a[j] = e[i + j].comp_size; b[j] = ARC_FIXED + (u64)e[i + j].name_len; c[j] = (a[j] + ARC_CHUNK - 1) >> ARC_CHUNK_LOG; }
-        }
-        const u64 ma = a[0] + a[1] + a[2] + a[3], mb = b[0] + b[1] + b[2] + b[3], mc = c[0] + c[1] + c[2] + c[3];
-        u64 sa = ma, sb = mb, sc = mc;
-        for (u32 d = 1; d < 32; d <<= 1) {
-            const u64 ta = __shfl_up_sync(0xffffffffu, sa, d), tb = __shfl_up_sync(0xffffffffu, sb, d),
-                      tc = __shfl_up_sync(0xffffffffu, sc, d);
-            if (lane >= d) { sa += ta; sb += tb; sc += tc; }
-        }
-        if (lane == 31) { arc_sts64(sm + warp * 24, sa); arc_sts64(sm + warp * 24 + 8, sb); arc_sts64(sm + warp * 24 + 16, sc); }
-        __syncthreads();
-        if (warp == 0) {                         // the warps' totals: scanned by one warp, exclusive prefixes back in place
-            u64 x = 0, y = 0, z = 0;
-            if (lane < nw) { x = arc_lds64(sm + lane * 24); y = arc_lds64(sm + lane * 24 + 8); z = arc_lds64(sm + lane * 24 + 16); }
-            u64 sx = x, sy = y, sz = z;
-            for (u32 d = 1; d < 32; d <<= 1) {
-                const u64 tx = __shfl_up_sync(0xffffffffu, sx, d), ty = __shfl_up_sync(0xffffffffu, sy, d),
-                          tz = __shfl_up_sync(0xffffffffu, sz, d);
-                if (lane >= d) { sx += tx; sy += ty; sz += tz; }
-            }
-            if (lane < nw) { arc_sts64(sm + lane * 24, sx - x); arc_sts64(sm + lane * 24 + 8, sy - y); arc_sts64(sm + lane * 24 + 16, sz - z); }
-            if (lane == 31) { arc_sts64(sm + 32 * 24, sx); arc_sts64(sm + 32 * 24 + 8, sy); arc_sts64(sm + 32 * 24 + 16, sz); }
-        }
-        __syncthreads();
-        const u64 pa = arc_lds64(sm + warp * 24), pb = arc_lds64(sm + warp * 24 + 8), pc = arc_lds64(sm + warp * 24 + 16);
-        const u64 ta = arc_lds64(sm + 32 * 24), tb = arc_lds64(sm + 32 * 24 + 8), tc = arc_lds64(sm + 32 * 24 + 16);
-        __syncthreads();
-        u64 ra = c0 + pa + sa - ma, rb = c1 + pb + sb - mb, rc = c2 + pc + sc - mc;
-#pragma unroll
-        for (u32 j = 0; j < 4; ++j) {
-            if (i + j < n) {
-                if (assign) e[i + j].offset = base + ra;
-                rec_off[i + j] = rb;
-                chunk_first[i + j] = rc;
-            }
-            ra += a[j]; rb += b[j]; rc += c[j];
-        }
-        c0 += ta; c1 += tb; c2 += tc;
+    if (tid == 0) {
+        const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long *>(totals + 5), 1ull);
+        sts32(sm + 36 * 24, (u32)t);
     }
-    if (tid == 0) { totals[0] = c0; totals[1] = c1; totals[2] = c2; totals[4] = 0; chunk_first[n] = c2; }   // [4]: the copy kernel's chunk counter
+    __syncthreads();
+    const u64 tile = lds32(sm + 36 * 24), ntiles = (n + (u64)blockDim.x * 4 - 1) / ((u64)blockDim.x * 4);
+    const u64 i = tile * blockDim.x * 4 + (u64)tid * 4;      // four consecutive entries per thread: their loads overlap
+    u64 a[4], b[4], c[4];
+#pragma unroll
+    for (u32 j = 0; j < 4; ++j) {
+        a[j] = b[j] = c[j] = 0;
+        if (i + j < n) { a[j] = e[i + j].comp_size; b[j] = ARC_FIXED + (u64)e[i + j].name_len; c[j] = (a[j] + ARC_CHUNK - 1) >> ARC_CHUNK_LOG; }
+    }
+    const u64 ma = a[0] + a[1] + a[2] + a[3], mb = b[0] + b[1] + b[2] + b[3], mc = c[0] + c[1] + c[2] + c[3];
+    u64 sa = ma, sb = mb, sc = mc;
+    for (u32 d = 1; d < 32; d <<= 1) {
+        const u64 ta = __shfl_up_sync(0xffffffffu, sa, d), tb = __shfl_up_sync(0xffffffffu, sb, d),
+                  tc = __shfl_up_sync(0xffffffffu, sc, d);
+        if (lane >= d) { sa += ta; sb += tb; sc += tc; }
+    }
+    if (lane == 31) { arc_sts64(sm + warp * 24, sa); arc_sts64(sm + warp * 24 + 8, sb); arc_sts64(sm + warp * 24 + 16, sc); }
+    __syncthreads();
+    if (warp == 0) {                             // the warps' totals: scanned by one warp, exclusive prefixes back in place
+        u64 x = 0, y = 0, z = 0;
+        if (lane < nw) { x = arc_lds64(sm + lane * 24); y = arc_lds64(sm + lane * 24 + 8); z = arc_lds64(sm + lane * 24 + 16); }
+        u64 sx = x, sy = y, sz = z;
+        for (u32 d = 1; d < 32; d <<= 1) {
+            const u64 tx = __shfl_up_sync(0xffffffffu, sx, d), ty = __shfl_up_sync(0xffffffffu, sy, d),
+                      tz = __shfl_up_sync(0xffffffffu, sz, d);
+            if (lane >= d) { sx += tx; sy += ty; sz += tz; }
+        }
+        if (lane < nw) { arc_sts64(sm + lane * 24, sx - x); arc_sts64(sm + lane * 24 + 8, sy - y); arc_sts64(sm + lane * 24 + 16, sz - z); }
+        if (lane == 31) {                        // the tile's totals: wait for the tiles before, publish the running totals
+            u64 b0 = 0, b1 = 0, b2 = 0;
+            if (tile > 0) {
+                while (chain[(tile - 1) * 4 + 3] == 0) spin_pause();
+                __threadfence();
+                b0 = chain[(tile - 1) * 4]; b1 = chain[(tile - 1) * 4 + 1]; b2 = chain[(tile - 1) * 4 + 2];
+            }
+            chain[tile * 4] = b0 + sx; chain[tile * 4 + 1] = b1 + sy; chain[tile * 4 + 2] = b2 + sz;
+            __threadfence();
+            chain[tile * 4 + 3] = 1;
+            arc_sts64(sm + 33 * 24, b0); arc_sts64(sm + 33 * 24 + 8, b1); arc_sts64(sm + 33 * 24 + 16, b2);
+            if (tile + 1 == ntiles) { totals[0] = b0 + sx; totals[1] = b1 + sy; totals[2] = b2 + sz; chunk_first[n] = b2 + sz; }
+        }
+    }
+    __syncthreads();
+    u64 ra = arc_lds64(sm + 33 * 24) + arc_lds64(sm + warp * 24) + sa - ma, rb = arc_lds64(sm + 33 * 24 + 8) + arc_lds64(sm + warp * 24 + 8) + sb - mb,
+        rc = arc_lds64(sm + 33 * 24 + 16) + arc_lds64(sm + warp * 24 + 16) + sc - mc;
+#pragma unroll
+    for (u32 j = 0; j < 4; ++j) {
+        if (i + j < n) {
+            if (assign) e[i + j].offset = base + ra;
+            rec_off[i + j] = rb;
+            chunk_first[i + j] = rc;
+        }
+        ra += a[j]; rb += b[j]; rc += c[j];
+    }
 }
 
 // ---- copy: dst and src never overlap (different buffers, or the caller's disjoint ranges)
@@ -349,8 +366,8 @@ ZPB_DEVINL void cdr_emit_body(const u8 *body, u64 B, const u32 *tile_pos, const 
 
 #ifndef ZPB_SIM
 __global__ void __launch_bounds__(ARC_SCAN_THREADS)
-arc_layout_kernel(ArcEntry *e, u64 n, u64 base, u32 assign, u64 *rec_off, u64 *chunk_first, u64 *totals) {
-    arc_layout_body(e, n, base, assign, rec_off, chunk_first, totals);
+arc_layout_kernel(ArcEntry *e, u64 n, u64 base, u32 assign, u64 *rec_off, u64 *chunk_first, u64 *totals, u64 *chain) {
+    arc_layout_body(e, n, base, assign, rec_off, chunk_first, totals, chain);
 }
 __global__ void __launch_bounds__(ARC_COPY_THREADS, 4)
 arc_copy_kernel(const u8 *__restrict__ src, u8 *__restrict__ dst, const ArcChunk *__restrict__ chunks, u64 nchunks,

@@ -97,7 +97,7 @@ struct zpb_ctx {
     int host_workers = 6;              // ZPB_HOST_WORKERS (tools/e2e_sweep.py: profiles/r1_e2e_sweep.jsonl)
     u64 host_chunk_bytes = 256u << 20; // decoded bytes per pipeline chunk (ZPB_HOST_CHUNK_MB)
     // device-resident container operations (archive_api.inl): entry table, record offsets, chunk table, totals, names; CDR walk tables
-    DevBuf d_arc_e, d_arc_rec, d_arc_chunk, d_arc_work, d_arc_tot, d_arc_names, d_cdr_jump, d_cdr_cnt, d_cdr_j2, d_cdr_anchor;
+    DevBuf d_arc_e, d_arc_rec, d_arc_chunk, d_arc_work, d_arc_scan, d_arc_tot, d_arc_names, d_cdr_jump, d_cdr_cnt, d_cdr_j2, d_cdr_anchor;
     int arc_dynamic = 1, arc_head_mask = 127;  // copy kernel: chunks drawn from a counter (ZPB_ARC_DYNAMIC=0: fixed deal), head bytes up to the 128-byte grid (ZPB_ARC_HEAD=15: 16-byte grid)
     int arc_ctas_per_sm = 4;           // copy kernel: CTAs per SM (ZPB_ARC_CTAS)
     float arc_ms[3] = {0, 0, 0};       // layout + directory kernels, copy kernel, open kernels of the last call
@@ -218,7 +218,7 @@ extern "C" void zpb_destroy(zpb_ctx *ctx) {
     ctx->d_zslot.release(); ctx->d_zseq.release(); ctx->d_zmeta.release(); ctx->d_zelit.release(); ctx->d_zhuf.release(); ctx->d_ztabs.release();
     for (cudaEvent_t e : ctx->pack_evs) cudaEventDestroy(e);
     ctx->d_partials.release(); ctx->d_acc.release();
-    ctx->d_arc_e.release(); ctx->d_arc_rec.release(); ctx->d_arc_chunk.release(); ctx->d_arc_work.release(); ctx->d_arc_tot.release(); ctx->d_arc_names.release();
+    ctx->d_arc_e.release(); ctx->d_arc_rec.release(); ctx->d_arc_chunk.release(); ctx->d_arc_work.release(); ctx->d_arc_scan.release(); ctx->d_arc_tot.release(); ctx->d_arc_names.release();
     ctx->d_cdr_jump.release(); ctx->d_cdr_cnt.release(); ctx->d_cdr_j2.release(); ctx->d_cdr_anchor.release();
     for (auto &ev : ctx->evs) if (ev) cudaEventDestroy(ev);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
