@@ -52,6 +52,11 @@
 #define FAST_EXEC_WARPS 8u
 #endif
 #define FAST_EXEC_SMEM (FAST_EXEC_WARPS * FAST_WARP_SMEM + 48u)   // per CTA, plus slack at both ends
+// the invariants the copies rely on, whatever the overridable sizes are set to
+static_assert(FAST_SCR % 16u == 0 && FAST_SCR >= 15u + FAST_ST + 1u, "a staged far match (<= FAST_ST bytes at any 16-byte phase) fits its scratch");
+static_assert((CR_SIZE & (CR_SIZE - 1u)) == 0 && CR_ROW == 32u * 16u && CR_SIZE % CR_ROW == 0, "staging ring: power of two, rows of 16 bytes per lane");
+static_assert(FAST_WARP_SMEM - (FAST_RING + 32u * FAST_SCR + CR_SIZE) >= 32u, "lane_copy reads up to four whole words past a range: 32 bytes of padding per warp");
+static_assert((FAST_RING & FAST_RMASK) == 0 && FAST_RING % 1024u == 0, "output ring: power of two, flushed in KiB units");
 
 #define FE_DONE    0u   // status already final (guards, unsupported method)
 #define FE_FAST    1u   // block table filled, goes through K1/K2
