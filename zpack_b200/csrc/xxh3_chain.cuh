@@ -38,10 +38,17 @@ xxh3_chain_kernel(const u64 *__restrict__ partials, u64 nscr, const u64 *__restr
     }
     // One chain step is acc' = ((x ^ (x >> 47)) ^ key) * PRIME32_1 with x = acc + S_n.  Carrying x instead of
     // acc (x' = acc' + S_{n+1}) puts the next add INSIDE the multiply-add: with y = (x ^ (x >> 47)) ^ key,
-    //     x' = y_lo * P + { S'_lo , y_hi * P + S'_hi }        (one mad.wide.u32 with a 64-bit addend)
-    // so the loop-carried path is shift -> xor3 -> mad.wide (3 dependent instructions) instead of
+    //     x' = (y_lo * P + S') + (y_hi * P << 32)
+    // so the loop-carried path is shift -> xor3 -> multiply-add (wide) -> multiply-add (high word) instead of
     // add.cc -> addc -> shift -> xor3 -> mad.wide -> mad.  The stream consumed is S shifted by one with a
     // trailing zero, so after the last step x is the accumulator itself.
+    // How the step is written decides what NVVM / ptxas make of it (SASS checked with cuobjdump, timed on B200).  An
+    // inline `mad.wide.u32` with a 64-bit addend, or the plain 64-bit C expression (NVVM reassociates it so that S' is
+    // added last) come out as IMAD.WIDE, IADD3, IADD3.X: five dependent instructions, 33 cycles per step.  Leaving only
+    // the additions in C makes ptxas fold y_hi * P + S'_hi into the addend's high half — behind a register-pair copy it
+    // spells `IMAD.WIDE R, RZ, x, R`, which puts two wide multiplies on the path: still 33 cycles.  With the product and
+    // the high-word multiply-add both opaque (asm) and S' added in C, the step is
+    //     IMAD.WIDE R, y_lo, P, S' (the pair LDS.64 delivered) -> IMAD hi -> SHF -> LOP3 -> next IMAD.WIDE.
     const u64 kk = c_xxh3_key[16 + i8];
     const u32 kl = (u32)kk, kh = (u32)(kk >> 32);
     const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(partials);   // 4 x 16 B per KiB
@@ -49,10 +56,14 @@ xxh3_chain_kernel(const u64 *__restrict__ partials, u64 nscr, const u64 *__restr
     auto step = [&](u64 x, u64 vnext) -> u64 {
         const u32 xl = (u32)x, xh = (u32)(x >> 32);
         const u32 yl = xl ^ (xh >> 15) ^ kl;
-        const u32 ch = (xh ^ kh) * XXH_P32_1 + (u32)(vnext >> 32);
+        u64 m;
+        asm("mul.wide.u32 %0, %1, %2;" : "=l"(m) : "r"(yl), "r"(XXH_P32_1));
+        m += vnext;                                                      // fused by ptxas: IMAD.WIDE R, y_lo, P, S'
+        u32 ml, mh, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(ml), "=r"(mh) : "l"(m));
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(hi) : "r"(xh ^ kh), "r"(XXH_P32_1), "r"(mh));   // IMAD on the high word
         u64 r;
-        asm("{\n\t.reg .b64 c;\n\tmov.b64 c, {%3, %4};\n\tmad.wide.u32 %0, %1, %2, c;\n\t}"
-            : "=l"(r) : "r"(yl), "r"(XXH_P32_1), "r"((u32)vnext), "r"(ch));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(ml), "r"(hi));
         return r;
     };
     const u64 nbatch = (nscr + XC_BATCH - 1) / XC_BATCH;
