@@ -25,4 +25,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:zstd
     python bench.py --workload c4 --entries 8192 --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_zstd.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:xxh3_chain -s 1 -c 1 -o gpurun_out/r2_chain_c5 \
     python bench.py --workload c5 --entries 8192 --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_chain.log 2>&1
+python tools/archive_bench.py > gpurun_out/r2_archive_bench.jsonl 2> gpurun_out/r2_archive_bench.err; cat gpurun_out/r2_archive_bench.jsonl
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches_archive.csv python tools/archive_bench.py 16384 > /dev/null 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:arc_copy -s 3 -c 1 -o gpurun_out/r2_arc_copy python tools/archive_bench.py 16384 > gpurun_out/ncu_arc.log 2>&1
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_archive.py -x -q -k "not file_to_device" 2>&1 | tail -4
 ls -la gpurun_out | tail -25
