@@ -29,6 +29,29 @@ def main():
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
         res[name] = round(out_b / best / 1e9, 2)
+    # the same bytes with ONE stream per direction: every H2D chunk on stream A, every D2H chunk on stream B, chunk k's D2H
+    # waiting (event) for chunk k's H2D — what a pipeline with dedicated copy streams would issue
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    for lag in (0, 1, 2):
+        best = None
+        for rep in range(3):
+            torch.cuda.synchronize()
+            evs = [torch.cuda.Event() for _ in range(nch)]
+            t0 = time.perf_counter()
+            for k in range(nch + lag):
+                if k < nch:
+                    with torch.cuda.stream(sa):
+                        d_in[k * ci:(k + 1) * ci].copy_(h_in[k * ci:(k + 1) * ci], non_blocking=True)
+                        evs[k].record(sa)
+                j = k - lag
+                if j >= 0:
+                    with torch.cuda.stream(sb):
+                        sb.wait_event(evs[j])
+                        h_out[j * co:(j + 1) * co].copy_(d_out[j * co:(j + 1) * co], non_blocking=True)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        res[f"one_stream_per_direction_lag{lag}"] = round(out_b / best / 1e9, 2)
     print(json.dumps(res))
 
 
