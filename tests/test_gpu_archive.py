@@ -285,3 +285,29 @@ def test_archive_file_to_verified_plaintext_without_a_host_copy_of_the_archive(g
 def zpack_entry_dtype():
     from zpack_b200.lib import Entry
     return Entry
+
+
+def test_empty_archive_and_empty_entries(gpu_ctx, oracle):
+    """n = 0 (the 42-byte archive the reference writes for no files) and entries of size 0 only."""
+    import torch
+    ref0 = container.assemble([], [], [], [], [])
+    assert len(ref0) == 42
+    d_arch = torch.full((64,), 0xEE, dtype=torch.uint8, device="cuda")
+    size = gpu_ctx.archive_build_device(None, 0, np.zeros(0, ArcEntry), np.zeros(0, np.uint8), d_arch, 64)
+    assert size == 42 and np.array_equal(d_arch.cpu().numpy()[:42], ref0)
+    res, e, nb = gpu_ctx.archive_open_device(d_arch, 42)
+    assert res == 0 and len(e) == 0
+    if oracle.have_ref():
+        assert oracle.RefReader.open_result(ref0) == 0
+    names = ["a", "", "ccc"]
+    e = np.zeros(3, ArcEntry)
+    e["name_len"], e["name_off"], e["method"], e["hash"] = [1, 0, 3], [0, 1, 1], [0, 2, 1], [7, 8, 9]
+    blob = np.frombuffer(b"accc", np.uint8)
+    ref = container.assemble(names, [b"", b"", b""], [0, 0, 0], [7, 8, 9], [0, 2, 1])
+    d_arch = torch.zeros(len(ref) + 16, dtype=torch.uint8, device="cuda")
+    size = gpu_ctx.archive_build_device(None, 0, e, blob, d_arch, len(ref) + 16)
+    assert size == len(ref) and np.array_equal(d_arch.cpu().numpy()[:size], ref)
+    assert (e["offset"] == 10).all()
+    res, eo, nb = gpu_ctx.archive_open_device(d_arch, size)
+    assert res == 0 and list(eo["name_len"]) == [1, 0, 3] and list(eo["hash"]) == [7, 8, 9]
+    gpu_ctx.copy_entries_device(d_arch, size, d_arch, size, np.zeros(0, ArcEntry))      # nothing to do is not an error
