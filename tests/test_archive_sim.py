@@ -183,3 +183,51 @@ def test_open_golden_and_reference_written_archives(sim, golden_dir, oracle):
         found, out, body = sim_open(sim, arch)
         assert found == len(d)
         same_directory(out, body, d)
+
+
+def test_copy_all_alignments_and_short_lengths(sim):
+    """every (source, destination) phase mod 16 x lengths around the vector / head / tail boundaries, all copy variants"""
+    rng = np.random.default_rng(31)
+    lens = [0, 1, 2, 15, 16, 17, 31, 32, 33, 47, 48, 63, 64, 65, 127, 128, 129, 255, 511, 2047, 2049, 4097]
+    cases = [(sp, dp, n) for sp in range(16) for dp in range(16) for n in (lens[(sp * 16 + dp + k) % len(lens)] for k in range(2))]
+    e = np.zeros(len(cases), ArcEntry)
+    spos = dpos = 0
+    for i, (sp, dp, n) in enumerate(cases):
+        spos += (sp - spos) % 16
+        dpos += (dp - dpos) % 16
+        e[i]["src_off"], e[i]["offset"], e[i]["comp_size"] = spos, dpos, n
+        spos += n + int(rng.integers(0, 9))
+        dpos += n + int(rng.integers(0, 9))
+    src, k1 = aligned(spos + 16)
+    src[:] = rng.integers(0, 256, len(src), dtype=np.uint8)
+    want = np.full(dpos + 16, 0xEE, np.uint8)
+    for r in e:
+        want[int(r["offset"]):int(r["offset"]) + int(r["comp_size"])] = src[int(r["src_off"]):int(r["src_off"]) + int(r["comp_size"])]
+    for seed in range(1, 8):
+        dst, k2 = aligned(dpos + 16)
+        dst[:] = 0xEE
+        totals = np.zeros(8, np.uint64)
+        sim.sim_archive_build(src.ctypes.data, e.ctypes.data, len(e), None, dst.ctypes.data, 0, 0, 0, 64, 3, seed, totals.ctypes.data)
+        assert np.array_equal(dst, want), seed
+
+
+def test_open_random_directories(sim):
+    """random record shapes (empty names, names longer than a tile, directories ending exactly on a tile edge) against the host mirror"""
+    rng = np.random.default_rng(32)
+    for trial in range(12):
+        n = int(rng.integers(1, 500))
+        kind = trial % 4
+        if kind == 0:
+            name_lens = [0] * n
+        elif kind == 1:
+            name_lens = [int(k) for k in rng.integers(0, 200, n)]
+        elif kind == 2:
+            name_lens = [int(k) if rng.random() > 0.03 else int(rng.integers(1000, 9000)) for k in rng.integers(0, 30, n)]
+        else:                       # 35 + 93 = 128 bytes per record: records end on every tile edge
+            name_lens = [93] * n
+        payloads, names, e, src, keep, blob = make_case(rng, [0] * n, name_lens)
+        arch = container.assemble(names, payloads, e["uncomp_size"], e["hash"], e["method"])
+        d = container.parse(arch)
+        found, out, body = sim_open(sim, arch, seed=trial + 1)
+        assert found == n, (trial, found, n)
+        same_directory(out, body, d)
