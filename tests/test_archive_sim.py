@@ -231,3 +231,6 @@ def test_open_random_directories(sim):
         found, out, body = sim_open(sim, arch, seed=trial + 1)
         assert found == n, (trial, found, n)
         same_directory(out, body, d)
+        d2 = container.directory_from_table(out, body, len(arch))      # the Python view of a device-side open
+        assert d2.names == d.names and d2.cdr_offset == d.cdr_offset and d2.file_size == d.file_size
+        assert np.array_equal(d2.entries(), d.entries())

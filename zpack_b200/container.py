@@ -96,6 +96,17 @@ def parse(buf) -> Directory:
                      fixed[:, 32].copy(), int(cdr_off), size)
 
 
+def directory_from_table(table: np.ndarray, names_blob, file_size: int) -> Directory:
+    """Directory from what zpb_archive_open_device returns (lib.Context.archive_open_device): the ArcEntry table parsed on
+    the device and the directory block its name_off / name_len point into — the same object parse() builds on the host."""
+    blob = bytes(memoryview(np.ascontiguousarray(names_blob, np.uint8)))
+    names = [blob[int(o):int(o) + int(k)].decode("utf-8", "surrogateescape") for o, k in zip(table["name_off"], table["name_len"])]
+    block = len(blob)
+    return Directory(names, table["offset"].astype(np.uint64), table["comp_size"].astype(np.uint64),
+                     table["uncomp_size"].astype(np.uint64), table["hash"].astype(np.uint64), table["method"].astype(np.uint8),
+                     file_size - EOCDR_SIZE - CDR_HEADER_SIZE - block, file_size)
+
+
 def cdr_bytes(names: Sequence[str], offset, comp, uncomp, hashes, method) -> bytes:
     """Central directory record for the given entries (zpack_write_cdr_memory, zpack_write.c:687-711)."""
     n = len(names)
