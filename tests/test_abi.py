@@ -36,6 +36,28 @@ def test_descriptor_layouts_are_64_bytes():
     assert zlib.Entry.fields["hash"][1] == 40 and zlib.Entry.fields["method"][1] == 48
 
 
+def test_header_structs_match_the_python_records(tmp_path):
+    """include/zpack_b200.h compiled as plain C: size and field offsets of every record equal the numpy dtypes of the binding."""
+    import subprocess
+    recs = {"zpb_entry": zlib.Entry, "zpb_file": zlib.File, "zpb_block": zlib.Block, "zpb_arc_entry": zlib.ArcEntry}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "zpack_b200.h"', 'int main(void) {']
+    for name, dt in recs.items():
+        lines.append(f'printf("{name} __sizeof %zu\\n", sizeof({name}));')
+        for f in dt.names:
+            lines.append(f'printf("{name} {f} %zu\\n", offsetof({name}, {f}));')
+    lines += ['return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    got = {tuple(l.split()[:2]): int(l.split()[2]) for l in out if l}
+    for name, dt in recs.items():
+        assert got[(name, "__sizeof")] == dt.itemsize, name
+        for f in dt.names:
+            assert got[(name, f)] == dt.fields[f][1], (name, f)
+
+
 def test_no_gpu_means_loud_failure():
     """No CPU fallback: without a device the context constructor raises instead of degrading."""
     import torch
