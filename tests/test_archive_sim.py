@@ -234,3 +234,29 @@ def test_open_random_directories(sim):
         d2 = container.directory_from_table(out, body, len(arch))      # the Python view of a device-side open
         assert d2.names == d.names and d2.cdr_offset == d.cdr_offset and d2.file_size == d.file_size
         assert np.array_equal(d2.entries(), d.entries())
+
+
+def test_build_is_byte_identical_to_the_reference_writer(sim, oracle):
+    """Stored (method NONE) files: the archive the kernels assemble from the raw files + their XXH3-64 digests is, byte for byte,
+    the archive the unmodified reference's zpack_write_archive produces for the same files."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not present")
+    rng = np.random.default_rng(41)
+    sizes = [0, 1, 17, 4096, 70001, 5, 131072, 33]
+    names = [f"dir{i % 3}/file_{i:03d}.dat" for i in range(len(sizes))]
+    bufs = [rng.integers(0, 256, s, dtype=np.uint8) for s in sizes]
+    ref = oracle.write_archive_ref(names, bufs, 0, 0)
+    e = np.zeros(len(sizes), ArcEntry)
+    pos = npos = 0
+    for i, b in enumerate(bufs):
+        e[i]["src_off"], e[i]["comp_size"], e[i]["uncomp_size"], e[i]["hash"], e[i]["method"] = pos, len(b), len(b), oracle.xxh3_port(b), 0
+        e[i]["name_off"], e[i]["name_len"] = npos, len(names[i])
+        pos += len(b) + 11
+        npos += len(names[i])
+    src, keep = aligned(pos + 16)
+    for r, b in zip(e, bufs):
+        src[int(r["src_off"]):int(r["src_off"]) + len(b)] = b
+    blob = np.frombuffer("".join(names).encode(), np.uint8).copy()
+    for seed in (1, 6):
+        out = sim_build(sim, e.copy(), src, blob, seed=seed)
+        assert len(out) == len(ref) and np.array_equal(out, ref), seed

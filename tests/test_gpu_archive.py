@@ -311,3 +311,43 @@ def test_empty_archive_and_empty_entries(gpu_ctx, oracle):
     res, eo, nb = gpu_ctx.archive_open_device(d_arch, size)
     assert res == 0 and list(eo["name_len"]) == [1, 0, 3] and list(eo["hash"]) == [7, 8, 9]
     gpu_ctx.copy_entries_device(d_arch, size, d_arch, size, np.zeros(0, ArcEntry))      # nothing to do is not an error
+
+
+def test_build_is_byte_identical_to_the_reference_writer_and_open_equals_its_reader(gpu_ctx, oracle):
+    """Stored files + their XXH3-64 digests (computed on the GPU): zpb_archive_build_device writes, byte for byte, the archive
+    the unmodified reference's zpack_write_archive writes; zpb_archive_open_device returns the unmodified reader's entries."""
+    import torch
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not present")
+    rng = np.random.default_rng(41)
+    sizes = [0, 1, 17, 4096, 70001, 5, 131072, 33, 300000]
+    names = [f"dir{i % 3}/file_{i:03d}.dat" for i in range(len(sizes))]
+    bufs = [rng.integers(0, 256, s, dtype=np.uint8) for s in sizes]
+    ref = oracle.write_archive_ref(names, bufs, 0, 0)
+    e = np.zeros(len(sizes), ArcEntry)
+    pos = npos = 0
+    for i, b in enumerate(bufs):
+        e[i]["src_off"], e[i]["comp_size"], e[i]["uncomp_size"], e[i]["method"] = pos, len(b), len(b), 0
+        e[i]["name_off"], e[i]["name_len"] = npos, len(names[i])
+        pos += (len(b) + 15) & ~15
+        npos += len(names[i])
+    src = np.zeros(pos + 16, np.uint8)
+    for r, b in zip(e, bufs):
+        src[int(r["src_off"]):int(r["src_off"]) + len(b)] = b
+    d_src = dev(src)
+    e["hash"] = gpu_ctx.xxh3_device(d_src, e["src_off"], e["comp_size"])
+    blob = np.frombuffer("".join(names).encode(), np.uint8)
+    d_arch = torch.zeros(len(ref) + 16, dtype=torch.uint8, device="cuda")
+    size = gpu_ctx.archive_build_device(d_src, len(src), e, blob, d_arch, len(ref) + 16)
+    assert size == len(ref) and np.array_equal(d_arch.cpu().numpy()[:size], ref)
+    res, eo, nb = gpu_ctx.archive_open_device(dev(ref), len(ref))
+    assert res == 0
+    rd = oracle.RefReader(ref)
+    assert rd.count == len(eo)
+    for i in range(rd.count):
+        r = rd.entry(i)
+        o, k = int(eo[i]["name_off"]), int(eo[i]["name_len"])
+        assert (int(r.offset), int(r.comp_size), int(r.uncomp_size), int(r.hash), int(r.comp_method)) == \
+               (int(eo[i]["offset"]), int(eo[i]["comp_size"]), int(eo[i]["uncomp_size"]), int(eo[i]["hash"]), int(eo[i]["method"]))
+        assert r.filename == bytes(nb[o:o + k])
+    rd.close()
